@@ -1,0 +1,352 @@
+#!/usr/bin/env python3
+"""bench.py -- WaveRange hot path on B200: raw-field compress/decompress GB/s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one compress followed by one decompress of the synthetic field of BASELINE.json
+configs[1] (512^3 float32 turbulence-like field, relative tolerance 1e-4).  `value` is raw-field
+GB/s (1 GB = 1e9 B), counting the field's native bytes once per direction:
+    value = 2 * ntot * 4 B / (t_compress + t_decompress),
+device-timed with CUDA events, field and coded stream resident in HBM.  `e2e` is the same metric
+through the host-buffer C-ABI calls (wrb_encode_host / wrb_decode_host, pinned host memory, H2D and
+D2H copies inside the timed region).  With N > 1 (torchrun) every rank codes its own field
+(independent fields shard with no data-path collective) -> weak scaling.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref, stock-style FMA
+build; single-threaded like the reference) on a bounded 256^3 sample of the same field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_FIELD = 512
+TOL = 1e-4
+SAMPLE = 256            # edge of the CPU-baseline sample cube
+METRIC = "raw-field compress+decompress throughput (device-timed)"
+UNIT = "GB/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synth_field(torch, n, seed, device, dtype, nm=48, expo=-5.0 / 6.0):
+    """Turbulence-like field: sum of nm plane waves with random integer wavevectors, random phases,
+    amplitude |k|^expo, evaluated in f64 on the device slab by slab through
+    separable complex tables, then rounded to `dtype`.  Deterministic for a given seed."""
+    rng = np.random.default_rng(seed)
+    kmax = 24
+    k = rng.integers(1, kmax + 1, size=(nm, 3)).astype(np.float64)
+    k *= rng.choice([-1.0, 1.0], size=(nm, 3))
+    ph = rng.uniform(0, 2 * np.pi, nm)
+    amp = (k ** 2).sum(1) ** (expo / 2.0 * 1.0)
+    x = np.arange(n, dtype=np.float64) / n
+    tab = [np.exp(2j * np.pi * np.outer(k[:, d], x)) for d in range(3)]          # (nm, n)
+    coef = torch.from_numpy(amp * np.exp(1j * ph)).to(device)
+    X = torch.from_numpy(tab[0]).to(device)
+    Y = torch.from_numpy(tab[1]).to(device)
+    Z = torch.from_numpy(tab[2]).to(device)
+    out = torch.empty((n, n, n), dtype=dtype, device=device)
+    slab = 16
+    for z0 in range(0, n, slab):
+        zc = Z[:, z0:z0 + slab] * coef[:, None]                                  # (nm, slab)
+        yz = torch.einsum("mz,my->mzy", zc, Y)                                   # (nm, slab, n)
+        f = torch.einsum("mzy,mx->zyx", yz, X).imag
+        out[z0:z0 + slab] = f.to(dtype)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile(prefix="wrb_clocks_", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [s.strip() for s in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def reference_lib():
+    from oracle.binding import Reference, Restatement
+    if Reference.available("fma"):
+        return Reference("fma"), "reference"
+    if Reference.available("strict"):
+        return Reference("strict"), "reference"
+    return Restatement(), "port"
+
+
+def cpu_time_sample(sample_f64, tol):
+    """encode+decode of the sample on one host core with the reference's own code; returns seconds"""
+    lib, kind = reference_lib()
+    t0 = time.perf_counter()
+    enc = lib.encode(sample_f64, tol)
+    t1 = time.perf_counter()
+    lib.decode(sample_f64.shape, enc["header"], enc["data"])
+    t2 = time.perf_counter()
+    return kind, t1 - t0, t2 - t1, enc["header"]
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    n = N_FIELD if dev == "cuda" else SAMPLE
+    fld = synth_field(torch, n, 1234, dev, torch.float32)
+    sample = fld[:SAMPLE, :SAMPLE, :SAMPLE].contiguous().cpu().numpy().astype(np.float64)
+    del fld
+    times = []
+    kind = "port"
+    for it in range(args.warmup + args.steps):
+        kind, te, td, h = cpu_time_sample(sample, TOL)
+        if it >= args.warmup:
+            times.append((te, td))
+    te = statistics.mean(t[0] for t in times)
+    td = statistics.mean(t[1] for t in times)
+    nbytes = sample.size * 4
+    val = 2 * nbytes / (te + td) / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": (te + td) * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "512^3 float32 turbulence-like field, tol 1e-4 (BASELINE.json configs[1])",
+                       "sample": "%d^3 corner sub-cube of the same field" % SAMPLE},
+            "compress_gbs": nbytes / te / 1e9, "decompress_gbs": nbytes / td / 1e9,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind,
+                             "sample": "%d^3 f32-valued sub-cube, encoding_wrap+decoding_wrap in process, 1 thread "
+                                       "(the reference is single-threaded); host has %d cores" % (SAMPLE, os.cpu_count())},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from waverange_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    n = N_FIELD
+    nz = ny = nx = n
+    ntot = n ** 3
+    field = synth_field(torch, n, 1234 + rank, dev, torch.float32)
+    nbytes = ntot * 4
+
+    stream = torch.cuda.current_stream()
+    codec = api.Codec(device=local_rank, stream=stream.cuda_stream)
+    codec.set_timing(True)
+    _, cap = api.setup_wr(nx, ny, nz)
+    cap = min(cap, ntot * 5 + (1 << 20))          # f32 field at tol 1e-4 codes to < 2 B/pt; keep HBM use modest
+    blob = torch.empty(cap + 64, dtype=torch.uint8, device=dev)
+    recon = torch.empty(ntot, dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    enc_ms, dec_ms, stage_enc, stage_dec = [], [], [], []
+    h = None
+    # ---- device-resident arm ----------------------------------------------------------------
+    for it in range(args.warmup):
+        h = codec.encode_device(field.data_ptr(), api.F32, nx, ny, nz, TOL, blob.data_ptr(), cap)
+        codec.decode_device(recon.data_ptr(), api.F32, nx, ny, nz, h, blob.data_ptr())
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = codec.launch_count()
+    t_wall0 = time.perf_counter()
+    tot_ev0 = torch.cuda.Event(enable_timing=True)
+    tot_ev1 = torch.cuda.Event(enable_timing=True)
+    tot_ev0.record(stream)
+    for it in range(args.steps):
+        ev[0].record(stream)
+        h = codec.encode_device(field.data_ptr(), api.F32, nx, ny, nz, TOL, blob.data_ptr(), cap)
+        se = codec.stage_ms()
+        ev[1].record(stream)
+        codec.decode_device(recon.data_ptr(), api.F32, nx, ny, nz, h, blob.data_ptr())
+        sd = codec.stage_ms()
+        ev[2].record(stream)
+        torch.cuda.synchronize()
+        enc_ms.append(ev[0].elapsed_time(ev[1])); dec_ms.append(ev[1].elapsed_time(ev[2]))
+        stage_enc.append(se); stage_dec.append(sd)
+    tot_ev1.record(stream)
+    barrier()
+    launches = codec.launch_count() - launches0
+    step_ms = tot_ev0.elapsed_time(tot_ev1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3 / args.steps
+
+    # correctness guard inside the bench: the reconstruction meets the requested tolerance
+    err = (recon.view(n, n, n).double() - field.double()).abs().max().item()
+    amax = field.double().abs().max().item()
+    assert err <= TOL * amax * 1.0000001, "reconstruction error %.3e exceeds tolerance" % (err / amax)
+
+    # ---- end-to-end arm: host buffers through the C ABI (pinned memory, copies timed) ---------
+    h_field = torch.empty((n, n, n), dtype=torch.float32, pin_memory=True)
+    h_field.copy_(field)
+    h_blob = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+    h_rec = torch.empty((n, n, n), dtype=torch.float32, pin_memory=True)
+    np_field, np_blob, np_rec = h_field.numpy(), h_blob.numpy(), h_rec.numpy()
+    e2e_ms = []
+    for it in range(max(1, min(args.warmup, 2)) + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        hh, data = codec.encode_host(np_field, TOL, out=np_blob)
+        codec.decode_host((n, n, n), hh, data, out=np_rec)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if it >= max(1, min(args.warmup, 2)):
+            e2e_ms.append((t1 - t0) * 1e3)
+    e2e_step = statistics.mean(e2e_ms)
+    assert np.array_equal(np_rec.ravel()[:4096], recon[:4096].cpu().numpy())
+
+    # ---- max over ranks ------------------------------------------------------------------------
+    vals = torch.tensor([step_ms, statistics.mean(enc_ms), statistics.mean(dec_ms), e2e_step], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    step_ms, enc_mean, dec_mean, e2e_step = [float(v) for v in vals.tolist()]
+    if rank != 0:
+        return
+
+    hbm, peak_src = peaks()
+    nlay = int(h.nlay)
+    se = [statistics.mean(s[i] for s in stage_enc) for i in range(4)]
+    sd = [statistics.mean(s[i] for s in stage_dec) for i in range(4)]
+    a_c = ntot * (4 + 8 + 9 * nlay)                    # algorithmic bytes, SURVEY.md section 8d
+    t_wq = (se[0] + se[1]) * 1e-3
+    achieved = a_c / t_wq / 1e9
+    value = world * 2 * nbytes / (step_ms * 1e-3) / 1e9
+    e2e_val = world * 2 * nbytes / (e2e_step * 1e-3) / 1e9
+
+    # CPU baseline on a bounded sample of the same workload (rank 0, N = 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        sample = field[:SAMPLE, :SAMPLE, :SAMPLE].contiguous().cpu().numpy().astype(np.float64)
+        kind, te, td, _ = cpu_time_sample(sample, TOL)
+        cpu = {"value": 2 * sample.size * 4 / (te + td) / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": "%d^3 sub-cube of the same field, encoding_wrap %.2f s + decoding_wrap %.2f s, 1 thread "
+                         "(reference is single-threaded); host has %d cores" % (SAMPLE, te, td, os.cpu_count())}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "512^3 float32 turbulence-like field, tol 1e-4 (BASELINE.json configs[1])",
+                   "field_bytes": nbytes, "tolerance": TOL, "nlay": nlay, "ntot_enc": int(h.ntot_enc),
+                   "ratio_vs_f32": nbytes / max(1, int(h.ntot_enc)), "chunk_symbols": 59999,
+                   "fields": "%d independent field(s), one per GPU" % world,
+                   "l2": "working set (0.5 GB field + 2 GB scratch) exceeds the 126 MB L2; no explicit flush"},
+        "compress_gbs": world * nbytes / (enc_mean * 1e-3) / 1e9,
+        "decompress_gbs": world * nbytes / (dec_mean * 1e-3) / 1e9,
+        "rel_linf_error": err / amax,
+        "stages_ms": {"encode": dict(zip(["transform", "quantise", "range_encode", "assemble"], se)),
+                      "decode": dict(zip(["parse", "range_decode", "dequantise", "inverse_transform"], sd)),
+                      "encode_total": enc_mean, "decode_total": dec_mean},
+        "roofline": {"bound": "hbm", "scope": "forward wavelet + quantise kernels of one compress (stage events)",
+                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                     "algorithmic_bytes": a_c, "peak_source": peak_src},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes + int(h.ntot_enc),
+                "d2h_bytes_per_step": nbytes + int(h.ntot_enc), "ms_per_step": e2e_step,
+                "api": "wrb_encode_host + wrb_decode_host (f32 pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "host_wall_ms_per_step": wall_ms,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,129 @@
+/*
+ * waverange_b200.h -- C ABI of the B200-native WaveRange compress/decompress hot path.
+ *
+ * One shared library, libwaverange_b200.so, exports two groups of entry points:
+ *
+ *  (1) the reference's own library interface, unchanged, so that the reference front-ends
+ *      (src/generic, src/flusi, src/mssg) and user Fortran/C++ codes link against it instead of
+ *      libwaverange.{a,so}:  encoding_wrap / decoding_wrap / setup_wr and the Fortran twins
+ *      (declared in include/waverange.h; reference src/core/wrappers.h:53,70,75,95,111,119);
+ *
+ *  (2) the wrb_* functions below: a codec handle that owns device scratch, device-pointer
+ *      encode/decode (what the benchmarks time), host-pointer encode/decode (what group (1) is
+ *      built on) and stage-level entry points used by the parity tests.
+ *
+ * Plain C types only; every pointer named d_* is a CUDA device pointer, every other pointer is
+ * host memory.  All functions return 0 on success, a negative WRB_E_* code otherwise;
+ * wrb_last_error() gives the text.  There is no CPU fallback: without a CUDA device every call
+ * that needs one fails with WRB_E_CUDA.
+ */
+#ifndef WAVERANGE_B200_H
+#define WAVERANGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WRB_NLAYMAX 8          /* reference src/core/defs.h:38  NLAYMAX   */
+#define WRB_BLOCKSIZE 60000    /* reference src/core/defs.h:36  BLOCKSIZE */
+#define WRB_WAV_LVL 4          /* reference src/core/defs.h:50  WAV_LVL   */
+
+#define WRB_F64 0
+#define WRB_F32 1
+
+#define WRB_E_ARG (-1)
+#define WRB_E_CUDA (-2)
+#define WRB_E_OVERFLOW (-3)    /* encoded data does not fit (reference wrappers.cpp:422-426) */
+#define WRB_E_FORMAT (-4)      /* malformed container / stream */
+#define WRB_E_NOMEM (-5)
+
+/* Coding metadata of one field: exactly the scalar/vector outputs of encoding_wrap()
+ * (reference src/core/wrappers.h:35-52). */
+typedef struct wrb_header {
+    double tolabs, midval, halfspanval;
+    unsigned char wlev, nlay;
+    unsigned long ntot_enc;
+    double deps_vec[WRB_NLAYMAX];
+    double minval_vec[WRB_NLAYMAX];
+    unsigned long len_enc_vec[WRB_NLAYMAX];
+} wrb_header;
+
+typedef struct wrb_codec wrb_codec;
+
+/* ---- handle -------------------------------------------------------------------------------- */
+int wrb_create(wrb_codec** out, int device);
+void wrb_destroy(wrb_codec* c);
+const char* wrb_last_error(const wrb_codec* c);
+/* CUDA stream (cudaStream_t) all work of this handle is launched on; NULL = legacy default stream */
+int wrb_set_stream(wrb_codec* c, void* cuda_stream);
+/* Chunking of each layer's symbol sequence for the parallel range coder.
+ *   blocks >= 1: chunk length = blocks*60000 - 1 symbols (default 1).  Each layer is stored as a
+ *                "WRCK" container: 32-byte header, u32 byte length per chunk, then the chunk
+ *                streams; every chunk stream is byte-identical to the reference's range_encode()
+ *                (wrappers.cpp:68-149) of that symbol sub-array.
+ *   blocks == 0: one stream per layer, byte-identical to the reference's encoding_wrap() output
+ *                (readable by the stock wrdec); serial on the GPU, for interoperability only. */
+int wrb_set_chunk_blocks(wrb_codec* c, int blocks);
+/* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
+unsigned long long wrb_launch_count(const wrb_codec* c);
+/* Release cached device scratch (it is otherwise kept and grown on demand). */
+int wrb_trim(wrb_codec* c);
+
+/* ---- sizes: replaces setup_wr() (reference wrappers.cpp:531-541) ------------------------------ */
+void wrb_setup(int nx, int ny, int nz, unsigned char* nlaymax, unsigned long* ntot_enc_max);
+
+/* ---- device-resident path (inputs/outputs already in HBM) ----------------------------------- */
+/* Compress: replaces encoding_wrap() (reference wrappers.cpp:228-452) for a field resident on the
+ * device as f64 or f32 (f32 is widened on the fly exactly like gen_aux.cpp:305-309 does on the
+ * host).  d_field is NOT modified.  d_data_enc (capacity cap bytes, >= wrb_setup's ntot_enc_max
+ * recommended) receives the encoded layers back to back; hdr (host) receives the metadata.
+ * The call returns after the stream has been synchronised. */
+int wrb_encode_device(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag,
+                      double tolrel, wrb_header* hdr, unsigned char* d_data_enc, unsigned long cap);
+/* Decompress: replaces decoding_wrap() (reference wrappers.cpp:456-527).  d_data_enc holds
+ * hdr->ntot_enc bytes followed by at least 16 readable bytes.  d_field_out is f64 or f32. */
+int wrb_decode_device(wrb_codec* c, void* d_field_out, int dtype, int nx, int ny, int nz, const wrb_header* hdr,
+                      const unsigned char* d_data_enc);
+
+/* ---- host-buffer path (copies inside) ------------------------------------------------------- */
+int wrb_encode_host(wrb_codec* c, const void* field, int dtype, int nx, int ny, int nz, int wtflag, double tolrel,
+                    wrb_header* hdr, unsigned char* data_enc, unsigned long cap);
+int wrb_decode_host(wrb_codec* c, void* field_out, int dtype, int nx, int ny, int nz, const wrb_header* hdr,
+                    const unsigned char* data_enc);
+
+/* ---- stage-level entry points (parity tests, profiling) -------------------------------------- */
+/* In-place 3-D CDF 9/7 transform of a device f64 array, sign of lvl selects direction:
+ * replaces waveletcdf97_3d() (reference src/waveletcdf97_3d/waveletcdf97_3d.h:39). */
+int wrb_wavelet3d_device(wrb_codec* c, double* d_x, int nx, int ny, int nz, int lvl);
+/* Transform + quantise only (no coder).  Outputs, all optional (NULL to skip):
+ *   d_coef  ntot doubles: wavelet coefficients in array order;
+ *   d_sym   WRB_NLAYMAX*ntot bytes, layer-major, array order: the symbols the reference holds in
+ *           fld_q for each layer (wrappers.cpp:384-389);
+ *   hdr     tolabs, midval, halfspanval, wlev, nlay, deps_vec, minval_vec (lengths are zero). */
+int wrb_quantise_device(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag,
+                        double tolrel, wrb_header* hdr, double* d_coef, unsigned char* d_sym);
+/* Code n symbols as ceil(n/chunk_len) independent streams (chunk_len == 0: one stream).
+ * d_out receives the streams back to back, lens (host, u64 per chunk) their byte lengths. */
+int wrb_range_encode_device(wrb_codec* c, const unsigned char* d_sym, unsigned long n, unsigned long chunk_len,
+                            unsigned char* d_out, unsigned long cap, unsigned long* lens, unsigned long* total);
+/* Inverse of the above: streams back to back in d_in, lens from the encoder. */
+int wrb_range_decode_device(wrb_codec* c, const unsigned char* d_in, const unsigned long* lens, unsigned long n,
+                            unsigned long chunk_len, unsigned char* d_sym);
+/* Physical -> wavelet-space index map: replaces ind_p2w_3d()
+ * (reference src/waveletcdf97_3d/waveletcdf97_3d.c:473-553).  Host arithmetic. */
+void wrb_ind_p2w_3d(int lvlin, int n1, int n2, int n3, int i1, int i2, int i3, int* lvl, int* o1, int* o2, int* o3);
+
+/* Device time, in milliseconds, of the stages of the last wrb_encode_device / wrb_decode_device
+ * call when timing is enabled with wrb_set_timing(c, 1) (CUDA events on the handle's stream).
+ * encode: [0] transform, [1] quantise layers, [2] range coder, [3] container assembly
+ * decode: [0] parse, [1] range decoder, [2] dequantise, [3] inverse transform */
+int wrb_set_timing(wrb_codec* c, int on);
+int wrb_last_stage_ms(const wrb_codec* c, float ms[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAVERANGE_B200_H */

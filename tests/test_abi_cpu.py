@@ -1,0 +1,67 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol the public
+headers declare, and its host-only entry points agree with the oracle.  No compute call needs a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    txt = re.sub(r"//[^\n]*", "", txt)
+    names = set(re.findall(r"\b(wrb_[a-z0-9_]+|encoding_wrap(?:_f)?|decoding_wrap(?:_f)?|setup_wr(?:_f)?)\s*\(", txt))
+    return {n for n in names if n not in ("wrb_codec", "wrb_header")}
+
+
+def test_library_exports_every_declared_symbol(product_lib):
+    lib = C.CDLL(product_lib)
+    want = declared_functions("waverange_b200.h") | declared_functions("waverange.h")
+    assert len(want) >= 25
+    missing = [n for n in sorted(want) if not hasattr(lib, n)]
+    assert not missing, missing
+    from waverange_b200 import api
+    assert want == set(api.EXPORTS)
+
+
+def test_setup_wr_matches_reference_formula(product_lib, oracle):
+    from waverange_b200 import api
+    for n in [(1, 1, 1), (10, 10, 10), (256, 256, 256), (2048, 2048, 2048), (7, 11, 13)]:
+        nlaymax, cap = api.setup_wr(*n)
+        ntot = n[0] * n[1] * n[2]
+        assert nlaymax == 8 and cap == 8 * max(1024, ntot)     # wrappers.cpp:531-541
+
+
+def test_ind_p2w_matches_golden(product_lib, golden):
+    from waverange_b200 import api
+    for row in golden["p2w"][::5]:
+        n, i, want = row[:3], row[3:6], row[6:]
+        assert api.ind_p2w_3d(4, tuple(int(v) for v in n), tuple(int(v) for v in i)) == tuple(int(v) for v in want)
+
+
+def test_no_cpu_fallback(product_lib):
+    """Without a CUDA device the product refuses to run instead of silently using a CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from waverange_b200 import api
+    with pytest.raises(api.WaveRangeError):
+        api.Codec(device=0)
+
+
+def test_product_does_not_reference_oracle():
+    """The oracle is test infrastructure: nothing under waverange_b200/ may import or link it."""
+    bad = []
+    for d, _, files in os.walk(os.path.join(ROOT, "waverange_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(d, f), errors="ignore").read()
+                if re.search(r"\boracle\b|wr_oracle|_ref/", txt) and f != "api.py":
+                    bad.append(f)
+                if f == "api.py" and re.search(r"import\s+oracle|from\s+oracle|wr_oracle", txt):
+                    bad.append(f)
+    assert not bad, bad

@@ -1,0 +1,256 @@
+"""GPU parity tests: every stage of the CUDA path, called through the C ABI, against the oracle
+(oracle/wr_oracle.c, pinned to the reference) and the golden vectors.  Bit-exact everywhere:
+wavelet coefficients (0 ULP), header doubles, symbols, chunk bytes, reconstructed field."""
+import numpy as np
+import pytest
+
+from util import SYM_GENS, bits_equal, sha
+
+pytestmark = pytest.mark.gpu
+
+F64, F32 = 0, 1
+L1 = 59999
+
+
+def dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+WV_SHAPES = [(1, 1, 8), (1, 1, 5), (1, 1, 16), (1, 1, 2), (1, 1, 3), (2, 2, 2), (3, 4, 5), (7, 1, 9), (1, 6, 1),
+             (17, 9, 33), (16, 16, 16), (5, 18, 31)]
+
+
+@pytest.mark.parametrize("shape", WV_SHAPES)
+@pytest.mark.parametrize("lvl", [1, 4])
+def test_wavelet_golden(codec, torch_cuda, golden, shape, lvl):
+    key = "wv_%dx%dx%d" % shape
+    x = dev(torch_cuda, golden[key + "_in"])
+    nz, ny, nx = shape
+    codec.wavelet3d_device(x.data_ptr(), nx, ny, nz, lvl)
+    assert bits_equal(x.cpu().numpy(), golden[key + "_fwd%d" % lvl])
+    codec.wavelet3d_device(x.data_ptr(), nx, ny, nz, -lvl)
+    assert bits_equal(x.cpu().numpy(), golden[key + "_inv%d" % lvl])
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 64), (33, 47, 129), (1, 200, 300), (128, 96, 80), (70, 1, 513), (9, 9, 1025)])
+def test_wavelet_vs_oracle(codec, torch_cuda, oracle, shape):
+    rng = np.random.default_rng(sum(shape))
+    a = rng.standard_normal(shape) * 3
+    nz, ny, nx = shape
+    for lvl in (1, 3, 4):
+        x = dev(torch_cuda, a)
+        codec.wavelet3d_device(x.data_ptr(), nx, ny, nz, lvl)
+        w = oracle.wavelet3d(a, lvl)
+        assert bits_equal(x.cpu().numpy(), w), "forward lvl %d" % lvl
+        codec.wavelet3d_device(x.data_ptr(), nx, ny, nz, -lvl)
+        assert bits_equal(x.cpu().numpy(), oracle.wavelet3d(w, -lvl)), "inverse lvl %d" % lvl
+
+
+@pytest.mark.parametrize("name,n", [("hash", 1), ("hash", 5), ("hash", 255), ("hash", 59999), ("hash", 60000),
+                                    ("hash", 60001), ("hash", 119999), ("hash", 120000), ("lcg", 150001),
+                                    ("peaked", 70000), ("zeros", 10), ("zeros", 60000)])
+def test_range_coder_single_stream_golden(codec, torch_cuda, golden, name, n):
+    """chunk_len == 0: the whole array is one stream == the reference's range_encode()."""
+    sym = SYM_GENS[name](n)
+    d_sym = dev(torch_cuda, sym)
+    out = torch_cuda.zeros(2 * n + 4096, dtype=torch_cuda.uint8, device="cuda")
+    lens, total = codec.range_encode_device(d_sym.data_ptr(), n, 0, out.data_ptr(), out.numel())
+    s = out[:total].cpu().numpy()
+    key = "rc_%s_%d" % (name, n)
+    assert lens == [total] and total == int(golden[key + "_len"][0])
+    assert np.array_equal(sha(s), golden[key + "_sha"])
+    back = torch_cuda.zeros(n, dtype=torch_cuda.uint8, device="cuda")
+    codec.range_decode_device(out.data_ptr(), lens, n, 0, back.data_ptr())
+    assert np.array_equal(back.cpu().numpy(), sym)
+
+
+@pytest.mark.parametrize("n,chunk", [(300000, L1), (300000, 119999), (59999 * 40 + 17, L1), (1000, 300), (120000, 60000),
+                                     (59999 * 33, L1)])
+@pytest.mark.parametrize("kind", ["uniform", "peaked", "runs"])
+def test_range_coder_chunks_vs_oracle(codec, torch_cuda, oracle, n, chunk, kind):
+    rng = np.random.default_rng(n + chunk)
+    if kind == "uniform":
+        sym = rng.integers(0, 256, n, dtype=np.uint8)
+    elif kind == "peaked":
+        sym = np.clip(np.rint(127.5 + 0.6 * rng.standard_normal(n)), 0, 255).astype(np.uint8)
+    else:
+        sym = np.repeat(rng.integers(0, 256, n // 97 + 1, dtype=np.uint8), 97)[:n]
+    d_sym = dev(torch_cuda, sym)
+    out = torch_cuda.zeros(2 * n + 4096 * (n // chunk + 2), dtype=torch_cuda.uint8, device="cuda")
+    lens, total = codec.range_encode_device(d_sym.data_ptr(), n, chunk, out.data_ptr(), out.numel())
+    blob = out[:total].cpu().numpy()
+    off = 0
+    for c, ln in enumerate(lens):
+        want = oracle.range_encode(sym[c * chunk:(c + 1) * chunk])
+        assert ln == len(want), "chunk %d length" % c
+        assert np.array_equal(blob[off:off + ln], want), "chunk %d bytes" % c
+        off += ln
+    assert off == total
+    back = torch_cuda.zeros(n, dtype=torch_cuda.uint8, device="cuda")
+    codec.range_decode_device(out.data_ptr(), lens, n, chunk, back.data_ptr())
+    assert np.array_equal(back.cpu().numpy(), sym)
+
+
+def test_chunk_streams_accepted_by_reference_decoder(codec, torch_cuda, ref):
+    """every chunk is a byte-valid stream for the reference's own range_decode()"""
+    n = 200000
+    sym = SYM_GENS["lcg"](n)
+    d_sym = dev(torch_cuda, sym)
+    out = torch_cuda.zeros(2 * n + 65536, dtype=torch_cuda.uint8, device="cuda")
+    lens, total = codec.range_encode_device(d_sym.data_ptr(), n, L1, out.data_ptr(), out.numel())
+    blob = out[:total].cpu().numpy()
+    off = 0
+    for c, ln in enumerate(lens):
+        part = sym[c * L1:(c + 1) * L1]
+        assert np.array_equal(ref.range_decode(blob[off:off + ln], part.size), part)
+        assert np.array_equal(ref.range_encode(part), blob[off:off + ln])
+        off += ln
+
+
+def quantise(codec, torch, f, tol, wtflag=1, dtype=F64):
+    nz, ny, nx = f.shape
+    d_f = dev(torch, f.astype(np.float32) if dtype == F32 else f)
+    coef = torch.zeros(f.size, dtype=torch.float64, device="cuda")
+    sym = torch.zeros(8 * f.size, dtype=torch.uint8, device="cuda")
+    h = codec.quantise_device(d_f.data_ptr(), dtype, nx, ny, nz, tol, wtflag, coef.data_ptr(), sym.data_ptr())
+    return h, coef.cpu().numpy(), sym.cpu().numpy().reshape(8, f.size)[:h.nlay]
+
+
+@pytest.mark.parametrize("shape,tol,wt", [((40, 40, 40), 1e-3, 1), ((20, 24, 32), 1e-6, 1), ((9, 30, 17), 1e-10, 1),
+                                          ((16, 16, 16), 1e-4, 0), ((64, 64, 64), 1e-5, 1), ((48, 50, 77), 1e-16, 1),
+                                          ((96, 96, 96), 1e-8, 1)])
+def test_quantiser_vs_oracle(codec, torch_cuda, oracle, shape, tol, wt):
+    f = oracle.probe_field(shape, seed=99 + shape[0], nm=16)
+    want = oracle.encode(f, tol, wtflag=wt, want_symbols=True)
+    hw = want["header"]
+    h, coef, sym = quantise(codec, torch_cuda, f, tol, wt)
+    assert bits_equal(coef.reshape(shape), oracle.wavelet3d(f, 4 if wt else 0))
+    assert (h.wlev, h.nlay) == (hw.wlev, hw.nlay)
+    assert bits_equal(np.array([h.tolabs, h.midval, h.halfspanval]), np.array([hw.tolabs, hw.midval, hw.halfspan]))
+    assert bits_equal(np.array(list(h.deps_vec)[:h.nlay]), np.array(list(hw.deps)[:hw.nlay]))
+    assert bits_equal(np.array(list(h.minval_vec)[:h.nlay]), np.array(list(hw.minval)[:hw.nlay]))
+    assert np.array_equal(sym, want["symbols"])
+
+
+def test_f32_input_is_widened_like_the_reference_front_end(codec, torch_cuda, oracle):
+    # generic front-end widens element by element on the host (gen_aux.cpp:305-309)
+    f32 = oracle.probe_field((48, 48, 48), seed=3).astype(np.float32)
+    want = oracle.encode(f32.astype(np.float64), 1e-4, want_symbols=True)
+    h, coef, sym = quantise(codec, torch_cuda, f32, 1e-4, 1, dtype=F32)
+    assert h.nlay == want["header"].nlay and np.array_equal(sym, want["symbols"])
+    assert bits_equal(np.array(list(h.deps_vec)[:h.nlay]), np.array(list(want["header"].deps)[:h.nlay]))
+
+
+def encode_dev(codec, torch, f, tol, wt=1, dtype=F64):
+    from waverange_b200 import api
+    nz, ny, nx = f.shape
+    d_f = dev(torch, f.astype(np.float32) if dtype == F32 else f)
+    _, cap = api.setup_wr(nx, ny, nz)
+    out = torch.zeros(cap + 64, dtype=torch.uint8, device="cuda")
+    h = codec.encode_device(d_f.data_ptr(), dtype, nx, ny, nz, tol, out.data_ptr(), cap, wt)
+    return h, out
+
+
+@pytest.mark.parametrize("shape,tol", [((64, 64, 64), 1e-5), ((40, 50, 60), 1e-3), ((100, 100, 100), 1e-8),
+                                       ((30, 1, 500), 1e-6), ((128, 128, 96), 1e-12)])
+def test_encode_chunks_bit_exact_and_decode(codec, torch_cuda, oracle, shape, tol):
+    from waverange_b200 import api
+    f = oracle.probe_field(shape, seed=7 + shape[2], nm=20)
+    h, out = encode_dev(codec, torch_cuda, f, tol)
+    want = oracle.encode(f, tol, chunk_len=L1, want_symbols=True)
+    hw = want["header"]
+    assert h.nlay == hw.nlay
+    blob = out[:h.ntot_enc].cpu().numpy()
+    off, woff = 0, 0
+    for l in range(h.nlay):
+        layer = blob[off:off + h.len_enc_vec[l]]
+        chunk_len, streams = api.parse_container(layer)
+        assert chunk_len == L1 and len(streams) == want["chunk_lens"].shape[1]
+        for c, s in enumerate(streams):
+            n = int(want["chunk_lens"][l][c])
+            assert s == want["data"][woff:woff + n].tobytes(), "layer %d chunk %d" % (l, c)
+            woff += n
+        off += h.len_enc_vec[l]
+    # compression ratio within 1 % of the reference's whole-layer streams
+    whole = oracle.encode(f, tol)
+    assert h.ntot_enc <= 1.01 * whole["header"].ntot_enc
+    # decode on the GPU: bit-identical to the reference decoder's reconstruction
+    nz, ny, nx = shape
+    rec = torch_cuda.zeros(f.size, dtype=torch_cuda.float64, device="cuda")
+    codec.decode_device(rec.data_ptr(), F64, nx, ny, nz, h, out.data_ptr())
+    want_rec = oracle.decode(shape, whole["header"], whole["data"])
+    assert bits_equal(rec.cpu().numpy().reshape(shape), want_rec)
+    assert np.abs(want_rec - f).max() <= tol * np.abs(f).max()
+
+
+@pytest.mark.parametrize("key", ["e2e_a", "e2e_b", "e2e_c", "e2e_d"])
+def test_single_stream_mode_is_byte_identical_to_reference(codec, torch_cuda, golden, key):
+    """chunk_blocks = 0: data_enc, lengths and header doubles equal encoding_wrap() of the reference."""
+    f = golden[key + "_in"]
+    tol, wt = golden[key + "_tol"]
+    codec.set_chunk_blocks(0)
+    h, out = encode_dev(codec, torch_cuda, f, float(tol), int(wt))
+    assert [h.wlev, h.nlay, h.ntot_enc] == list(golden[key + "_int"])
+    assert bits_equal(np.array([h.tolabs, h.midval, h.halfspanval]), golden[key + "_scal"])
+    assert bits_equal(np.array(list(h.deps_vec)[:h.nlay]), golden[key + "_deps"])
+    assert bits_equal(np.array(list(h.minval_vec)[:h.nlay]), golden[key + "_minval"])
+    assert list(h.len_enc_vec)[:h.nlay] == list(golden[key + "_len"])
+    assert np.array_equal(out[:h.ntot_enc].cpu().numpy(), golden[key + "_data"])
+    nz, ny, nx = f.shape
+    rec = torch_cuda.zeros(f.size, dtype=torch_cuda.float64, device="cuda")
+    codec.decode_device(rec.data_ptr(), F64, nx, ny, nz, h, out.data_ptr())
+    assert np.array_equal(sha(rec.cpu().numpy()), golden[key + "_rec_sha"])
+
+
+def test_constant_field_trivial_exit(codec, torch_cuda, golden):
+    f = np.full((4, 5, 6), 3.25)
+    h, out = encode_dev(codec, torch_cuda, f, 1e-6)
+    assert [h.wlev, h.nlay, h.ntot_enc] == list(golden["e2e_const_int"])
+    assert bits_equal(np.array([h.tolabs, h.midval, h.halfspanval]), golden["e2e_const_scal"])
+    rec = torch_cuda.zeros(f.size, dtype=torch_cuda.float64, device="cuda")
+    codec.decode_device(rec.data_ptr(), F64, 6, 5, 4, h, out.data_ptr())
+    assert np.all(rec.cpu().numpy() == 3.25)
+
+
+def test_reference_entry_points_on_host_buffers(product_lib, torch_cuda, oracle):
+    """encoding_wrap / decoding_wrap with the reference's signatures (host arrays in, host arrays out)."""
+    from waverange_b200 import api
+    f = oracle.probe_field((50, 60, 70), seed=11)
+    h, data = api.encoding_wrap(f, 1e-6)
+    want = oracle.encode(f, 1e-6)
+    hw = want["header"]
+    assert (h.wlev, h.nlay) == (hw.wlev, hw.nlay)
+    assert bits_equal(np.array(list(h.deps_vec)), np.array(list(hw.deps)))
+    assert bits_equal(np.array(list(h.minval_vec)), np.array(list(hw.minval)))
+    rec = api.decoding_wrap(f.shape, h, data)
+    assert bits_equal(rec, oracle.decode(f.shape, hw, want["data"]))
+    assert np.abs(rec - f).max() <= 1e-6 * np.abs(f).max()
+
+
+def test_f32_roundtrip_host_api(codec, torch_cuda, oracle):
+    f = oracle.probe_field((64, 64, 64), seed=21).astype(np.float32)
+    h, data = codec.encode_host(f, 1e-4)
+    rec = codec.decode_host(f.shape, h, data, dtype=np.float32)
+    want = oracle.encode(f.astype(np.float64), 1e-4)
+    want_rec = oracle.decode(f.shape, want["header"], want["data"]).astype(np.float32)
+    assert bits_equal(rec, want_rec)
+    assert np.abs(rec.astype(np.float64) - f).max() <= 1e-4 * np.abs(f).max()
+
+
+def test_overflow_is_reported(codec, torch_cuda, oracle):
+    from waverange_b200 import api
+    f = np.random.default_rng(1).standard_normal((32, 32, 32))
+    d_f = dev(torch_cuda, f)
+    out = torch_cuda.zeros(4096, dtype=torch_cuda.uint8, device="cuda")
+    with pytest.raises(api.WaveRangeError):
+        codec.encode_device(d_f.data_ptr(), F64, 32, 32, 32, 1e-12, out.data_ptr(), 1000)
+
+
+def test_corrupt_container_is_rejected(codec, torch_cuda, oracle):
+    from waverange_b200 import api
+    f = oracle.probe_field((32, 32, 32), seed=2)
+    h, out = encode_dev(codec, torch_cuda, f, 1e-4)
+    out[0] = 0x55
+    rec = torch_cuda.zeros(f.size, dtype=torch_cuda.float64, device="cuda")
+    with pytest.raises(api.WaveRangeError):
+        codec.decode_device(rec.data_ptr(), F64, 32, 32, 32, h, out.data_ptr())

@@ -1,0 +1,122 @@
+"""CPU tests: the oracle restatement against the golden vectors produced by the unmodified
+reference (tests/golden/make_golden.py), and against oracle/_ref directly where it is present."""
+import numpy as np
+import pytest
+
+from util import SYM_GENS, bits_equal, sha
+
+RC_CASES = [("hash", n) for n in (1, 5, 255, 59999, 60000, 60001, 119999, 120000)] + \
+           [("lcg", 150001), ("peaked", 70000), ("zeros", 10), ("zeros", 60000)]
+WV_SHAPES = [(1, 1, 8), (1, 1, 5), (1, 1, 16), (1, 1, 2), (1, 1, 3), (2, 2, 2), (3, 4, 5), (7, 1, 9), (1, 6, 1),
+             (17, 9, 33), (16, 16, 16), (5, 18, 31)]
+E2E = ["e2e_a", "e2e_b", "e2e_c", "e2e_d"]
+
+
+@pytest.mark.parametrize("name,n", RC_CASES)
+def test_range_encode_golden(oracle, golden, name, n):
+    sym = SYM_GENS[name](n)
+    s = oracle.range_encode(sym)
+    key = "rc_%s_%d" % (name, n)
+    assert len(s) == int(golden[key + "_len"][0])
+    assert np.array_equal(sha(s), golden[key + "_sha"])
+    assert np.array_equal(s[:16], golden[key + "_head"]) and np.array_equal(s[-16:], golden[key + "_tail"])
+    dec, cnt = oracle.range_decode(s, n)
+    assert cnt == n and np.array_equal(dec, sym)
+
+
+def test_range_encode_empty_trailing_block(oracle):
+    # n % 60000 == 0 appends an empty block: 513 extra bytes (hard part 2)
+    a = len(oracle.range_encode(SYM_GENS["hash"](59999)))
+    b = len(oracle.range_encode(SYM_GENS["hash"](60000)))
+    assert b - a == 513
+
+
+@pytest.mark.parametrize("shape", WV_SHAPES)
+@pytest.mark.parametrize("lvl", [1, 4])
+def test_wavelet_golden(oracle, golden, shape, lvl):
+    key = "wv_%dx%dx%d" % shape
+    x = golden[key + "_in"]
+    w = oracle.wavelet3d(x, lvl)
+    assert bits_equal(w, golden[key + "_fwd%d" % lvl])
+    assert bits_equal(oracle.wavelet3d(w, -lvl), golden[key + "_inv%d" % lvl])
+
+
+def test_wavelet_survey_kat(oracle, golden):
+    # waveletcdf97_3d(8,1,1,1,{1..8})
+    w = oracle.wavelet3d(golden["wv_ramp8_in"], 1).ravel()
+    assert bits_equal(w, golden["wv_ramp8_fwd1"].ravel())
+    assert abs(w[0] - 1.8860525098649028) < 1e-15 and abs(w[7] - 0.61170892111963648) < 1e-15
+
+
+@pytest.mark.parametrize("key", E2E)
+def test_encode_decode_golden(oracle, golden, key):
+    f = golden[key + "_in"]
+    tol, wt = golden[key + "_tol"]
+    e = oracle.encode(f, float(tol), wtflag=int(wt))
+    h = e["header"]
+    assert [h.wlev, h.nlay, h.ntot_enc] == list(golden[key + "_int"])
+    assert bits_equal(np.array([h.tolabs, h.midval, h.halfspan]), golden[key + "_scal"])
+    assert bits_equal(np.array(list(h.deps)[:h.nlay]), golden[key + "_deps"])
+    assert bits_equal(np.array(list(h.minval)[:h.nlay]), golden[key + "_minval"])
+    assert list(h.len)[:h.nlay] == list(golden[key + "_len"])
+    assert np.array_equal(e["data"], golden[key + "_data"])
+    assert np.array_equal(sha(e["residual"]), golden[key + "_residual_sha"])
+    rec = oracle.decode(f.shape, h, e["data"])
+    assert np.array_equal(sha(rec), golden[key + "_rec_sha"])
+    # the reference's accuracy contract (examples/fortran/example_fort.f90:43-45): Linf error ~ tol*max|f|
+    assert np.abs(rec - f).max() <= float(tol) * np.abs(f).max()
+
+
+def test_constant_field_golden(oracle, golden):
+    e = oracle.encode(np.full((4, 5, 6), 3.25), 1e-6)
+    h = e["header"]
+    assert [h.wlev, h.nlay, h.ntot_enc] == list(golden["e2e_const_int"])
+    assert bits_equal(np.array([h.tolabs, h.midval, h.halfspan]), golden["e2e_const_scal"])
+    assert np.all(oracle.decode((4, 5, 6), h, e["data"]) == 3.25)
+
+
+def test_ind_p2w_golden(oracle, golden):
+    for row in golden["p2w"][::7]:
+        n, i, want = row[:3], row[3:6], row[6:]
+        assert oracle.ind_p2w(4, tuple(n), tuple(i)) == tuple(want)
+
+
+def test_chunked_streams_are_reference_streams(oracle, golden):
+    """A chunked encode is the per-chunk range_encode of the same symbols; decode agrees bit for bit."""
+    f = golden["e2e_b_in"]
+    L = 59999
+    whole = oracle.encode(f, 1e-3, want_symbols=True)
+    ch = oracle.encode(f, 1e-3, chunk_len=L, want_symbols=True)
+    assert np.array_equal(whole["symbols"], ch["symbols"])
+    off = 0
+    for l in range(ch["header"].nlay):
+        for c, n in enumerate(ch["chunk_lens"][l]):
+            want = oracle.range_encode(ch["symbols"][l][c * L:(c + 1) * L])
+            assert np.array_equal(ch["data"][off:off + n], want)
+            off += int(n)
+    rec = oracle.decode(f.shape, ch["header"], ch["data"], L, ch["chunk_lens"])
+    assert bits_equal(rec, oracle.decode(f.shape, whole["header"], whole["data"]))
+    # container overhead of chunking stays far below the 1 % ratio budget
+    assert ch["header"].ntot_enc <= 1.01 * whole["header"].ntot_enc
+
+
+# ---- direct comparison with the compiled reference (only where oracle/_ref is present) --------
+def test_restatement_vs_reference_random(oracle, ref):
+    rng = np.random.default_rng(5)
+    for shp in [(6, 7, 8), (1, 1, 37), (13, 1, 4), (32, 32, 32), (11, 21, 31)]:
+        x = rng.standard_normal(shp) * 10
+        for lvl in (1, 2, 3, 4):
+            w = oracle.wavelet3d(x, lvl)
+            assert bits_equal(w, ref.wavelet3d(x, lvl))
+            assert bits_equal(oracle.wavelet3d(w, -lvl), ref.wavelet3d(w, -lvl))
+    for n in (1, 2, 1000, 60000, 123457):
+        sym = rng.integers(0, 256, n, dtype=np.uint8)
+        s = oracle.range_encode(sym)
+        assert np.array_equal(s, ref.range_encode(sym))
+        assert np.array_equal(ref.range_decode(s, n), sym)
+    f = oracle.probe_field((24, 28, 36))
+    for tol in (1e-2, 1e-6, 1e-12, 1e-16):
+        a, b = oracle.encode(f, tol), ref.encode(f, tol)
+        assert np.array_equal(a["data"], b["data"])
+        assert bytes(a["header"]) == bytes(b["header"])
+        assert bits_equal(oracle.decode(f.shape, a["header"], a["data"]), ref.decode(f.shape, b["header"], b["data"]))

@@ -1,0 +1,276 @@
+"""Host-side mirror of the WaveRange library interface, bound to libwaverange_b200.so via ctypes.
+
+The product is the shared library (CUDA kernels + C ABI, see include/waverange_b200.h and
+include/waverange.h); this module only passes pointers.  It never falls back to a CPU
+implementation: if the library has not been built, importing the bindings raises.
+
+Two levels, as in the C ABI:
+  * encoding_wrap / decoding_wrap / setup_wr -- the reference's entry points
+    (reference src/core/wrappers.h:53,70,75) on HOST numpy arrays;
+  * Codec -- handle-based device-pointer API (what bench.py times) and the stage-level entry
+    points the parity tests use.  Device buffers are passed as integers (e.g. torch
+    tensor.data_ptr()), so nothing here depends on torch.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libwaverange_b200.so")
+NLAYMAX = 8
+BLOCKSIZE = 60000
+F64, F32 = 0, 1
+
+
+class Header(C.Structure):
+    """wrb_header (include/waverange_b200.h): the coding metadata encoding_wrap() returns."""
+    _fields_ = [("tolabs", C.c_double), ("midval", C.c_double), ("halfspanval", C.c_double),
+                ("wlev", C.c_ubyte), ("nlay", C.c_ubyte), ("ntot_enc", C.c_ulong),
+                ("deps_vec", C.c_double * NLAYMAX), ("minval_vec", C.c_double * NLAYMAX),
+                ("len_enc_vec", C.c_ulong * NLAYMAX)]
+
+    def as_dict(self):
+        n = self.nlay
+        return dict(tolabs=self.tolabs, midval=self.midval, halfspanval=self.halfspanval, wlev=self.wlev,
+                    nlay=n, ntot_enc=self.ntot_enc, deps_vec=list(self.deps_vec)[:n],
+                    minval_vec=list(self.minval_vec)[:n], len_enc_vec=list(self.len_enc_vec)[:n])
+
+
+class WaveRangeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# every symbol include/waverange_b200.h and include/waverange.h declare
+EXPORTS = ["wrb_create", "wrb_destroy", "wrb_last_error", "wrb_set_stream", "wrb_set_chunk_blocks",
+           "wrb_launch_count", "wrb_trim", "wrb_setup", "wrb_encode_device", "wrb_decode_device",
+           "wrb_encode_host", "wrb_decode_host", "wrb_wavelet3d_device", "wrb_quantise_device",
+           "wrb_range_encode_device", "wrb_range_decode_device", "wrb_ind_p2w_3d", "wrb_set_timing",
+           "wrb_last_stage_ms",
+           "encoding_wrap", "decoding_wrap", "setup_wr", "encoding_wrap_f", "decoding_wrap_f", "setup_wr_f"]
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise WaveRangeError("libwaverange_b200.so is not built (run `python -m waverange_b200.build` or "
+                             "__graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i, d, ul = C.c_void_p, C.c_int, C.c_double, C.c_ulong
+    H = C.POINTER(Header)
+    L.wrb_create.argtypes = [C.POINTER(vp), i]
+    L.wrb_destroy.argtypes = [vp]
+    L.wrb_destroy.restype = None
+    L.wrb_last_error.argtypes = [vp]
+    L.wrb_last_error.restype = C.c_char_p
+    L.wrb_set_stream.argtypes = [vp, vp]
+    L.wrb_set_chunk_blocks.argtypes = [vp, i]
+    L.wrb_launch_count.argtypes = [vp]
+    L.wrb_launch_count.restype = C.c_ulonglong
+    L.wrb_trim.argtypes = [vp]
+    L.wrb_setup.argtypes = [i, i, i, C.POINTER(C.c_ubyte), C.POINTER(ul)]
+    L.wrb_setup.restype = None
+    L.wrb_encode_device.argtypes = [vp, vp, i, i, i, i, i, d, H, vp, ul]
+    L.wrb_decode_device.argtypes = [vp, vp, i, i, i, i, H, vp]
+    L.wrb_encode_host.argtypes = [vp, vp, i, i, i, i, i, d, H, vp, ul]
+    L.wrb_decode_host.argtypes = [vp, vp, i, i, i, i, H, vp]
+    L.wrb_wavelet3d_device.argtypes = [vp, vp, i, i, i, i]
+    L.wrb_quantise_device.argtypes = [vp, vp, i, i, i, i, i, d, H, vp, vp]
+    L.wrb_range_encode_device.argtypes = [vp, vp, ul, ul, vp, ul, C.POINTER(ul), C.POINTER(ul)]
+    L.wrb_range_decode_device.argtypes = [vp, vp, C.POINTER(ul), ul, ul, vp]
+    L.wrb_ind_p2w_3d.argtypes = [i] * 7 + [C.POINTER(i)] * 4
+    L.wrb_ind_p2w_3d.restype = None
+    L.wrb_set_timing.argtypes = [vp, i]
+    L.wrb_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    f64p, u8p, ulp = C.POINTER(d), C.POINTER(C.c_ubyte), C.POINTER(ul)
+    L.encoding_wrap.argtypes = [i, i, i, f64p, i, i, i, i, f64p, f64p, f64p, f64p, u8p, u8p, ulp, f64p, f64p, ulp, u8p]
+    L.encoding_wrap.restype = None
+    L.decoding_wrap.argtypes = [i, i, i, f64p, f64p, f64p, f64p, u8p, u8p, ulp, f64p, f64p, ulp, u8p]
+    L.decoding_wrap.restype = None
+    L.setup_wr.argtypes = [i, i, i, u8p, ulp]
+    L.setup_wr.restype = None
+    _lib = L
+    return L
+
+
+def setup_wr(nx, ny, nz):
+    """reference wrappers.cpp:531-541 -> (nlaymax, ntot_enc_max)"""
+    n, m = C.c_ubyte(), C.c_ulong()
+    lib().wrb_setup(nx, ny, nz, C.byref(n), C.byref(m))
+    return n.value, m.value
+
+
+def _np_ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def encoding_wrap(fld, tol, wtflag=1):
+    """The reference's encoding_wrap on a host float64 array shaped (nz, ny, nx).
+    Returns (Header, data_enc[:ntot_enc])."""
+    L = lib()
+    a = np.ascontiguousarray(fld, dtype=np.float64)
+    nz, ny, nx = a.shape
+    _, cap = setup_wr(nx, ny, nz)
+    data = np.zeros(cap, dtype=np.uint8)
+    cut = np.array([tol], dtype=np.float64)
+    h = Header()
+    tolabs, mid, half = C.c_double(), C.c_double(), C.c_double()
+    wlev, nlay, ntot_enc = C.c_ubyte(), C.c_ubyte(), C.c_ulong()
+    deps, minv = np.zeros(NLAYMAX), np.zeros(NLAYMAX)
+    lens = (C.c_ulong * NLAYMAX)()
+    L.encoding_wrap(nx, ny, nz, _np_ptr(a, C.c_double), wtflag, 1, 1, 1, _np_ptr(cut, C.c_double),
+                    C.byref(tolabs), C.byref(mid), C.byref(half), C.byref(wlev), C.byref(nlay), C.byref(ntot_enc),
+                    _np_ptr(deps, C.c_double), _np_ptr(minv, C.c_double), lens, _np_ptr(data, C.c_ubyte))
+    h.tolabs, h.midval, h.halfspanval = tolabs.value, mid.value, half.value
+    h.wlev, h.nlay, h.ntot_enc = wlev.value, nlay.value, ntot_enc.value
+    for k in range(nlay.value):
+        h.deps_vec[k], h.minval_vec[k], h.len_enc_vec[k] = deps[k], minv[k], lens[k]
+    return h, data[:ntot_enc.value].copy()
+
+
+def decoding_wrap(shape, h, data):
+    """The reference's decoding_wrap; returns a float64 array of `shape` = (nz, ny, nx)."""
+    L = lib()
+    nz, ny, nx = shape
+    out = np.empty(shape, dtype=np.float64)
+    buf = np.zeros(len(data) + 64, dtype=np.uint8)
+    buf[:len(data)] = data
+    tolabs, mid, half = C.c_double(h.tolabs), C.c_double(h.midval), C.c_double(h.halfspanval)
+    wlev, nlay, ntot_enc = C.c_ubyte(h.wlev), C.c_ubyte(h.nlay), C.c_ulong(h.ntot_enc)
+    deps = np.array(list(h.deps_vec), dtype=np.float64)
+    minv = np.array(list(h.minval_vec), dtype=np.float64)
+    lens = (C.c_ulong * NLAYMAX)(*list(h.len_enc_vec))
+    L.decoding_wrap(nx, ny, nz, _np_ptr(out, C.c_double), C.byref(tolabs), C.byref(mid), C.byref(half),
+                    C.byref(wlev), C.byref(nlay), C.byref(ntot_enc), _np_ptr(deps, C.c_double),
+                    _np_ptr(minv, C.c_double), lens, _np_ptr(buf, C.c_ubyte))
+    return out
+
+
+def ind_p2w_3d(lvl, n, idx):
+    o = [C.c_int() for _ in range(4)]
+    lib().wrb_ind_p2w_3d(lvl, n[0], n[1], n[2], idx[0], idx[1], idx[2], *[C.byref(x) for x in o])
+    return tuple(x.value for x in o)
+
+
+def parse_container(layer_bytes):
+    """Split one layer of data_enc into its chunk streams.
+    Returns (chunk_len, [stream bytes...]); a bare reference stream gives (0, [layer])."""
+    b = bytes(layer_bytes)
+    if b[:4] != b"WRCK":
+        return 0, [b]
+    chunk_len = int.from_bytes(b[8:16], "little")
+    nch = int.from_bytes(b[24:28], "little")
+    lens = np.frombuffer(b, dtype="<u4", count=nch, offset=32)
+    off = 32 + 4 * nch
+    out = []
+    for n in lens:
+        out.append(b[off:off + int(n)])
+        off += int(n)
+    assert off == len(b), "container length mismatch"
+    return chunk_len, out
+
+
+class Codec:
+    """wrb_codec handle.  Pointers are plain integers (device addresses)."""
+
+    def __init__(self, device=0, chunk_blocks=None, stream=None):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.wrb_create(C.byref(h), device)
+        if rc != 0 or not h.value:
+            raise WaveRangeError("wrb_create failed (%d): no usable CUDA device; there is no CPU fallback" % rc)
+        self.h = h
+        if chunk_blocks is not None:
+            self._ck(self.L.wrb_set_chunk_blocks(self.h, chunk_blocks))
+        if stream is not None:
+            self.set_stream(stream)
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.L.wrb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise WaveRangeError("%s (code %d)" % (self.L.wrb_last_error(self.h).decode(), rc))
+
+    def set_stream(self, stream_handle):
+        self._ck(self.L.wrb_set_stream(self.h, C.c_void_p(stream_handle)))
+
+    def set_chunk_blocks(self, k):
+        self._ck(self.L.wrb_set_chunk_blocks(self.h, k))
+
+    def set_timing(self, on):
+        self._ck(self.L.wrb_set_timing(self.h, int(on)))
+
+    def stage_ms(self):
+        a = (C.c_float * 4)()
+        self._ck(self.L.wrb_last_stage_ms(self.h, a))
+        return list(a)
+
+    def launch_count(self):
+        return int(self.L.wrb_launch_count(self.h))
+
+    def trim(self):
+        self._ck(self.L.wrb_trim(self.h))
+
+    # ---- device path -----------------------------------------------------------------------
+    def encode_device(self, d_field, dtype, nx, ny, nz, tol, d_out, cap, wtflag=1):
+        h = Header()
+        self._ck(self.L.wrb_encode_device(self.h, d_field, dtype, nx, ny, nz, wtflag, tol, C.byref(h), d_out, cap))
+        return h
+
+    def decode_device(self, d_out, dtype, nx, ny, nz, h, d_data):
+        self._ck(self.L.wrb_decode_device(self.h, d_out, dtype, nx, ny, nz, C.byref(h), d_data))
+
+    # ---- host path -------------------------------------------------------------------------
+    def encode_host(self, fld, tol, wtflag=1, out=None):
+        a = np.ascontiguousarray(fld)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64)
+        dtype = F32 if a.dtype == np.float32 else F64
+        nz, ny, nx = a.shape
+        _, cap = setup_wr(nx, ny, nz)
+        data = out if out is not None else np.empty(cap, dtype=np.uint8)
+        h = Header()
+        self._ck(self.L.wrb_encode_host(self.h, a.ctypes.data, dtype, nx, ny, nz, wtflag, tol, C.byref(h),
+                                        data.ctypes.data, min(cap, data.size)))
+        return h, data[:h.ntot_enc]
+
+    def decode_host(self, shape, h, data, dtype=np.float64, out=None):
+        nz, ny, nx = shape
+        res = out if out is not None else np.empty(shape, dtype=dtype)
+        d = np.ascontiguousarray(data)
+        self._ck(self.L.wrb_decode_host(self.h, res.ctypes.data, F32 if res.dtype == np.float32 else F64, nx, ny, nz,
+                                        C.byref(h), d.ctypes.data if d.size else None))
+        return res
+
+    # ---- stages ----------------------------------------------------------------------------
+    def wavelet3d_device(self, d_x, nx, ny, nz, lvl):
+        self._ck(self.L.wrb_wavelet3d_device(self.h, d_x, nx, ny, nz, lvl))
+
+    def quantise_device(self, d_field, dtype, nx, ny, nz, tol, wtflag=1, d_coef=None, d_sym=None):
+        h = Header()
+        self._ck(self.L.wrb_quantise_device(self.h, d_field, dtype, nx, ny, nz, wtflag, tol, C.byref(h), d_coef, d_sym))
+        return h
+
+    def range_encode_device(self, d_sym, n, chunk_len, d_out, cap):
+        nch = 1 if chunk_len == 0 or chunk_len >= n else (n + chunk_len - 1) // chunk_len
+        lens = (C.c_ulong * nch)()
+        total = C.c_ulong()
+        self._ck(self.L.wrb_range_encode_device(self.h, d_sym, n, chunk_len, d_out, cap, lens, C.byref(total)))
+        return list(lens), total.value
+
+    def range_decode_device(self, d_in, lens, n, chunk_len, d_sym):
+        arr = (C.c_ulong * len(lens))(*lens)
+        self._ck(self.L.wrb_range_decode_device(self.h, d_in, arr, n, chunk_len, d_sym))

@@ -1,0 +1,562 @@
+// codec.cu -- codec handle, device-side pipeline orchestration and the wrb_* C ABI.
+//
+// Pipeline (compress), all on one stream, no host round trip until the final header read-back:
+//   state_init -> forward transform (field extrema + coefficient extrema fused) -> state_prepare
+//   -> for l in 0..7 { layer_params(l); quantise(l) }   (layers after the last one exit at once)
+//   -> range_encode (all layers, all chunks in one launch) -> container assembly -> D2H(state)
+// which restates encoding_wrap() (reference src/core/wrappers.cpp:228-452).
+// Decompress mirrors decoding_wrap() (:456-527).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <atomic>
+#include <new>
+#include "wr_common.cuh"
+#include "wr_kernels.h"
+#include "../../include/waverange_b200.h"
+
+namespace wrb {
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+}  // namespace wrb
+
+using namespace wrb;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = n + n / 16 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, n); want = n; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct wrb_codec {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int chunk_blocks = 1;
+    std::string err;
+    DevBuf coef, tmp, lllA, lllB, sym, hist, slots, lens, dstoff, state, blob, field, offs, layoff, misc;
+    DevState* h_state = nullptr;      // pinned
+    unsigned long long* h_u64 = nullptr;   // pinned scratch (64 KiB)
+    int timing = 0;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float stage_ms[4] = {0, 0, 0, 0};
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            c->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return (e_ == cudaErrorMemoryAllocation) ? WRB_E_NOMEM : WRB_E_CUDA;                   \
+        }                                                                                          \
+    } while (0)
+
+static int fail(wrb_codec* c, int code, const char* msg) { c->err = msg; return code; }
+
+static unsigned long long chunk_len_of(const wrb_codec* c)
+{
+    return c->chunk_blocks > 0 ? (unsigned long long)c->chunk_blocks * kBlock - 1ull : 0ull;
+}
+
+static inline int half_up(int n) { return (n + 1) / 2; }
+
+extern "C" {
+
+int wrb_create(wrb_codec** out, int device)
+{
+    if (!out) return WRB_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return WRB_E_CUDA;   // no CPU fallback
+    if (device < 0 || device >= ndev) return WRB_E_ARG;
+    wrb_codec* c = new (std::nothrow) wrb_codec();
+    if (!c) return WRB_E_NOMEM;
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMallocHost((void**)&c->h_state, sizeof(DevState)) != cudaSuccess ||
+        cudaMallocHost((void**)&c->h_u64, 65536) != cudaSuccess) {
+        delete c;
+        return WRB_E_CUDA;
+    }
+    for (int i = 0; i < 5; i++) cudaEventCreate(&c->ev[i]);
+    const char* env = getenv("WRB_CHUNK_BLOCKS");
+    if (env && *env) { int v = atoi(env); if (v >= 0) c->chunk_blocks = v; }
+    *out = c;
+    return 0;
+}
+
+int wrb_trim(wrb_codec* c)
+{
+    if (!c) return WRB_E_ARG;
+    cudaSetDevice(c->device);
+    DevBuf* all[] = {&c->coef, &c->tmp, &c->lllA, &c->lllB, &c->sym, &c->hist, &c->slots, &c->lens,
+                     &c->dstoff, &c->blob, &c->field, &c->offs, &c->layoff, &c->misc};
+    for (DevBuf* b : all) b->release();
+    return 0;
+}
+
+void wrb_destroy(wrb_codec* c)
+{
+    if (!c) return;
+    wrb_trim(c);
+    c->state.release();
+    if (c->h_state) cudaFreeHost(c->h_state);
+    if (c->h_u64) cudaFreeHost(c->h_u64);
+    for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    delete c;
+}
+
+const char* wrb_last_error(const wrb_codec* c) { return c ? c->err.c_str() : "null codec"; }
+int wrb_set_stream(wrb_codec* c, void* s) { if (!c) return WRB_E_ARG; c->stream = (cudaStream_t)s; return 0; }
+int wrb_set_chunk_blocks(wrb_codec* c, int b) { if (!c || b < 0) return WRB_E_ARG; c->chunk_blocks = b; return 0; }
+unsigned long long wrb_launch_count(const wrb_codec*) { return g_launches.load(); }
+int wrb_set_timing(wrb_codec* c, int on) { if (!c) return WRB_E_ARG; c->timing = on; return 0; }
+int wrb_last_stage_ms(const wrb_codec* c, float ms[4])
+{
+    if (!c || !ms) return WRB_E_ARG;
+    for (int i = 0; i < 4; i++) ms[i] = c->stage_ms[i];
+    return 0;
+}
+
+// reference wrappers.cpp:531-541
+void wrb_setup(int nx, int ny, int nz, unsigned char* nlaymax, unsigned long* ntot_enc_max)
+{
+    unsigned long ntot = (unsigned long)nx * (unsigned long)ny * (unsigned long)nz;
+    if (nlaymax) *nlaymax = (unsigned char)kNLayMax;
+    if (ntot_enc_max) *ntot_enc_max = 1ul * kNLayMax * (ntot < 1024ul ? 1024ul : ntot);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// small utility kernels
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void fill_kernel(T* out, unsigned long long n, double v)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        out[i] = (T)v;
+}
+
+// chunk-major padded symbols <-> array order
+__global__ void unpad_symbols_kernel(const uint8_t* __restrict__ sym, unsigned long long layer_stride, ChunkGeom g,
+                                     uint8_t* __restrict__ flat)
+{
+    const unsigned int c = blockIdx.x;
+    const int l = blockIdx.z;
+    const unsigned long long cstart = (unsigned long long)c * g.chunk_len;
+    const unsigned long long clen = (g.ntot - cstart < g.chunk_len) ? g.ntot - cstart : g.chunk_len;
+    const uint8_t* in = sym + (unsigned long long)l * layer_stride + (unsigned long long)c * g.pitch;
+    uint8_t* out = flat + (unsigned long long)l * g.ntot + cstart;
+    for (unsigned long long i = blockIdx.y * (unsigned long long)blockDim.x + threadIdx.x; i < clen;
+         i += (unsigned long long)gridDim.y * blockDim.x)
+        out[i] = in[i];
+}
+
+// array-order symbols -> chunk-major padded layout + per-coder-block histograms (one CTA per block)
+__global__ void __launch_bounds__(256) pad_hist_kernel(const uint8_t* __restrict__ flat, ChunkGeom g,
+                                                       uint8_t* __restrict__ sym, uint32_t* __restrict__ hist)
+{
+    __shared__ uint32_t s_hist[256];
+    const int tid = threadIdx.x;
+    s_hist[tid] = 0;
+    __syncthreads();
+    const unsigned int b = blockIdx.x;
+    const unsigned int c = b / g.blocks_per_chunk, kb = b % g.blocks_per_chunk;
+    const unsigned long long cstart = (unsigned long long)c * g.chunk_len;
+    const unsigned long long clen = (g.ntot - cstart < g.chunk_len) ? g.ntot - cstart : g.chunk_len;
+    const unsigned long long boff = (unsigned long long)kb * kBlock;
+    const unsigned int bs = (clen - boff < kBlock) ? (unsigned int)(clen - boff) : kBlock;
+    const uint8_t* in = flat + cstart + boff;
+    uint8_t* out = sym + (unsigned long long)c * g.pitch + boff;
+    for (unsigned int i = tid; i < bs; i += 256) {
+        uint8_t q = in[i];
+        out[i] = q;
+        atomicAdd(&s_hist[q], 1u);
+    }
+    __syncthreads();
+    hist[(unsigned long long)b * 256 + tid] = s_hist[tid];
+}
+
+__global__ void set_nlay_kernel(DevState* st, int nlay) { st->nlay = nlay; st->error = 0; }
+
+static int grid_for(unsigned long long n)
+{
+    unsigned long long b = (n + 256ull * 8 - 1) / (256ull * 8);
+    if (b < 1) b = 1;
+    if (b > 148ull * 16) b = 148ull * 16;
+    return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------
+// buffer sizing
+// ------------------------------------------------------------------------------------------
+static int ensure_transform_buffers(wrb_codec* c, int nx, int ny, int nz)
+{
+    const size_t ntot = (size_t)nx * ny * nz;
+    const size_t m1 = (size_t)half_up(nx) * half_up(ny) * half_up(nz);
+    const size_t m2 = (size_t)half_up(half_up(nx)) * half_up(half_up(ny)) * half_up(half_up(nz));
+    CK(c->coef.ensure(ntot * 8));
+    CK(c->tmp.ensure(ntot * 8));
+    CK(c->lllA.ensure(m1 * 8 + 64));
+    CK(c->lllB.ensure(m2 * 8 + 64));
+    CK(c->state.ensure(sizeof(DevState)));
+    return 0;
+}
+
+static int ensure_coder_buffers(wrb_codec* c, const ChunkGeom& g, int nlayers, bool need_slots)
+{
+    CK(c->sym.ensure((size_t)nlayers * g.nchunks * g.pitch + 64));
+    CK(c->hist.ensure((size_t)nlayers * g.nblocks * 256 * 4));
+    if (need_slots) {
+        CK(c->slots.ensure((size_t)nlayers * g.nchunks * chunk_slot_pitch(g)));
+        CK(c->lens.ensure((size_t)nlayers * g.nchunks * 8));
+        CK(c->dstoff.ensure((size_t)nlayers * g.nchunks * 8));
+    }
+    CK(c->offs.ensure((size_t)nlayers * g.nchunks * 8 + 64));
+    CK(c->layoff.ensure(16 * 8));
+    CK(c->misc.ensure(256));
+    CK(c->state.ensure(sizeof(DevState)));
+    return 0;
+}
+
+static void header_from_state(const DevState& s, int wtflag, wrb_header* hdr)
+{
+    memset(hdr, 0, sizeof(*hdr));
+    hdr->tolabs = s.tolabs;
+    hdr->midval = s.midval;
+    hdr->halfspanval = s.halfspan;
+    hdr->wlev = (unsigned char)(wtflag ? kWavLvl : 0);        // wrappers.cpp:241 (set even when trivial)
+    hdr->nlay = (unsigned char)s.nlay;
+    hdr->ntot_enc = (unsigned long)s.ntot_enc;
+    for (int l = 0; l < s.nlay && l < kNLayMax; l++) {
+        hdr->deps_vec[l] = s.deps[l];
+        hdr->minval_vec[l] = s.minval[l];
+        hdr->len_enc_vec[l] = (unsigned long)s.len_enc[l];
+    }
+}
+
+// transform + all layers; leaves coefficients in c->coef, symbols (padded) in c->sym, histograms
+// in c->hist and layer parameters in the device state
+static int run_transform_and_quantise(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag,
+                                      double tolrel, const ChunkGeom& g)
+{
+    DevState* st = (DevState*)c->state.p;
+    cudaStream_t s = c->stream;
+    state_init(st, s);
+    if (c->timing) cudaEventRecord(c->ev[0], s);
+    wavelet_forward(d_field, dtype == WRB_F32, (double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p,
+                    (double*)c->lllB.p, nx, ny, nz, wtflag ? kWavLvl : 0, st, s);
+    state_prepare(st, tolrel, s);
+    if (c->timing) cudaEventRecord(c->ev[1], s);
+    const unsigned long long lstride = (unsigned long long)g.nchunks * g.pitch;
+    const unsigned long long hstride = (unsigned long long)g.nblocks * 256;
+    for (int l = 0; l < kNLayMax; l++) {
+        layer_params(st, l, s);
+        quantise_layer((const double*)c->coef.p, g, l, st, (uint8_t*)c->sym.p + l * lstride,
+                       (uint32_t*)c->hist.p + l * hstride, s);
+    }
+    if (c->timing) cudaEventRecord(c->ev[2], s);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+int wrb_encode_device(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag, double tolrel,
+                      wrb_header* hdr, unsigned char* d_data_enc, unsigned long cap)
+{
+    if (!c || !d_field || !hdr || !d_data_enc || nx < 1 || ny < 1 || nz < 1 || (dtype != WRB_F64 && dtype != WRB_F32))
+        return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    const unsigned long long ntot = (unsigned long long)nx * ny * nz;
+    const ChunkGeom g = make_geom(ntot, chunk_len_of(c));
+    const int chunked = c->chunk_blocks > 0;
+    int rc;
+    if ((rc = ensure_transform_buffers(c, nx, ny, nz))) return rc;
+    if ((rc = ensure_coder_buffers(c, g, kNLayMax, true))) return rc;
+    DevState* st = (DevState*)c->state.p;
+    cudaStream_t s = c->stream;
+    if ((rc = run_transform_and_quantise(c, d_field, dtype, nx, ny, nz, wtflag, tolrel, g))) return rc;
+    const unsigned long long lstride = (unsigned long long)g.nchunks * g.pitch;
+    const unsigned long long hstride = (unsigned long long)g.nblocks * 256;
+    const unsigned long long sp = chunk_slot_pitch(g);
+    range_encode_chunks((const uint8_t*)c->sym.p, lstride, (const uint32_t*)c->hist.p, hstride, g, kNLayMax, st->active,
+                        (uint8_t*)c->slots.p, sp, (unsigned long long*)c->lens.p, s);
+    if (c->timing) cudaEventRecord(c->ev[3], s);
+    assemble_container((const uint8_t*)c->slots.p, sp, (const unsigned long long*)c->lens.p, g, chunked, st,
+                       d_data_enc, cap, (unsigned long long*)c->dstoff.p, s);
+    if (c->timing) cudaEventRecord(c->ev[4], s);
+    CK(cudaMemcpyAsync(c->h_state, st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (c->timing) for (int i = 0; i < 4; i++) cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]);
+    header_from_state(*c->h_state, wtflag, hdr);
+    if (c->h_state->error) return fail(c, WRB_E_OVERFLOW, "encoded data does not fit in data_enc");
+    return 0;
+}
+
+int wrb_quantise_device(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag,
+                        double tolrel, wrb_header* hdr, double* d_coef, unsigned char* d_sym)
+{
+    if (!c || !d_field || nx < 1 || ny < 1 || nz < 1 || (dtype != WRB_F64 && dtype != WRB_F32))
+        return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    const unsigned long long ntot = (unsigned long long)nx * ny * nz;
+    const ChunkGeom g = make_geom(ntot, chunk_len_of(c));
+    int rc;
+    if ((rc = ensure_transform_buffers(c, nx, ny, nz))) return rc;
+    if ((rc = ensure_coder_buffers(c, g, kNLayMax, false))) return rc;
+    DevState* st = (DevState*)c->state.p;
+    cudaStream_t s = c->stream;
+    if ((rc = run_transform_and_quantise(c, d_field, dtype, nx, ny, nz, wtflag, tolrel, g))) return rc;
+    CK(cudaMemcpyAsync(c->h_state, st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (hdr) { header_from_state(*c->h_state, wtflag, hdr); hdr->ntot_enc = 0; }
+    if (d_coef) CK(cudaMemcpyAsync(d_coef, c->coef.p, ntot * 8, cudaMemcpyDeviceToDevice, s));
+    if (d_sym && c->h_state->nlay > 0) {
+        unsigned long long per = (g.chunk_len + 255) / 256;
+        unsigned int gy = (unsigned int)(per < 64 ? (per ? per : 1) : 64);
+        dim3 grid(g.nchunks, gy, c->h_state->nlay);
+        unpad_symbols_kernel<<<grid, 256, 0, s>>>((const uint8_t*)c->sym.p, (unsigned long long)g.nchunks * g.pitch, g, d_sym);
+        note_launch(1);
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int wrb_decode_device(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int nz, const wrb_header* hdr,
+                      const unsigned char* d_data_enc)
+{
+    if (!c || !d_out || !hdr || nx < 1 || ny < 1 || nz < 1 || (dtype != WRB_F64 && dtype != WRB_F32))
+        return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const unsigned long long ntot = (unsigned long long)nx * ny * nz;
+    if (hdr->ntot_enc == 0) {                                 // wrappers.cpp:462-469
+        if (dtype == WRB_F32) fill_kernel<float><<<grid_for(ntot), 256, 0, s>>>((float*)d_out, ntot, hdr->midval);
+        else fill_kernel<double><<<grid_for(ntot), 256, 0, s>>>((double*)d_out, ntot, hdr->midval);
+        note_launch(1);
+        CK(cudaStreamSynchronize(s));
+        return 0;
+    }
+    if (!d_data_enc || hdr->nlay < 1 || hdr->nlay > kNLayMax || hdr->wlev > 16) return fail(c, WRB_E_ARG, "bad header");
+    const int nlay = hdr->nlay;
+    unsigned long long* lay = c->h_u64;                       // layer offsets [nlay+1]
+    lay[0] = 0;
+    for (int l = 0; l < nlay; l++) lay[l + 1] = lay[l] + hdr->len_enc_vec[l];
+    if (lay[nlay] != hdr->ntot_enc) return fail(c, WRB_E_FORMAT, "len_enc_vec does not sum to ntot_enc");
+    // container geometry from the first layer's header (all layers share it)
+    unsigned char* peek = (unsigned char*)(c->h_u64 + 64);
+    const size_t npeek = hdr->len_enc_vec[0] < 32 ? hdr->len_enc_vec[0] : 32;
+    if (c->timing) cudaEventRecord(c->ev[0], s);
+    CK(cudaMemcpyAsync(peek, d_data_enc, npeek, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    int chunked = 0;
+    unsigned long long chunk_len = 0;
+    if (npeek >= 32 && peek[0] == 'W' && peek[1] == 'R' && peek[2] == 'C' && peek[3] == 'K') {
+        chunked = 1;
+        unsigned long long nsym = 0, nch = 0;
+        for (int k = 0; k < 8; k++) { chunk_len |= (unsigned long long)peek[8 + k] << (8 * k); nsym |= (unsigned long long)peek[16 + k] << (8 * k); }
+        for (int k = 0; k < 4; k++) nch |= (unsigned long long)peek[24 + k] << (8 * k);
+        if (nsym != ntot || chunk_len == 0 || chunk_len > ntot || nch != (ntot + chunk_len - 1) / chunk_len)
+            return fail(c, WRB_E_FORMAT, "chunk container header does not match the field size");
+    } else if (npeek >= 1 && peek[0] != 0x00) {
+        return fail(c, WRB_E_FORMAT, "layer is neither a WRCK container nor a reference stream");
+    }
+    const ChunkGeom g = make_geom(ntot, chunk_len);
+    int rc;
+    if ((rc = ensure_transform_buffers(c, nx, ny, nz))) return rc;
+    if ((rc = ensure_coder_buffers(c, g, nlay, false))) return rc;
+    int* d_err = (int*)c->misc.p;
+    CK(cudaMemsetAsync(d_err, 0, sizeof(int), s));
+    CK(cudaMemcpyAsync(c->layoff.p, lay, (nlay + 1) * 8, cudaMemcpyHostToDevice, s));
+    parse_container(d_data_enc, g, chunked, nlay, (const unsigned long long*)c->layoff.p, (unsigned long long*)c->offs.p, d_err, s);
+    if (c->timing) cudaEventRecord(c->ev[1], s);
+    const unsigned long long lstride = (unsigned long long)g.nchunks * g.pitch;
+    range_decode_chunks(d_data_enc, (const unsigned long long*)c->offs.p, g, nlay, (uint8_t*)c->sym.p, lstride, d_err, s);
+    if (c->timing) cudaEventRecord(c->ev[2], s);
+    dequantise((const uint8_t*)c->sym.p, lstride, g, nlay, hdr->deps_vec, hdr->minval_vec, (double*)c->coef.p, s);
+    if (c->timing) cudaEventRecord(c->ev[3], s);
+    wavelet_inverse((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, d_out, dtype == WRB_F32,
+                    nx, ny, nz, (int)hdr->wlev, s);
+    if (c->timing) cudaEventRecord(c->ev[4], s);
+    int* h_err = (int*)(c->h_u64 + 128);
+    CK(cudaMemcpyAsync(h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (c->timing) for (int i = 0; i < 4; i++) cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]);
+    if (*h_err) return fail(c, WRB_E_FORMAT, "range decoder: malformed chunk stream");
+    return 0;
+}
+
+int wrb_encode_host(wrb_codec* c, const void* field, int dtype, int nx, int ny, int nz, int wtflag, double tolrel,
+                    wrb_header* hdr, unsigned char* data_enc, unsigned long cap)
+{
+    if (!c || !field || !hdr || !data_enc || nx < 1 || ny < 1 || nz < 1 || (dtype != WRB_F64 && dtype != WRB_F32))
+        return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    const size_t ntot = (size_t)nx * ny * nz;
+    const size_t esz = dtype == WRB_F32 ? 4 : 8;
+    CK(c->field.ensure(ntot * esz));
+    CK(c->blob.ensure((size_t)cap + 64));
+    CK(cudaMemcpyAsync(c->field.p, field, ntot * esz, cudaMemcpyHostToDevice, c->stream));
+    int rc = wrb_encode_device(c, c->field.p, dtype, nx, ny, nz, wtflag, tolrel, hdr, (unsigned char*)c->blob.p, cap);
+    if (rc) return rc;
+    if (hdr->ntot_enc) CK(cudaMemcpyAsync(data_enc, c->blob.p, hdr->ntot_enc, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int wrb_decode_host(wrb_codec* c, void* field_out, int dtype, int nx, int ny, int nz, const wrb_header* hdr,
+                    const unsigned char* data_enc)
+{
+    if (!c || !field_out || !hdr || nx < 1 || ny < 1 || nz < 1 || (dtype != WRB_F64 && dtype != WRB_F32))
+        return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    const size_t ntot = (size_t)nx * ny * nz;
+    const size_t esz = dtype == WRB_F32 ? 4 : 8;
+    CK(c->field.ensure(ntot * esz));
+    CK(c->blob.ensure((size_t)hdr->ntot_enc + 64));
+    if (hdr->ntot_enc) {
+        if (!data_enc) return fail(c, WRB_E_ARG, "data_enc is null");
+        CK(cudaMemcpyAsync(c->blob.p, data_enc, hdr->ntot_enc, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync((unsigned char*)c->blob.p + hdr->ntot_enc, 0, 64, c->stream));
+    }
+    int rc = wrb_decode_device(c, c->field.p, dtype, nx, ny, nz, hdr, (const unsigned char*)c->blob.p);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(field_out, c->field.p, ntot * esz, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int wrb_wavelet3d_device(wrb_codec* c, double* d_x, int nx, int ny, int nz, int lvl)
+{
+    if (!c || !d_x || nx < 1 || ny < 1 || nz < 1) return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    const size_t ntot = (size_t)nx * ny * nz;
+    int rc;
+    if ((rc = ensure_transform_buffers(c, nx, ny, nz))) return rc;
+    CK(c->field.ensure(ntot * 8));
+    cudaStream_t s = c->stream;
+    if (lvl == 0) return 0;
+    if (lvl > 0) {
+        DevState* st = (DevState*)c->state.p;
+        state_init(st, s);
+        CK(cudaMemcpyAsync(c->field.p, d_x, ntot * 8, cudaMemcpyDeviceToDevice, s));
+        wavelet_forward(c->field.p, 0, d_x, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, nx, ny, nz, lvl, st, s);
+    } else {
+        wavelet_inverse(d_x, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, c->field.p, 0, nx, ny, nz, -lvl, s);
+        CK(cudaMemcpyAsync(d_x, c->field.p, ntot * 8, cudaMemcpyDeviceToDevice, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int wrb_range_encode_device(wrb_codec* c, const unsigned char* d_sym, unsigned long n, unsigned long chunk_len,
+                            unsigned char* d_out, unsigned long cap, unsigned long* lens, unsigned long* total)
+{
+    if (!c || !d_sym || !d_out || n < 1) return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    const ChunkGeom g = make_geom(n, chunk_len);
+    int rc;
+    if ((rc = ensure_coder_buffers(c, g, 1, true))) return rc;
+    cudaStream_t s = c->stream;
+    DevState* st = (DevState*)c->state.p;
+    state_init(st, s);
+    set_nlay_kernel<<<1, 1, 0, s>>>(st, 1);
+    pad_hist_kernel<<<g.nblocks, 256, 0, s>>>(d_sym, g, (uint8_t*)c->sym.p, (uint32_t*)c->hist.p);
+    note_launch(2);
+    const unsigned long long sp = chunk_slot_pitch(g);
+    range_encode_chunks((const uint8_t*)c->sym.p, 0, (const uint32_t*)c->hist.p, 0, g, 1, nullptr, (uint8_t*)c->slots.p, sp,
+                        (unsigned long long*)c->lens.p, s);
+    assemble_container((const uint8_t*)c->slots.p, sp, (const unsigned long long*)c->lens.p, g, 0, st, d_out, cap,
+                       (unsigned long long*)c->dstoff.p, s);
+    CK(cudaMemcpyAsync(c->h_state, st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
+    if (lens) {
+        if ((size_t)g.nchunks * 8 <= 65536 - 2048) {
+            CK(cudaMemcpyAsync(c->h_u64 + 256, c->lens.p, (size_t)g.nchunks * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            for (unsigned int i = 0; i < g.nchunks; i++) lens[i] = (unsigned long)c->h_u64[256 + i];
+        } else {
+            CK(cudaStreamSynchronize(s));
+            CK(cudaMemcpy(lens, c->lens.p, (size_t)g.nchunks * 8, cudaMemcpyDeviceToHost));
+        }
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (total) *total = (unsigned long)c->h_state->ntot_enc;
+    if (c->h_state->error) return fail(c, WRB_E_OVERFLOW, "encoded data does not fit");
+    return 0;
+}
+
+int wrb_range_decode_device(wrb_codec* c, const unsigned char* d_in, const unsigned long* lens, unsigned long n,
+                            unsigned long chunk_len, unsigned char* d_sym)
+{
+    if (!c || !d_in || !lens || !d_sym || n < 1) return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    const ChunkGeom g = make_geom(n, chunk_len);
+    int rc;
+    if ((rc = ensure_coder_buffers(c, g, 1, false))) return rc;
+    cudaStream_t s = c->stream;
+    unsigned long long* offs = (unsigned long long*)malloc((size_t)g.nchunks * 8);
+    if (!offs) return fail(c, WRB_E_NOMEM, "host allocation failed");
+    unsigned long long acc = 0;
+    for (unsigned int i = 0; i < g.nchunks; i++) { offs[i] = acc; acc += lens[i]; }
+    int* d_err = (int*)c->misc.p;
+    cudaError_t e1 = cudaMemsetAsync(d_err, 0, sizeof(int), s);
+    cudaError_t e2 = cudaMemcpyAsync(c->offs.p, offs, (size_t)g.nchunks * 8, cudaMemcpyHostToDevice, s);
+    cudaError_t e3 = cudaStreamSynchronize(s);
+    free(offs);
+    CK(e1); CK(e2); CK(e3);
+    range_decode_chunks(d_in, (const unsigned long long*)c->offs.p, g, 1, (uint8_t*)c->sym.p, 0, d_err, s);
+    unsigned long long per = (g.chunk_len + 255) / 256;
+    unsigned int gy = (unsigned int)(per < 64 ? (per ? per : 1) : 64);
+    dim3 grid(g.nchunks, gy, 1);
+    unpad_symbols_kernel<<<grid, 256, 0, s>>>((const uint8_t*)c->sym.p, 0, g, d_sym);
+    note_launch(1);
+    int* h_err = (int*)(c->h_u64 + 128);
+    CK(cudaMemcpyAsync(h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (*h_err) return fail(c, WRB_E_FORMAT, "range decoder: malformed chunk stream");
+    return 0;
+}
+
+// reference src/waveletcdf97_3d/waveletcdf97_3d.c:473-553.  The index is updated one direction
+// at a time and re-tested against the current box before each direction, as the reference does.
+void wrb_ind_p2w_3d(int lvlin, int n1, int n2, int n3, int i1, int i2, int i3, int* lvl, int* o1, int* o2, int* o3)
+{
+    int n[3] = {n1, n2, n3}, idx[3] = {i1, i2, i3};
+    int level = 0, moved = 0;
+    for (int k = 1; k <= lvlin; k++) {
+        int m[3] = {half_up(n[0]), half_up(n[1]), half_up(n[2])};
+        for (int d = 0; d < 3; d++) {
+            if (n[d] <= 1) continue;
+            if (idx[0] < n[0] && idx[1] < n[1] && idx[2] < n[2]) {
+                idx[d] = (idx[d] & 1) ? idx[d] / 2 + m[d] : idx[d] / 2;
+                moved = 1;
+            }
+        }
+        for (int d = 0; d < 3; d++) n[d] = m[d];
+        if (moved) level++;
+    }
+    if (lvl) *lvl = level;
+    if (o1) *o1 = idx[0];
+    if (o2) *o2 = idx[1];
+    if (o3) *o3 = idx[2];
+}
+
+}  // extern "C"

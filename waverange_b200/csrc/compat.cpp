@@ -1,0 +1,136 @@
+// compat.cpp -- the reference's library entry points on top of the wrb_* C ABI.
+//
+// Same names, argument meaning and error behaviour as reference src/core/wrappers.cpp:
+//   encoding_wrap :228-452   decoding_wrap :456-527   setup_wr :531-541
+//   encoding_wrap_f :545-563 decoding_wrap_f :567-580 setup_wr_f :584-594
+// A program linked against libwaverange_b200.so instead of libwaverange.so runs on the GPU:
+// the host buffers are copied to the device, compressed / decompressed there, and copied back.
+// There is no CPU path: without a usable CUDA device these functions throw.
+#include <cstdio>
+#include <cstdlib>
+#include <exception>
+#include <iostream>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include "../../include/waverange_b200.h"
+#include "../../include/waverange.h"
+
+namespace {
+std::mutex g_mu;
+wrb_codec* g_codec = nullptr;
+
+wrb_codec* codec()
+{
+    if (!g_codec) {
+        int dev = 0;
+        if (const char* e = getenv("WRB_DEVICE")) dev = atoi(e);
+        int rc = wrb_create(&g_codec, dev);
+        if (rc != 0 || !g_codec) {
+            fprintf(stderr, "waverange_b200: no usable CUDA device (wrb_create -> %d); there is no CPU fallback\n", rc);
+            throw std::runtime_error("waverange_b200: CUDA device unavailable");
+        }
+    }
+    return g_codec;
+}
+bool verbose() { const char* e = getenv("WRB_VERBOSE"); return e && *e && *e != '0'; }
+}  // namespace
+
+extern "C" void encoding_wrap(int nx, int ny, int nz, double* fld_1d, int wtflag, int mx, int my, int mz,
+                              double* cutoffvec, double& tolabs, double& midval, double& halfspanval,
+                              unsigned char& wlev, unsigned char& nlay, unsigned long int& ntot_enc, double* deps_vec,
+                              double* minval_vec, unsigned long int* len_enc_vec, unsigned char* data_enc)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    wrb_codec* c = codec();
+    // minimum cutoff (wrappers.cpp:292-293).  The spatially varying branch (:343-379) is compiled
+    // out of every reference front-end (UNIFORM_CUTOFF 1, defs.h:40); with mtot > 1 the global
+    // minimum is applied everywhere, which is at least as accurate at every point.
+    unsigned int mtot = (unsigned int)(mx * my * mz);
+    double tolrel = cutoffvec[0];
+    for (unsigned int k = 1; k < mtot; k++) if (cutoffvec[k] < tolrel) tolrel = cutoffvec[k];
+    if (mtot > 1) fprintf(stderr, "waverange_b200: local cutoff (mx*my*mz > 1) not supported, using the minimum cutoff everywhere\n");
+    if (verbose()) std::cout << "Wavelet decomposition..." << std::endl << "Range encoding..." << std::endl;
+    unsigned char nlaymax; unsigned long cap;
+    wrb_setup(nx, ny, nz, &nlaymax, &cap);
+    wrb_header h;
+    int rc = wrb_encode_host(c, fld_1d, WRB_F64, nx, ny, nz, wtflag, tolrel, &h, data_enc, cap);
+    if (rc == WRB_E_OVERFLOW) {                                  // wrappers.cpp:422-426
+        std::cout << "Error: encoded array is too large. Use larger SAFETY_BUFFER_FACTOR" << std::endl;
+        throw std::exception();
+    }
+    if (rc != 0) {
+        fprintf(stderr, "waverange_b200: encoding_wrap failed: %s\n", wrb_last_error(c));
+        throw std::runtime_error(std::string("waverange_b200: ") + wrb_last_error(c));
+    }
+    tolabs = h.tolabs; midval = h.midval; halfspanval = h.halfspanval;
+    wlev = h.wlev; nlay = h.nlay; ntot_enc = h.ntot_enc;
+    for (int l = 0; l < h.nlay; l++) {
+        deps_vec[l] = h.deps_vec[l]; minval_vec[l] = h.minval_vec[l]; len_enc_vec[l] = h.len_enc_vec[l];
+        if (verbose()) std::cout << "ilay=" << l << " deps=" << h.deps_vec[l] << " len_out_q=" << h.len_enc_vec[l] << std::endl;
+    }
+}
+
+extern "C" void decoding_wrap(int nx, int ny, int nz, double* fld_1d, double& tolabs, double& midval,
+                              double& halfspanval, unsigned char& wlev, unsigned char& nlay,
+                              unsigned long int& ntot_enc, double* deps_vec, double* minval_vec,
+                              unsigned long int* len_enc_vec, unsigned char* data_enc)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    wrb_codec* c = codec();
+    wrb_header h{};
+    h.tolabs = tolabs; h.midval = midval; h.halfspanval = halfspanval;
+    h.wlev = wlev; h.nlay = nlay; h.ntot_enc = ntot_enc;
+    for (int l = 0; l < nlay && l < WRB_NLAYMAX; l++) {
+        h.deps_vec[l] = deps_vec[l]; h.minval_vec[l] = minval_vec[l]; h.len_enc_vec[l] = len_enc_vec[l];
+    }
+    if (verbose()) std::cout << "Range decoding..." << std::endl << "Wavelet reconstruction..." << std::endl;
+    int rc = wrb_decode_host(c, fld_1d, WRB_F64, nx, ny, nz, &h, data_enc);
+    if (rc == WRB_E_FORMAT) {                                    // wrappers.cpp:168-171
+        fprintf(stderr, "could not successfully open input data\n");
+        exit(1);
+    }
+    if (rc != 0) {
+        fprintf(stderr, "waverange_b200: decoding_wrap failed: %s\n", wrb_last_error(c));
+        throw std::runtime_error(std::string("waverange_b200: ") + wrb_last_error(c));
+    }
+}
+
+extern "C" void setup_wr(int nx, int ny, int nz, unsigned char& nlaymax, unsigned long int& ntot_enc_max)
+{
+    wrb_setup(nx, ny, nz, &nlaymax, &ntot_enc_max);
+}
+
+extern "C" void encoding_wrap_f(int* nx, int* ny, int* nz, double* fld, int* wtflag, double* tolrel, double& tolabs,
+                                double& midval, double& halfspanval, unsigned char& wlev, unsigned char& nlay,
+                                long int& ntot_enc_sg, double* deps_vec, double* minval_vec, long int* len_enc_vec_sg,
+                                unsigned char* data_enc)
+{
+    unsigned long int ntot_enc = 0;
+    unsigned long int len_enc_vec[WRB_NLAYMAX] = {0};
+    double cut[1] = {*tolrel};
+    encoding_wrap(*nx, *ny, *nz, fld, *wtflag, 1, 1, 1, cut, tolabs, midval, halfspanval, wlev, nlay, ntot_enc,
+                  deps_vec, minval_vec, len_enc_vec, data_enc);
+    ntot_enc_sg = (long int)ntot_enc;
+    for (int j = 0; j < WRB_NLAYMAX; j++) len_enc_vec_sg[j] = (long int)len_enc_vec[j];   // all 8 slots (:561-562)
+}
+
+extern "C" void decoding_wrap_f(int* nx, int* ny, int* nz, double* fld, double& midval, double& halfspanval,
+                                unsigned char& wlev, unsigned char& nlay, long int& ntot_enc_sg, double* deps_vec,
+                                double* minval_vec, long int* len_enc_vec_sg, unsigned char* data_enc)
+{
+    double tolabs = 0;
+    unsigned long int ntot_enc = (unsigned long int)ntot_enc_sg;
+    unsigned long int len_enc_vec[WRB_NLAYMAX];
+    for (int j = 0; j < WRB_NLAYMAX; j++) len_enc_vec[j] = (unsigned long int)len_enc_vec_sg[j];
+    decoding_wrap(*nx, *ny, *nz, fld, tolabs, midval, halfspanval, wlev, nlay, ntot_enc, deps_vec, minval_vec,
+                  len_enc_vec, data_enc);
+}
+
+extern "C" void setup_wr_f(int* nx, int* ny, int* nz, int& nlaymax, long int& ntot_enc_max)
+{
+    unsigned char n; unsigned long m;
+    wrb_setup(*nx, *ny, *nz, &n, &m);
+    nlaymax = n;
+    ntot_enc_max = (long int)m;
+}

@@ -1,0 +1,173 @@
+// quant.cu -- byte-plane quantiser of the wavelet coefficients.
+//
+// Replaces the layer loop of encoding_wrap() (reference src/core/wrappers.cpp:305-441) and the
+// accumulate loop of decoding_wrap() (:480-515).
+//
+// The reference keeps the residual in place and sweeps it ~5 times per layer.  Here the
+// coefficient array is never rewritten: the pass for layer l re-derives the residual from the
+// coefficient by replaying the l earlier (deps, minval) pairs in registers with bit-identical
+// operations, emits the 1-byte symbol, reduces min/max of the new residual (the only global
+// dependency between layers, wrappers.cpp:308-314) and accumulates the 256-bin histogram of the
+// coder block the symbol belongs to.  Layer parameters live in device memory (DevState), so the
+// host never waits between layers; layers after the terminating one exit immediately.
+#include <cfloat>
+#include "wr_common.cuh"
+#include "wr_kernels.h"
+
+namespace wrb {
+
+ChunkGeom make_geom(unsigned long long ntot, unsigned long long chunk_len)
+{
+    ChunkGeom g{};
+    g.ntot = ntot;
+    g.chunk_len = (chunk_len == 0 || chunk_len > ntot) ? ntot : chunk_len;
+    g.pitch = (g.chunk_len + 15ull) & ~15ull;
+    g.nchunks = (unsigned int)((ntot + g.chunk_len - 1) / g.chunk_len);
+    g.blocks_per_chunk = (unsigned int)(g.chunk_len / kBlock + 1);
+    unsigned long long last = ntot - (unsigned long long)(g.nchunks - 1) * g.chunk_len;
+    g.nblocks = (g.nchunks - 1) * g.blocks_per_chunk + (unsigned int)(last / kBlock + 1);
+    return g;
+}
+
+__global__ void state_init_kernel(DevState* st)
+{
+    st->fmin_key = kKeyMinInit; st->fmax_key = kKeyMaxInit;
+    for (int l = 0; l <= kNLayMax; l++) { st->rmin_key[l] = kKeyMinInit; st->rmax_key[l] = kKeyMaxInit; }
+    for (int l = 0; l < kNLayMax; l++) {
+        st->active[l] = 0; st->deps[l] = 0; st->minval[l] = 0; st->aopt[l] = 0; st->bopt[l] = 0; st->len_enc[l] = 0;
+    }
+    st->tolabs = 0; st->midval = 0; st->halfspan = 0;
+    st->nlay = 0; st->done = 0; st->trivial = 0; st->error = 0; st->ntot_enc = 0;
+}
+void state_init(DevState* st, cudaStream_t s) { state_init_kernel<<<1, 1, 0, s>>>(st); note_launch(1); }
+
+// reference wrappers.cpp:253-266 (mid / half-span, trivial exit) and :292-299 (tolerance)
+__global__ void state_prepare_kernel(DevState* st, double tolrel)
+{
+    double mn = dunkey(st->fmin_key), mx = dunkey(st->fmax_key);
+    double half = (mx - mn) / 2;
+    st->halfspan = half;
+    st->midval = mn + half;
+    if (half <= 2 * DBL_MIN) { st->trivial = 1; st->tolabs = 0; return; }
+    double tolabs = tolrel * fmax(fabs(mn), fabs(mx));
+    tolabs /= WRB_ACC_COEF;
+    st->tolabs = tolabs;
+}
+void state_prepare(DevState* st, double tolrel, cudaStream_t s) { state_prepare_kernel<<<1, 1, 0, s>>>(st, tolrel); note_launch(1); }
+
+// reference wrappers.cpp:316-340
+__global__ void layer_params_kernel(DevState* st, int l)
+{
+    if (st->trivial || st->done) { st->active[l] = 0; return; }
+    double mn = dunkey(st->rmin_key[l]), mx = dunkey(st->rmax_key[l]);
+    st->minval[l] = mn;
+    double deps = (mx - mn) / 255.0;
+    int last = 0;
+    if (deps < st->tolabs) { deps = st->tolabs; last = 1; }
+    if (l >= kNLayMax - 1) last = 1;
+    st->deps[l] = deps;
+    double aopt = 1.0 / deps;
+    st->aopt[l] = aopt;
+    st->bopt[l] = -mn * aopt + 0.5;
+    st->active[l] = 1;
+    st->nlay = l + 1;
+    if (last) st->done = 1;
+}
+void layer_params(DevState* st, int layer, cudaStream_t s) { layer_params_kernel<<<1, 1, 0, s>>>(st, layer); note_launch(1); }
+
+// One CTA per coder block (<= 60000 symbols).  reference wrappers.cpp:384-398 + rangecod.c:389-397
+__global__ void __launch_bounds__(256) quantise_kernel(const double* __restrict__ coef, ChunkGeom g, int layer,
+                                                       DevState* st, uint8_t* __restrict__ sym,
+                                                       uint32_t* __restrict__ hist)
+{
+    if (!st->active[layer]) return;
+    __shared__ uint32_t s_hist[256];
+    __shared__ double s_a[kNLayMax], s_b[kNLayMax], s_d[kNLayMax], s_m[kNLayMax];
+    const int tid = threadIdx.x;
+    s_hist[tid] = 0;
+    if (tid <= layer) { s_a[tid] = st->aopt[tid]; s_b[tid] = st->bopt[tid]; s_d[tid] = st->deps[tid]; s_m[tid] = st->minval[tid]; }
+    __syncthreads();
+    const unsigned int b = blockIdx.x;
+    const unsigned int c = b / g.blocks_per_chunk, kb = b % g.blocks_per_chunk;
+    const unsigned long long cstart = (unsigned long long)c * g.chunk_len;
+    const unsigned long long clen = (g.ntot - cstart < g.chunk_len) ? g.ntot - cstart : g.chunk_len;
+    const unsigned long long boff = (unsigned long long)kb * kBlock;
+    const unsigned int bs = (clen - boff < kBlock) ? (unsigned int)(clen - boff) : kBlock;
+    const double* __restrict__ in = coef + cstart + boff;
+    uint8_t* __restrict__ out = sym + (unsigned long long)c * g.pitch + boff;
+    unsigned long long kmin = kKeyMinInit, kmax = kKeyMaxInit;
+    const unsigned int lane = tid & 31;
+    for (unsigned int i0 = 0; i0 < bs; i0 += 256) {
+        unsigned int i = i0 + tid;
+        bool ok = i < bs;
+        unsigned int q = 0;
+        if (ok) {
+            double r = in[i];
+            for (int m = 0; m < layer; m++) {                // replay earlier layers (:387-398)
+                double fq = s_a[m] * r + s_b[m];
+                unsigned int qm = (unsigned int)(unsigned char)__double2int_rz(fq);
+                r = r - ((double)qm * s_d[m] + s_m[m]);
+            }
+            double fq = s_a[layer] * r + s_b[layer];
+            q = (unsigned int)(unsigned char)__double2int_rz(fq);
+            r = r - ((double)q * s_d[layer] + s_m[layer]);
+            out[i] = (uint8_t)q;
+            unsigned long long k = dkey(r);
+            kmin = k < kmin ? k : kmin;
+            kmax = k > kmax ? k : kmax;
+        }
+        // warp-aggregated histogram update (peaked distributions would serialise plain atomics)
+        unsigned int act = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            unsigned int peers = __match_any_sync(act, q);
+            if ((unsigned int)(__ffs(peers) - 1) == lane) atomicAdd(&s_hist[q], (unsigned int)__popc(peers));
+        }
+    }
+    __syncthreads();
+    hist[(unsigned long long)b * 256 + tid] = s_hist[tid];
+    block_minmax_commit(kmin, kmax, &st->rmin_key[layer + 1], &st->rmax_key[layer + 1]);
+}
+
+void quantise_layer(const double* coef, const ChunkGeom& g, int layer, DevState* st, uint8_t* sym, uint32_t* hist,
+                    cudaStream_t s)
+{
+    quantise_kernel<<<g.nblocks, 256, 0, s>>>(coef, g, layer, st, sym, hist);
+    note_launch(1);
+}
+
+struct DequantParams { double deps[kNLayMax], minval[kNLayMax]; };
+
+// reference wrappers.cpp:480 and :513-514: fld = 0; fld = fld + (q*deps + minval) per layer
+__global__ void __launch_bounds__(256) dequantise_kernel(const uint8_t* __restrict__ sym, unsigned long long layer_stride,
+                                                         ChunkGeom g, int nlay, DequantParams p,
+                                                         double* __restrict__ coef)
+{
+    const unsigned int c = blockIdx.x;
+    const unsigned long long cstart = (unsigned long long)c * g.chunk_len;
+    const unsigned long long clen = (g.ntot - cstart < g.chunk_len) ? g.ntot - cstart : g.chunk_len;
+    const uint8_t* __restrict__ in = sym + (unsigned long long)c * g.pitch;
+    for (unsigned long long i = blockIdx.y * (unsigned long long)blockDim.x + threadIdx.x; i < clen;
+         i += (unsigned long long)gridDim.y * blockDim.x) {
+        double f = 0;
+        for (int l = 0; l < nlay; l++) {
+            double q = (double)in[(unsigned long long)l * layer_stride + i];
+            f = f + (q * p.deps[l] + p.minval[l]);
+        }
+        coef[cstart + i] = f;
+    }
+}
+
+void dequantise(const uint8_t* sym, unsigned long long layer_stride, const ChunkGeom& g, int nlay, const double* deps,
+                const double* minval, double* coef, cudaStream_t s)
+{
+    DequantParams p{};
+    for (int l = 0; l < nlay; l++) { p.deps[l] = deps[l]; p.minval[l] = minval[l]; }
+    unsigned long long per = (g.chunk_len + 255) / 256;
+    unsigned int gy = (unsigned int)(per < 64 ? (per ? per : 1) : 64);
+    if (g.nchunks == 1) gy = (unsigned int)(per < 148 * 32 ? (per ? per : 1) : 148 * 32);
+    dim3 grid(g.nchunks, gy, 1);
+    dequantise_kernel<<<grid, 256, 0, s>>>(sym, layer_stride, g, nlay, p, coef);
+    note_launch(1);
+}
+
+}  // namespace wrb

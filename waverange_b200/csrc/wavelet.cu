@@ -1,0 +1,393 @@
+// wavelet.cu -- 3-D CDF 9/7 lifting transform, general-shape kernels.
+//
+// Replaces waveletcdf97_3d() (reference src/waveletcdf97_3d/waveletcdf97_3d.c:38-468).
+// The reference runs each 1-D lifting over whole lines, in place, one line at a time.  Here
+// every thread produces R consecutive low/high output pairs of one line by evaluating the
+// four lifting stages on a private register window (2R+7 input samples); because each lifting
+// stage only combines neighbours, the window reproduces the whole-line result bit for bit as
+// long as every + and * is rounded separately (-fmad=false) and the line-end formulas
+// (mirror at both ends, extrapolated phantom sample for odd lengths) are applied at the same
+// indices.  Passes are out of place: src -> dst, so no line has to be owned by one CTA.
+//
+// Data flow per level (see codec.cu): x-pass src->A, y-pass A->B, z-pass B->{coefficients,lll};
+// the z-pass routes the low-low-low octant to a compact scratch (input of the next level) and
+// every final coefficient to the coefficient array, reducing their min/max on the way.
+#include "wr_common.cuh"
+#include "wr_kernels.h"
+
+namespace wrb {
+
+// ------------------------------------------------------------------------------------------
+// Forward lifting of output pairs [i0, i0+R) of a line of N > 1 samples.
+// reference: waveletcdf97_3d.c:101-132 (split, phantom :109, stages :112-125, scale :128-132)
+// ------------------------------------------------------------------------------------------
+template <int R, class LD>
+__device__ __forceinline__ void fwd_pairs(LD ld, int N, int i0, double (&so)[R], double (&dd)[R])
+{
+    const int M = (N + 1) >> 1;
+    double s0[R + 4], d0[R + 3];
+#pragma unroll
+    for (int t = 0; t < R + 4; t++) {
+        int j = i0 - 2 + t;
+        s0[t] = (j >= 0 && j < M) ? ld(2 * j) : 0.0;
+    }
+#pragma unroll
+    for (int t = 0; t < R + 3; t++) {
+        int j = i0 - 2 + t;
+        double v = 0.0;
+        if (j >= 0 && 2 * j + 1 < N) v = ld(2 * j + 1);
+        else if (t >= 1 && j == M - 1)            // N odd: phantom sample (:109)
+            v = (s0[t - 1] * WRB_E0 + d0[t >= 1 ? t - 1 : 0] * WRB_E1) + s0[t] * WRB_E2;
+        d0[t] = v;
+    }
+    double d1[R + 3], s1[R + 2], d2[R + 1];
+#pragma unroll
+    for (int t = 0; t < R + 3; t++) {
+        int j = i0 - 2 + t;
+        d1[t] = (j < M - 1) ? d0[t] + WRB_LA * (s0[t + 1] + s0[t]) : d0[t] + (WRB_LA * 2) * s0[t];
+    }
+#pragma unroll
+    for (int t = 0; t < R + 2; t++) {
+        int j = i0 - 1 + t;
+        s1[t] = (j == 0) ? s0[t + 1] + (WRB_LB * 2) * d1[t + 1] : s0[t + 1] + WRB_LB * (d1[t + 1] + d1[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < R + 1; t++) {
+        int j = i0 - 1 + t;
+        d2[t] = (j < M - 1) ? d1[t + 1] + WRB_LC * (s1[t + 1] + s1[t]) : d1[t + 1] + (WRB_LC * 2) * s1[t];
+    }
+#pragma unroll
+    for (int t = 0; t < R; t++) {
+        int j = i0 + t;
+        double s2 = (j == 0) ? s1[t + 1] + (WRB_LD * 2) * d2[t + 1] : s1[t + 1] + WRB_LD * (d2[t + 1] + d2[t]);
+        so[t] = s2 * WRB_SCL;
+        dd[t] = d2[t + 1] * WRB_PSCL;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Inverse lifting: samples x[2j], x[2j+1] for j in [i0, i0+R) of a line of M > 1 coefficients
+// stored low half [0,Q) then high half [Q,M).   reference: waveletcdf97_3d.c:311-337
+// ------------------------------------------------------------------------------------------
+template <int R, class LD>
+__device__ __forceinline__ void inv_pairs(LD ld, int M, int i0, double (&ev)[R], double (&od)[R])
+{
+    const int Q = (M + 1) >> 1, NH = M - Q;
+    double h[R + 4], l[R + 3];
+#pragma unroll
+    for (int t = 0; t < R + 4; t++) {
+        int j = i0 - 2 + t;
+        h[t] = (j >= 0 && j < NH) ? ld(Q + j) * WRB_SCL : 0.0;      // phantom detail = 0 (:314)
+    }
+#pragma unroll
+    for (int t = 0; t < R + 3; t++) {
+        int j = i0 - 1 + t;
+        l[t] = (j >= 0 && j < Q) ? ld(j) * WRB_PSCL : 0.0;
+    }
+    double s1[R + 3], d1[R + 2], s2[R + 1];
+#pragma unroll
+    for (int t = 0; t < R + 3; t++) {
+        int j = i0 - 1 + t;
+        s1[t] = (j == 0) ? l[t] - (WRB_LD * 2) * h[t + 1] : l[t] - WRB_LD * (h[t + 1] + h[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < R + 2; t++) {
+        int j = i0 - 1 + t;
+        d1[t] = (j < Q - 1) ? h[t + 1] - WRB_LC * (s1[t + 1] + s1[t]) : h[t + 1] - (WRB_LC * 2) * s1[t];
+    }
+#pragma unroll
+    for (int t = 0; t < R + 1; t++) {
+        int j = i0 + t;
+        s2[t] = (j == 0) ? s1[t + 1] - (WRB_LB * 2) * d1[t + 1] : s1[t + 1] - WRB_LB * (d1[t + 1] + d1[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < R; t++) {
+        int j = i0 + t;
+        ev[t] = s2[t];
+        od[t] = (j < Q - 1) ? d1[t + 1] - WRB_LA * (s2[t + 1] + s2[t]) : d1[t + 1] - (WRB_LA * 2) * s2[t];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pass kernels.  Thread (tx, ty, tz): for DIM 0 tx indexes groups of R pairs along x; for
+// DIM 1/2 tx indexes x (coalesced) and the group index comes from ty / tz.
+// ------------------------------------------------------------------------------------------
+struct FwdPassArgs {
+    const void* src; long long ssy, ssz;     // input box (x stride 1)
+    double* dst;     long long dsy, dsz;     // output (array strides)
+    double* lll;     long long lsy, lsz;     // DIM 2 only: compact low-low-low scratch (or null)
+    int n0, n1, n2;                          // box extents of this level
+    int m0, m1;                              // low extents in x, y (for lll routing)
+    unsigned long long* in_min;  unsigned long long* in_max;    // reduce over loaded samples (or null)
+    unsigned long long* out_min; unsigned long long* out_max;   // reduce over values stored to dst (or null)
+};
+
+template <int DIM, class TIN, int R>
+__global__ void __launch_bounds__(128) fwd_pass_kernel(FwdPassArgs a)
+{
+    const TIN* __restrict__ src = (const TIN*)a.src;
+    const int nd[3] = {a.n0, a.n1, a.n2};
+    const int N = nd[DIM], M = (N + 1) >> 1;
+    const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ty = blockIdx.y * blockDim.y + threadIdx.y;
+    const int tz = blockIdx.z;
+    int x, y, z, g;
+    if (DIM == 0) { g = tx; x = 0; y = ty; z = tz; }
+    else if (DIM == 1) { x = tx; g = ty; y = 0; z = tz; }
+    else { x = tx; y = ty; g = tz; z = 0; }
+    unsigned long long kmin = kKeyMinInit, kmax = kKeyMaxInit, omin = kKeyMinInit, omax = kKeyMaxInit;
+    const int i0 = g * R;
+    const int ngroups = (N == 1) ? 1 : (M + R - 1) / R;
+    bool live = (g < ngroups) && (DIM == 0 || x < a.n0) && (DIM == 1 || y < a.n1) && (DIM == 2 || z < a.n2);
+    if (live) {
+        const long long sstride = (DIM == 0) ? 1 : (DIM == 1 ? a.ssy : a.ssz);
+        const long long dstride = (DIM == 0) ? 1 : (DIM == 1 ? a.dsy : a.dsz);
+        const long long sbase = x + (long long)y * a.ssy + (long long)z * a.ssz;
+        const long long dbase = x + (long long)y * a.dsy + (long long)z * a.dsz;
+        double so[R], dd[R];
+        const bool track_in = a.in_min != nullptr;
+        auto ld = [&](int j) -> double {
+            double v = (double)src[sbase + (long long)j * sstride];
+            if (track_in) { unsigned long long k = dkey(v); kmin = k < kmin ? k : kmin; kmax = k > kmax ? k : kmax; }
+            return v;
+        };
+        auto st = [&](int j, double v) {        // j = output index along DIM
+            if (DIM == 2 && a.lll != nullptr && x < a.m0 && y < a.m1 && j < M) {
+                a.lll[x + (long long)y * a.lsy + (long long)j * a.lsz] = v;
+            } else {
+                a.dst[dbase + (long long)j * dstride] = v;
+                if (a.out_min != nullptr) { unsigned long long k = dkey(v); omin = k < omin ? k : omin; omax = k > omax ? k : omax; }
+            }
+        };
+        if (N == 1) {
+            st(0, ld(0));                        // direction skipped (waveletcdf97_3d.c:82,146,210)
+        } else {
+            fwd_pairs<R>(ld, N, i0, so, dd);
+#pragma unroll
+            for (int t = 0; t < R; t++) {
+                int j = i0 + t;
+                if (j < M) {
+                    st(j, so[t]);
+                    if (2 * j + 1 < N) st(M + j, dd[t]);
+                }
+            }
+        }
+    }
+    if (a.in_min != nullptr) block_minmax_commit(kmin, kmax, a.in_min, a.in_max);
+    if (a.out_min != nullptr) block_minmax_commit(omin, omax, a.out_min, a.out_max);
+}
+
+struct InvPassArgs {
+    const double* src; long long ssy, ssz;   // input box
+    const double* lll; long long lsy, lsz;   // DIM 2 only: low-low-low octant comes from here (or null)
+    void* dst;         long long dsy, dsz;
+    int n0, n1, n2;                          // box extents of this level
+    int q0, q1, q2;                          // low extents (lll routing)
+};
+
+template <int DIM, class TOUT, int R>
+__global__ void __launch_bounds__(128) inv_pass_kernel(InvPassArgs a)
+{
+    TOUT* __restrict__ dst = (TOUT*)a.dst;
+    const int nd[3] = {a.n0, a.n1, a.n2};
+    const int M = nd[DIM], Q = (M + 1) >> 1;
+    const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ty = blockIdx.y * blockDim.y + threadIdx.y;
+    const int tz = blockIdx.z;
+    int x, y, z, g;
+    if (DIM == 0) { g = tx; x = 0; y = ty; z = tz; }
+    else if (DIM == 1) { x = tx; g = ty; y = 0; z = tz; }
+    else { x = tx; y = ty; g = tz; z = 0; }
+    const int i0 = g * R;
+    const int ngroups = (M == 1) ? 1 : (Q + R - 1) / R;
+    bool live = (g < ngroups) && (DIM == 0 || x < a.n0) && (DIM == 1 || y < a.n1) && (DIM == 2 || z < a.n2);
+    if (!live) return;
+    const long long sstride = (DIM == 0) ? 1 : (DIM == 1 ? a.ssy : a.ssz);
+    const long long dstride = (DIM == 0) ? 1 : (DIM == 1 ? a.dsy : a.dsz);
+    const long long sbase = x + (long long)y * a.ssy + (long long)z * a.ssz;
+    const long long dbase = x + (long long)y * a.dsy + (long long)z * a.dsz;
+    auto ld = [&](int j) -> double {
+        if (DIM == 2 && a.lll != nullptr && x < a.q0 && y < a.q1 && j < a.q2)
+            return a.lll[x + (long long)y * a.lsy + (long long)j * a.lsz];
+        return a.src[sbase + (long long)j * sstride];
+    };
+    if (M == 1) { dst[dbase] = (TOUT)ld(0); return; }
+    double ev[R], od[R];
+    inv_pairs<R>(ld, M, i0, ev, od);
+#pragma unroll
+    for (int t = 0; t < R; t++) {
+        int j = i0 + t;
+        if (j < Q) {
+            dst[dbase + (long long)(2 * j) * dstride] = (TOUT)ev[t];
+            if (2 * j + 1 < M) dst[dbase + (long long)(2 * j + 1) * dstride] = (TOUT)od[t];
+        }
+    }
+}
+
+// widen / copy with min-max (wtflag == 0 path: the "transform" is the identity)
+template <class TIN>
+__global__ void __launch_bounds__(256) widen_minmax_kernel(const TIN* __restrict__ src, double* __restrict__ dst,
+                                                           unsigned long long n, unsigned long long* in_min,
+                                                           unsigned long long* in_max, unsigned long long* out_min,
+                                                           unsigned long long* out_max)
+{
+    unsigned long long kmin = kKeyMinInit, kmax = kKeyMaxInit;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        double v = (double)src[i];
+        dst[i] = v;
+        unsigned long long k = dkey(v);
+        kmin = k < kmin ? k : kmin;
+        kmax = k > kmax ? k : kmax;
+    }
+    block_minmax_commit(kmin, kmax, in_min, in_max);
+    if (out_min != nullptr) block_minmax_commit(kmin, kmax, out_min, out_max);
+}
+
+template <class TOUT>
+__global__ void __launch_bounds__(256) narrow_copy_kernel(const double* __restrict__ src, TOUT* __restrict__ dst,
+                                                          unsigned long long n)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        dst[i] = (TOUT)src[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------
+constexpr int kR = 4;
+
+static void pass_geometry(int dim, int nx_threads, int n_second, int n_third, dim3& grid, dim3& block)
+{
+    int bx = 128;
+    while (bx > 32 && bx / 2 >= nx_threads) bx >>= 1;
+    int by = 128 / bx;
+    block = dim3(bx, by, 1);
+    grid = dim3((nx_threads + bx - 1) / bx, (n_second + by - 1) / by, n_third);
+    (void)dim;
+}
+
+template <int DIM, class TIN>
+static void launch_fwd_pass(const FwdPassArgs& a, cudaStream_t s)
+{
+    const int nd[3] = {a.n0, a.n1, a.n2};
+    int N = nd[DIM], M = (N + 1) / 2;
+    int groups = (N == 1) ? 1 : (M + kR - 1) / kR;
+    dim3 grid, block;
+    if (DIM == 0) pass_geometry(0, groups, a.n1, a.n2, grid, block);
+    else if (DIM == 1) pass_geometry(1, a.n0, groups, a.n2, grid, block);
+    else pass_geometry(2, a.n0, a.n1, groups, grid, block);
+    fwd_pass_kernel<DIM, TIN, kR><<<grid, block, 0, s>>>(a);
+    note_launch(1);
+}
+
+template <int DIM, class TOUT>
+static void launch_inv_pass(const InvPassArgs& a, cudaStream_t s)
+{
+    const int nd[3] = {a.n0, a.n1, a.n2};
+    int M = nd[DIM], Q = (M + 1) / 2;
+    int groups = (M == 1) ? 1 : (Q + kR - 1) / kR;
+    dim3 grid, block;
+    if (DIM == 0) pass_geometry(0, groups, a.n1, a.n2, grid, block);
+    else if (DIM == 1) pass_geometry(1, a.n0, groups, a.n2, grid, block);
+    else pass_geometry(2, a.n0, a.n1, groups, grid, block);
+    inv_pass_kernel<DIM, TOUT, kR><<<grid, block, 0, s>>>(a);
+    note_launch(1);
+}
+
+static inline int half_up(int n) { return (n + 1) / 2; }
+
+// Forward transform, `levels` levels.  src: raw field (f32 or f64, array strides nx, nx*ny).
+// coef: coefficient array (array strides), tmp: scratch of the same size, lllA/lllB: compact
+// scratches for the low-low-low octants (>= ceil(n/2)^3 and ceil(n/4)^3 doubles).
+// Field extrema -> st->fmin/fmax keys, coefficient extrema -> st->rmin_key[0]/rmax_key[0].
+void wavelet_forward(const void* src, int src_is_f32, double* coef, double* tmp, double* lllA, double* lllB,
+                     int nx, int ny, int nz, int levels, DevState* st, cudaStream_t s)
+{
+    const long long ay = nx, az = (long long)nx * ny;
+    unsigned long long* fmin = &st->fmin_key; unsigned long long* fmax = &st->fmax_key;
+    unsigned long long* cmin = &st->rmin_key[0]; unsigned long long* cmax = &st->rmax_key[0];
+    if (levels == 0) {
+        unsigned long long n = (unsigned long long)nx * ny * nz;
+        int blocks = (int)((n + 256ull * 8 - 1) / (256ull * 8));
+        if (blocks < 1) blocks = 1;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        if (src_is_f32) widen_minmax_kernel<float><<<blocks, 256, 0, s>>>((const float*)src, coef, n, fmin, fmax, cmin, cmax);
+        else widen_minmax_kernel<double><<<blocks, 256, 0, s>>>((const double*)src, coef, n, fmin, fmax, cmin, cmax);
+        note_launch(1);
+        return;
+    }
+    int n0 = nx, n1 = ny, n2 = nz;
+    const void* cur = src; long long csy = ay, csz = az;   // level input
+    bool cur_f32 = src_is_f32 != 0;
+    for (int k = 1; k <= levels; k++) {
+        const int m0 = half_up(n0), m1 = half_up(n1), m2 = half_up(n2);
+        const bool last = (k == levels);
+        double* lll = last ? nullptr : ((k & 1) ? lllA : lllB);
+        FwdPassArgs a{};
+        a.n0 = n0; a.n1 = n1; a.n2 = n2; a.m0 = m0; a.m1 = m1;
+        // x: cur -> coef (box region used as scratch)
+        a.src = cur; a.ssy = csy; a.ssz = csz; a.dst = coef; a.dsy = ay; a.dsz = az;
+        a.in_min = (k == 1) ? fmin : nullptr; a.in_max = (k == 1) ? fmax : nullptr;
+        if (cur_f32) launch_fwd_pass<0, float>(a, s); else launch_fwd_pass<0, double>(a, s);
+        // y: coef -> tmp
+        a.in_min = a.in_max = nullptr;
+        a.src = coef; a.ssy = ay; a.ssz = az; a.dst = tmp; a.dsy = ay; a.dsz = az;
+        launch_fwd_pass<1, double>(a, s);
+        // z: tmp -> coef (+ lll)
+        a.src = tmp; a.dst = coef; a.lll = lll; a.lsy = m0; a.lsz = (long long)m0 * m1;
+        a.out_min = cmin; a.out_max = cmax;
+        launch_fwd_pass<2, double>(a, s);
+        cur = lll; csy = m0; csz = (long long)m0 * m1; cur_f32 = false;
+        n0 = m0; n1 = m1; n2 = m2;
+    }
+}
+
+static inline int ceil_shift(int n, int k) { return (int)(((long long)n + (1ll << k) - 1) >> k); }
+
+// Inverse transform.  coef: coefficient array (destroyed), tmp: scratch, out: result (f32/f64,
+// array strides).  reference: waveletcdf97_3d.c:281-466 (levels coarsest first, z then y then x)
+void wavelet_inverse(double* coef, double* tmp, double* lllA, double* lllB, void* out, int out_is_f32,
+                     int nx, int ny, int nz, int levels, cudaStream_t s)
+{
+    const long long ay = nx, az = (long long)nx * ny;
+    if (levels == 0) {
+        unsigned long long n = (unsigned long long)nx * ny * nz;
+        int blocks = (int)((n + 256ull * 8 - 1) / (256ull * 8));
+        if (blocks < 1) blocks = 1;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        if (out_is_f32) narrow_copy_kernel<float><<<blocks, 256, 0, s>>>(coef, (float*)out, n);
+        else narrow_copy_kernel<double><<<blocks, 256, 0, s>>>(coef, (double*)out, n);
+        note_launch(1);
+        return;
+    }
+    const double* lll = nullptr; long long lsy = 0, lsz = 0;
+    for (int k = levels - 1; k >= 0; k--) {
+        const int n0 = ceil_shift(nx, k), n1 = ceil_shift(ny, k), n2 = ceil_shift(nz, k);
+        const int q0 = half_up(n0), q1 = half_up(n1), q2 = half_up(n2);
+        InvPassArgs a{};
+        a.n0 = n0; a.n1 = n1; a.n2 = n2; a.q0 = q0; a.q1 = q1; a.q2 = q2;
+        // z: coef (+lll) -> tmp
+        a.src = coef; a.ssy = ay; a.ssz = az; a.lll = lll; a.lsy = lsy; a.lsz = lsz;
+        a.dst = tmp; a.dsy = ay; a.dsz = az;
+        launch_inv_pass<2, double>(a, s);
+        // y: tmp -> coef
+        a.lll = nullptr;
+        a.src = tmp; a.dst = coef;
+        launch_inv_pass<1, double>(a, s);
+        // x: coef -> next lll (compact) or the output array
+        a.src = coef;
+        if (k == 0) {
+            a.dst = out; a.dsy = ay; a.dsz = az;
+            if (out_is_f32) launch_inv_pass<0, float>(a, s); else launch_inv_pass<0, double>(a, s);
+        } else {
+            double* nxt = (k & 1) ? lllA : lllB;
+            a.dst = nxt; a.dsy = n0; a.dsz = (long long)n0 * n1;
+            launch_inv_pass<0, double>(a, s);
+            lll = nxt; lsy = n0; lsz = (long long)n0 * n1;
+        }
+    }
+}
+
+}  // namespace wrb

@@ -1,0 +1,56 @@
+// wr_kernels.h -- internal launcher interface between codec.cu and the kernel files.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "wr_common.cuh"
+
+namespace wrb {
+
+// ---- wavelet.cu ---------------------------------------------------------------------------
+void wavelet_forward(const void* src, int src_is_f32, double* coef, double* tmp, double* lllA, double* lllB,
+                     int nx, int ny, int nz, int levels, DevState* st, cudaStream_t s);
+void wavelet_inverse(double* coef, double* tmp, double* lllA, double* lllB, void* out, int out_is_f32,
+                     int nx, int ny, int nz, int levels, cudaStream_t s);
+
+// ---- quant.cu -----------------------------------------------------------------------------
+// Geometry of the chunked symbol container of one layer.
+//   chunk c covers symbols [c*chunk_len, min(ntot,(c+1)*chunk_len)); each chunk is cut into coder
+//   blocks of 60000 symbols exactly as the reference's range_encode() cuts a whole array
+//   (wrappers.cpp:85-128: a chunk whose length is a multiple of 60000 ends with an EMPTY block).
+//   Symbols are kept chunk-major with a padded pitch so that every chunk starts 16-byte aligned.
+struct ChunkGeom {
+    unsigned long long ntot;        // symbols per layer
+    unsigned long long chunk_len;   // symbols per chunk (last chunk may be shorter)
+    unsigned long long pitch;       // bytes between chunk starts in the symbol buffer (multiple of 16)
+    unsigned int nchunks;
+    unsigned int blocks_per_chunk;  // coder blocks in a full chunk (incl. a possible empty one)
+    unsigned int nblocks;           // total coder blocks in the layer
+};
+ChunkGeom make_geom(unsigned long long ntot, unsigned long long chunk_len);
+
+void state_init(DevState* st, cudaStream_t s);
+void state_prepare(DevState* st, double tolrel, cudaStream_t s);          // after field extrema are known
+void layer_params(DevState* st, int layer, cudaStream_t s);                // before quantising `layer`
+void quantise_layer(const double* coef, const ChunkGeom& g, int layer, DevState* st, uint8_t* sym,
+                    uint32_t* hist, cudaStream_t s);
+void dequantise(const uint8_t* sym, unsigned long long layer_stride, const ChunkGeom& g, int nlay,
+                const double* deps, const double* minval, double* coef, cudaStream_t s);
+
+// ---- rangecoder.cu ------------------------------------------------------------------------
+// slot_pitch: bytes reserved per chunk in the scratch output (worst case 2 B/symbol + tables)
+unsigned long long chunk_slot_pitch(const ChunkGeom& g);
+void range_encode_chunks(const uint8_t* sym, unsigned long long sym_layer_stride, const uint32_t* hist,
+                         unsigned long long hist_layer_stride, const ChunkGeom& g, int nlayers, const int* active,
+                         uint8_t* slots, unsigned long long slot_pitch, unsigned long long* lens, cudaStream_t s);
+void assemble_container(const uint8_t* slots, unsigned long long slot_pitch, const unsigned long long* lens,
+                        const ChunkGeom& g, int chunked, DevState* st, uint8_t* blob, unsigned long long cap,
+                        unsigned long long* dst_off, cudaStream_t s);
+void parse_container(const uint8_t* blob, const ChunkGeom& g, int chunked, int nlay, const unsigned long long* lay_off,
+                     unsigned long long* offs, int* error, cudaStream_t s);
+void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, const ChunkGeom& g, int nlay, uint8_t* sym,
+                         unsigned long long sym_layer_stride, int* error, cudaStream_t s);
+
+// ---- codec.cu -----------------------------------------------------------------------------
+void note_launch(int n);   // kernel-launch accounting (wrb_launch_count)
+
+}  // namespace wrb
