@@ -187,7 +187,7 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    n = N_FIELD
+    n = args.size
     nz = ny = nx = n
     ntot = n ** 3
     field = synth_field(torch, n, 1234 + rank, dev, torch.float32)
@@ -252,7 +252,7 @@ def run_ours(args, rank, world, local_rank):
     h_rec = torch.empty((n, n, n), dtype=torch.float32, pin_memory=True)
     np_field, np_blob, np_rec = h_field.numpy(), h_blob.numpy(), h_rec.numpy()
     e2e_ms = []
-    for it in range(max(1, min(args.warmup, 2)) + args.steps):
+    for it in range(0 if args.no_e2e else max(1, min(args.warmup, 2)) + args.steps):
         barrier()
         t0 = time.perf_counter()
         hh, data = codec.encode_host(np_field, TOL, out=np_blob)
@@ -261,8 +261,9 @@ def run_ours(args, rank, world, local_rank):
         t1 = time.perf_counter()
         if it >= max(1, min(args.warmup, 2)):
             e2e_ms.append((t1 - t0) * 1e3)
-    e2e_step = statistics.mean(e2e_ms)
-    assert np.array_equal(np_rec.ravel()[:4096], recon[:4096].cpu().numpy())
+    e2e_step = statistics.mean(e2e_ms) if e2e_ms else float('nan')
+    if e2e_ms:
+        assert np.array_equal(np_rec.ravel()[:4096], recon[:4096].cpu().numpy())
 
     # ---- max over ranks ------------------------------------------------------------------------
     vals = torch.tensor([step_ms, statistics.mean(enc_ms), statistics.mean(dec_ms), e2e_step], device=dev, dtype=torch.float64)
@@ -285,7 +286,7 @@ def run_ours(args, rank, world, local_rank):
     # CPU baseline on a bounded sample of the same workload (rank 0, N = 1 only)
     cpu = None
     if world == 1 and not args.no_cpu:
-        sample = field[:SAMPLE, :SAMPLE, :SAMPLE].contiguous().cpu().numpy().astype(np.float64)
+        sample = field[:min(n, SAMPLE), :min(n, SAMPLE), :min(n, SAMPLE)].contiguous().cpu().numpy().astype(np.float64)
         kind, te, td, _ = cpu_time_sample(sample, TOL)
         cpu = {"value": 2 * sample.size * 4 / (te + td) / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
                "sample": "%d^3 sub-cube of the same field, encoding_wrap %.2f s + decoding_wrap %.2f s, 1 thread "
@@ -295,7 +296,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "512^3 float32 turbulence-like field, tol 1e-4 (BASELINE.json configs[1])",
+        "config": {"workload": "%d^3 float32 turbulence-like field, tol 1e-4%s" % (n, " (BASELINE.json configs[1])" if n == N_FIELD else " (profiling size)"),
                    "field_bytes": nbytes, "tolerance": TOL, "nlay": nlay, "ntot_enc": int(h.ntot_enc),
                    "ratio_vs_f32": nbytes / max(1, int(h.ntot_enc)), "chunk_symbols": 59999,
                    "fields": "%d independent field(s), one per GPU" % world,
@@ -328,6 +329,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--size", type=int, default=N_FIELD, help="field edge (default 512 = BASELINE configs[1]; other sizes are for profiling only)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (profiling only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

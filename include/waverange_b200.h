@@ -61,12 +61,16 @@ const char* wrb_last_error(const wrb_codec* c);
 int wrb_set_stream(wrb_codec* c, void* cuda_stream);
 /* Chunking of each layer's symbol sequence for the parallel range coder.
  *   blocks >= 1: chunk length = blocks*60000 - 1 symbols (default 1).  Each layer is stored as a
- *                "WRCK" container: 32-byte header, u32 byte length per chunk, then the chunk
- *                streams; every chunk stream is byte-identical to the reference's range_encode()
+ *                "WRCK" container: 32-byte header, u32 byte length per chunk, seek table, then the
+ *                chunk streams; every chunk stream is byte-identical to the reference's range_encode()
  *                (wrappers.cpp:68-149) of that symbol sub-array.
  *   blocks == 0: one stream per layer, byte-identical to the reference's encoding_wrap() output
  *                (readable by the stock wrdec); serial on the GPU, for interoperability only. */
 int wrb_set_chunk_blocks(wrb_codec* c, int blocks);
+/* Seek points per chunk (0..15, default 3): the encoder stores (low, range, stream position) at
+ * n interior symbol positions of every single-block chunk, 12 bytes each, in the container's
+ * seek table; the decoder then runs n+1 lanes per chunk.  Chunk streams are unaffected. */
+int wrb_set_seek_points(wrb_codec* c, int n);
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 unsigned long long wrb_launch_count(const wrb_codec* c);
 /* Release cached device scratch (it is otherwise kept and grown on demand). */
@@ -84,7 +88,7 @@ void wrb_setup(int nx, int ny, int nz, unsigned char* nlaymax, unsigned long* nt
 int wrb_encode_device(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag,
                       double tolrel, wrb_header* hdr, unsigned char* d_data_enc, unsigned long cap);
 /* Decompress: replaces decoding_wrap() (reference wrappers.cpp:456-527).  d_data_enc holds
- * hdr->ntot_enc bytes followed by at least 16 readable bytes.  d_field_out is f64 or f32. */
+ * hdr->ntot_enc bytes followed by at least 32 readable bytes, and is 8-byte aligned.  d_field_out is f64 or f32. */
 int wrb_decode_device(wrb_codec* c, void* d_field_out, int dtype, int nx, int ny, int nz, const wrb_header* hdr,
                       const unsigned char* d_data_enc);
 

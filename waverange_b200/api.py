@@ -44,7 +44,7 @@ class WaveRangeError(RuntimeError):
 _lib = None
 
 # every symbol include/waverange_b200.h and include/waverange.h declare
-EXPORTS = ["wrb_create", "wrb_destroy", "wrb_last_error", "wrb_set_stream", "wrb_set_chunk_blocks",
+EXPORTS = ["wrb_create", "wrb_destroy", "wrb_last_error", "wrb_set_stream", "wrb_set_chunk_blocks", "wrb_set_seek_points",
            "wrb_launch_count", "wrb_trim", "wrb_setup", "wrb_encode_device", "wrb_decode_device",
            "wrb_encode_host", "wrb_decode_host", "wrb_wavelet3d_device", "wrb_quantise_device",
            "wrb_range_encode_device", "wrb_range_decode_device", "wrb_ind_p2w_3d", "wrb_set_timing",
@@ -69,6 +69,7 @@ def lib():
     L.wrb_last_error.restype = C.c_char_p
     L.wrb_set_stream.argtypes = [vp, vp]
     L.wrb_set_chunk_blocks.argtypes = [vp, i]
+    L.wrb_set_seek_points.argtypes = [vp, i]
     L.wrb_launch_count.argtypes = [vp]
     L.wrb_launch_count.restype = C.c_ulonglong
     L.wrb_trim.argtypes = [vp]
@@ -162,10 +163,12 @@ def parse_container(layer_bytes):
     b = bytes(layer_bytes)
     if b[:4] != b"WRCK":
         return 0, [b]
+    assert int.from_bytes(b[4:8], "little") == 2, "container version"
     chunk_len = int.from_bytes(b[8:16], "little")
     nch = int.from_bytes(b[24:28], "little")
+    nseek = int.from_bytes(b[28:32], "little")
     lens = np.frombuffer(b, dtype="<u4", count=nch, offset=32)
-    off = 32 + 4 * nch
+    off = 32 + 4 * nch + 12 * nseek * nch
     out = []
     for n in lens:
         out.append(b[off:off + int(n)])
@@ -209,6 +212,9 @@ class Codec:
 
     def set_chunk_blocks(self, k):
         self._ck(self.L.wrb_set_chunk_blocks(self.h, k))
+
+    def set_seek_points(self, n):
+        self._ck(self.L.wrb_set_seek_points(self.h, n))
 
     def set_timing(self, on):
         self._ck(self.L.wrb_set_timing(self.h, int(on)))

@@ -43,8 +43,9 @@ struct wrb_codec {
     int device = 0;
     cudaStream_t stream = nullptr;
     int chunk_blocks = 1;
+    int seek_points = 3;             // decoder entry points inside a chunk (4 lanes decode one chunk)
     std::string err;
-    DevBuf coef, tmp, lllA, lllB, sym, hist, slots, lens, dstoff, state, blob, field, offs, layoff, misc;
+    DevBuf coef, tmp, lllA, lllB, sym, hist, slots, lens, dstoff, seek, state, blob, field, offs, layoff, misc;
     DevState* h_state = nullptr;      // pinned
     unsigned long long* h_u64 = nullptr;   // pinned scratch (64 KiB)
     int timing = 0;
@@ -90,6 +91,8 @@ int wrb_create(wrb_codec** out, int device)
     for (int i = 0; i < 5; i++) cudaEventCreate(&c->ev[i]);
     const char* env = getenv("WRB_CHUNK_BLOCKS");
     if (env && *env) { int v = atoi(env); if (v >= 0) c->chunk_blocks = v; }
+    env = getenv("WRB_SEEK_POINTS");
+    if (env && *env) { int v = atoi(env); if (v >= 0 && v <= 15) c->seek_points = v; }
     *out = c;
     return 0;
 }
@@ -99,7 +102,7 @@ int wrb_trim(wrb_codec* c)
     if (!c) return WRB_E_ARG;
     cudaSetDevice(c->device);
     DevBuf* all[] = {&c->coef, &c->tmp, &c->lllA, &c->lllB, &c->sym, &c->hist, &c->slots, &c->lens,
-                     &c->dstoff, &c->blob, &c->field, &c->offs, &c->layoff, &c->misc};
+                     &c->dstoff, &c->seek, &c->blob, &c->field, &c->offs, &c->layoff, &c->misc};
     for (DevBuf* b : all) b->release();
     return 0;
 }
@@ -118,6 +121,7 @@ void wrb_destroy(wrb_codec* c)
 const char* wrb_last_error(const wrb_codec* c) { return c ? c->err.c_str() : "null codec"; }
 int wrb_set_stream(wrb_codec* c, void* s) { if (!c) return WRB_E_ARG; c->stream = (cudaStream_t)s; return 0; }
 int wrb_set_chunk_blocks(wrb_codec* c, int b) { if (!c || b < 0) return WRB_E_ARG; c->chunk_blocks = b; return 0; }
+int wrb_set_seek_points(wrb_codec* c, int n) { if (!c || n < 0 || n > 15) return WRB_E_ARG; c->seek_points = n; return 0; }
 unsigned long long wrb_launch_count(const wrb_codec*) { return g_launches.load(); }
 int wrb_set_timing(wrb_codec* c, int on) { if (!c) return WRB_E_ARG; c->timing = on; return 0; }
 int wrb_last_stage_ms(const wrb_codec* c, float ms[4])
@@ -222,6 +226,7 @@ static int ensure_coder_buffers(wrb_codec* c, const ChunkGeom& g, int nlayers, b
         CK(c->slots.ensure((size_t)nlayers * g.nchunks * chunk_slot_pitch(g)));
         CK(c->lens.ensure((size_t)nlayers * g.nchunks * 8));
         CK(c->dstoff.ensure((size_t)nlayers * g.nchunks * 8));
+        CK(c->seek.ensure((size_t)nlayers * g.nchunks * (g.nseek ? g.nseek : 1) * 12 + 64));
     }
     CK(c->offs.ensure((size_t)nlayers * g.nchunks * 8 + 64));
     CK(c->layoff.ensure(16 * 8));
@@ -280,7 +285,7 @@ int wrb_encode_device(wrb_codec* c, const void* d_field, int dtype, int nx, int 
         return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
     CK(cudaSetDevice(c->device));
     const unsigned long long ntot = (unsigned long long)nx * ny * nz;
-    const ChunkGeom g = make_geom(ntot, chunk_len_of(c));
+    const ChunkGeom g = make_geom(ntot, chunk_len_of(c), (unsigned)c->seek_points);
     const int chunked = c->chunk_blocks > 0;
     int rc;
     if ((rc = ensure_transform_buffers(c, nx, ny, nz))) return rc;
@@ -292,10 +297,10 @@ int wrb_encode_device(wrb_codec* c, const void* d_field, int dtype, int nx, int 
     const unsigned long long hstride = (unsigned long long)g.nblocks * 256;
     const unsigned long long sp = chunk_slot_pitch(g);
     range_encode_chunks((const uint8_t*)c->sym.p, lstride, (const uint32_t*)c->hist.p, hstride, g, kNLayMax, st->active,
-                        (uint8_t*)c->slots.p, sp, (unsigned long long*)c->lens.p, s);
+                        (uint8_t*)c->slots.p, sp, (unsigned long long*)c->lens.p, (uint32_t*)c->seek.p, s);
     if (c->timing) cudaEventRecord(c->ev[3], s);
-    assemble_container((const uint8_t*)c->slots.p, sp, (const unsigned long long*)c->lens.p, g, chunked, st,
-                       d_data_enc, cap, (unsigned long long*)c->dstoff.p, s);
+    assemble_container((const uint8_t*)c->slots.p, sp, (const unsigned long long*)c->lens.p, (const uint32_t*)c->seek.p, g,
+                       chunked, st, d_data_enc, cap, (unsigned long long*)c->dstoff.p, s);
     if (c->timing) cudaEventRecord(c->ev[4], s);
     CK(cudaMemcpyAsync(c->h_state, st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -313,7 +318,7 @@ int wrb_quantise_device(wrb_codec* c, const void* d_field, int dtype, int nx, in
         return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
     CK(cudaSetDevice(c->device));
     const unsigned long long ntot = (unsigned long long)nx * ny * nz;
-    const ChunkGeom g = make_geom(ntot, chunk_len_of(c));
+    const ChunkGeom g = make_geom(ntot, chunk_len_of(c), (unsigned)c->seek_points);
     int rc;
     if ((rc = ensure_transform_buffers(c, nx, ny, nz))) return rc;
     if ((rc = ensure_coder_buffers(c, g, kNLayMax, false))) return rc;
@@ -364,18 +369,19 @@ int wrb_decode_device(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int 
     CK(cudaMemcpyAsync(peek, d_data_enc, npeek, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     int chunked = 0;
-    unsigned long long chunk_len = 0;
+    unsigned long long chunk_len = 0, nseek = 0;
     if (npeek >= 32 && peek[0] == 'W' && peek[1] == 'R' && peek[2] == 'C' && peek[3] == 'K') {
         chunked = 1;
-        unsigned long long nsym = 0, nch = 0;
+        unsigned long long nsym = 0, nch = 0, ver = 0;
         for (int k = 0; k < 8; k++) { chunk_len |= (unsigned long long)peek[8 + k] << (8 * k); nsym |= (unsigned long long)peek[16 + k] << (8 * k); }
-        for (int k = 0; k < 4; k++) nch |= (unsigned long long)peek[24 + k] << (8 * k);
-        if (nsym != ntot || chunk_len == 0 || chunk_len > ntot || nch != (ntot + chunk_len - 1) / chunk_len)
+        for (int k = 0; k < 4; k++) { ver |= (unsigned long long)peek[4 + k] << (8 * k); nch |= (unsigned long long)peek[24 + k] << (8 * k); nseek |= (unsigned long long)peek[28 + k] << (8 * k); }
+        if (ver != 2 || nsym != ntot || chunk_len == 0 || chunk_len > ntot || nch != (ntot + chunk_len - 1) / chunk_len || nseek > 15)
             return fail(c, WRB_E_FORMAT, "chunk container header does not match the field size");
     } else if (npeek >= 1 && peek[0] != 0x00) {
         return fail(c, WRB_E_FORMAT, "layer is neither a WRCK container nor a reference stream");
     }
-    const ChunkGeom g = make_geom(ntot, chunk_len);
+    const ChunkGeom g = make_geom(ntot, chunk_len, (unsigned)nseek);
+    if (g.nseek != nseek) return fail(c, WRB_E_FORMAT, "seek table does not match the chunk geometry");
     int rc;
     if ((rc = ensure_transform_buffers(c, nx, ny, nz))) return rc;
     if ((rc = ensure_coder_buffers(c, g, nlay, false))) return rc;
@@ -385,7 +391,8 @@ int wrb_decode_device(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int 
     parse_container(d_data_enc, g, chunked, nlay, (const unsigned long long*)c->layoff.p, (unsigned long long*)c->offs.p, d_err, s);
     if (c->timing) cudaEventRecord(c->ev[1], s);
     const unsigned long long lstride = (unsigned long long)g.nchunks * g.pitch;
-    range_decode_chunks(d_data_enc, (const unsigned long long*)c->offs.p, g, nlay, (uint8_t*)c->sym.p, lstride, d_err, s);
+    range_decode_chunks(d_data_enc, (const unsigned long long*)c->offs.p, (const unsigned long long*)c->layoff.p, g, nlay,
+                        (uint8_t*)c->sym.p, lstride, d_err, s);
     if (c->timing) cudaEventRecord(c->ev[2], s);
     dequantise((const uint8_t*)c->sym.p, lstride, g, nlay, hdr->deps_vec, hdr->minval_vec, (double*)c->coef.p, s);
     if (c->timing) cudaEventRecord(c->ev[3], s);
@@ -470,7 +477,7 @@ int wrb_range_encode_device(wrb_codec* c, const unsigned char* d_sym, unsigned l
 {
     if (!c || !d_sym || !d_out || n < 1) return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
     CK(cudaSetDevice(c->device));
-    const ChunkGeom g = make_geom(n, chunk_len);
+    const ChunkGeom g = make_geom(n, chunk_len, 0);
     int rc;
     if ((rc = ensure_coder_buffers(c, g, 1, true))) return rc;
     cudaStream_t s = c->stream;
@@ -481,9 +488,9 @@ int wrb_range_encode_device(wrb_codec* c, const unsigned char* d_sym, unsigned l
     note_launch(2);
     const unsigned long long sp = chunk_slot_pitch(g);
     range_encode_chunks((const uint8_t*)c->sym.p, 0, (const uint32_t*)c->hist.p, 0, g, 1, nullptr, (uint8_t*)c->slots.p, sp,
-                        (unsigned long long*)c->lens.p, s);
-    assemble_container((const uint8_t*)c->slots.p, sp, (const unsigned long long*)c->lens.p, g, 0, st, d_out, cap,
-                       (unsigned long long*)c->dstoff.p, s);
+                        (unsigned long long*)c->lens.p, (uint32_t*)c->seek.p, s);
+    assemble_container((const uint8_t*)c->slots.p, sp, (const unsigned long long*)c->lens.p, (const uint32_t*)c->seek.p, g, 0,
+                       st, d_out, cap, (unsigned long long*)c->dstoff.p, s);
     CK(cudaMemcpyAsync(c->h_state, st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
     if (lens) {
         if ((size_t)g.nchunks * 8 <= 65536 - 2048) {
@@ -507,7 +514,7 @@ int wrb_range_decode_device(wrb_codec* c, const unsigned char* d_in, const unsig
 {
     if (!c || !d_in || !lens || !d_sym || n < 1) return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
     CK(cudaSetDevice(c->device));
-    const ChunkGeom g = make_geom(n, chunk_len);
+    const ChunkGeom g = make_geom(n, chunk_len, 0);
     int rc;
     if ((rc = ensure_coder_buffers(c, g, 1, false))) return rc;
     cudaStream_t s = c->stream;
@@ -521,7 +528,7 @@ int wrb_range_decode_device(wrb_codec* c, const unsigned char* d_in, const unsig
     cudaError_t e3 = cudaStreamSynchronize(s);
     free(offs);
     CK(e1); CK(e2); CK(e3);
-    range_decode_chunks(d_in, (const unsigned long long*)c->offs.p, g, 1, (uint8_t*)c->sym.p, 0, d_err, s);
+    range_decode_chunks(d_in, (const unsigned long long*)c->offs.p, nullptr, g, 1, (uint8_t*)c->sym.p, 0, d_err, s);
     unsigned long long per = (g.chunk_len + 255) / 256;
     unsigned int gy = (unsigned int)(per < 64 ? (per ? per : 1) : 64);
     dim3 grid(g.nchunks, gy, 1);

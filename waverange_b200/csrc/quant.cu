@@ -16,7 +16,7 @@
 
 namespace wrb {
 
-ChunkGeom make_geom(unsigned long long ntot, unsigned long long chunk_len)
+ChunkGeom make_geom(unsigned long long ntot, unsigned long long chunk_len, unsigned int nseek_req)
 {
     ChunkGeom g{};
     g.ntot = ntot;
@@ -26,6 +26,15 @@ ChunkGeom make_geom(unsigned long long ntot, unsigned long long chunk_len)
     g.blocks_per_chunk = (unsigned int)(g.chunk_len / kBlock + 1);
     unsigned long long last = ntot - (unsigned long long)(g.nchunks - 1) * g.chunk_len;
     g.nblocks = (g.nchunks - 1) * g.blocks_per_chunk + (unsigned int)(last / kBlock + 1);
+    g.nseek = 0;
+    g.sub_len = 0;
+    if (nseek_req > 0 && g.blocks_per_chunk == 1 && g.chunk_len >= 64ull * (nseek_req + 1)) {
+        g.nseek = nseek_req;
+        unsigned long long sub = (g.chunk_len + nseek_req) / (nseek_req + 1);      // ceil(chunk_len / nsub)
+        g.sub_len = (unsigned int)((sub + 15ull) & ~15ull);
+        while (g.nseek > 0 && (unsigned long long)g.nseek * g.sub_len >= g.chunk_len) g.nseek--;   // drop empty tails
+        if (g.nseek == 0) g.sub_len = 0;
+    }
     return g;
 }
 

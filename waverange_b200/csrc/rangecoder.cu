@@ -8,9 +8,21 @@
 // contiguous run of chunk_len symbols of a layer, coded as an independent stream that is byte
 // for byte what the reference's range_encode() produces for that sub-array (lead byte 00,
 // per-60000-symbol block: 1-of-2 marker, 256 raw 16-bit counts, symbols against the static
-// cumulative table; end marker; 5-byte flush).  One GPU thread owns one chunk (32 chunks per
-// warp); per-lane frequency tables sit in shared memory laid out [symbol][lane] so the
-// data-dependent lookups of a warp never bank-conflict.  All arithmetic is u32, bit-exact.
+// cumulative table; end marker; 5-byte flush).  One GPU thread owns one chunk; per-lane
+// frequency tables sit in shared memory laid out [symbol][lane] so the data-dependent lookups of
+// a warp never bank-conflict.  All coder arithmetic is u32, bit-exact.
+//
+// Three things keep the serial chain short (a lone warp pays ~4 cycles per dependent instruction):
+//  * k-step renormalisation: for tot <= 60000 the quotient r = range/tot is >= 139, so at most two
+//    byte shifts are pending before a symbol; k is computed directly and applied with one shift.
+//  * deferred carries: instead of the reference's buffer/bytes_to_follow bookkeeping
+//    (rangecod.c:182-207) the encoder stores the raw 9-bit value low >> 23 of every shift; the
+//    compaction kernel then forms byte j as B_j + carry(first later entry != 0xFF), which is what
+//    that bookkeeping produces, in parallel over all bytes.
+//  * seek points: the encoder records (low, range, position) at a few interior symbol indices of a
+//    chunk.  From them and the final stream bytes W at that position a decoder state follows as
+//    X = W - 2*low (mod 2^32), X being the decoder's (low << 1 | last bit read), so several lanes
+//    decode one chunk concurrently.  The chunk stream itself is unchanged.
 #include "wr_common.cuh"
 #include "wr_kernels.h"
 
@@ -19,72 +31,48 @@ namespace wrb {
 constexpr uint32_t kTop = 0x80000000u;      // Top_value    (rangecod.c:121)
 constexpr uint32_t kBottom = 0x00800000u;   // Bottom_value (rangecod.c:129)
 constexpr int kShiftBits = 23;              // SHIFT_BITS   (rangecod.c:127)
-constexpr int kExtraBits = 7;               // EXTRA_BITS   (rangecod.c:128)
+constexpr uint32_t kTerm = 0x8000u;         // raw-entry flag: written by done_encoding, stops carry scans
 
 unsigned long long chunk_slot_pitch(const ChunkGeom& g)
 {
-    // worst case 2 B/symbol + 513 B per coder block + framing (wrappers.cpp:79 uses 2*BLOCKSIZE+1000)
-    unsigned long long p = 2 * g.chunk_len + 1024ull * (g.blocks_per_chunk + 1);
+    // worst case 2 B/symbol + 513 B per coder block + framing (wrappers.cpp:79 uses 2*BLOCKSIZE+1000),
+    // two bytes of scratch per output byte (raw 9-bit entries)
+    unsigned long long p = 2 * (2 * g.chunk_len + 1024ull * (g.blocks_per_chunk + 1));
     return (p + 15ull) & ~15ull;
 }
 
-// exact n / d for n <= 2^31 by multiply-shift: q = (n * mul) >> sh
-struct Magic { uint32_t mul; uint32_t sh; };
+// exact n / d for n <= 2^31, d >= 2: q = umulhi(n, mul) >> sh with l = ceil(log2 d),
+// mul = ceil(2^(31+l) / d), sh = l - 1
+struct Magic { uint32_t mul, sh; bool one; };
 __device__ __forceinline__ Magic make_magic(uint32_t d)
 {
-    uint32_t l = (d <= 1) ? 0 : 32 - __clz(d - 1);          // ceil(log2 d)
-    unsigned long long p = 1ull << (31 + l);
     Magic m;
-    m.mul = (uint32_t)((p + d - 1) / d);
-    m.sh = 31 + l;
+    m.one = d <= 1;
+    const uint32_t l2 = m.one ? 1 : 32 - __clz(d - 1);
+    m.mul = m.one ? 0 : (uint32_t)(((1ull << (31 + l2)) + d - 1) / d);
+    m.sh = l2 - 1;
     return m;
 }
-__device__ __forceinline__ uint32_t div_magic(uint32_t n, Magic m)
+__device__ __forceinline__ uint32_t div_magic(uint32_t n, const Magic& m)
 {
-    return (uint32_t)(((unsigned long long)n * m.mul) >> m.sh);
+    return m.one ? n : (__umulhi(n, m.mul) >> m.sh);
 }
 
-// 8-byte packing byte sink; base must be 8-byte aligned
-struct Sink {
-    uint8_t* base;
-    unsigned long long acc;
-    unsigned long long pos;
-    __device__ __forceinline__ void put(uint32_t b)
-    {
-        acc |= (unsigned long long)(b & 0xFFu) << ((pos & 7ull) * 8);
-        pos++;
-        if ((pos & 7ull) == 0) { *reinterpret_cast<unsigned long long*>(base + pos - 8) = acc; acc = 0; }
-    }
-    __device__ __forceinline__ void flush()
-    {
-        unsigned long long r = pos & 7ull;
-        for (unsigned long long k = 0; k < r; k++) base[pos - r + k] = (uint8_t)(acc >> (8 * k));
-    }
-};
-
+// ------------------------------------------------------------------------------------------
+// encoder
+// ------------------------------------------------------------------------------------------
 struct Enc {
-    uint32_t low, range, pending, count, held;
-    Sink out;
+    uint32_t low, range, pos;    // pos = raw entries written (entry 0 is the lead byte)
+    uint16_t* raw;
 };
 
-// rangecod.c:182-207
+// generic renormalisation (markers, raw shorts, flush).  rangecod.c:182-207 minus the carry logic
 __device__ __forceinline__ void enc_renorm(Enc& e)
 {
     while (e.range <= kBottom) {
-        if (e.low < (0xFFu << kShiftBits)) {
-            e.out.put(e.held);
-            for (; e.pending; e.pending--) e.out.put(0xFF);
-            e.held = e.low >> kShiftBits;
-        } else if (e.low & kTop) {
-            e.out.put(e.held + 1);
-            for (; e.pending; e.pending--) e.out.put(0x00);
-            e.held = (e.low >> kShiftBits) & 0xFF;
-        } else {
-            e.pending++;
-        }
+        e.raw[e.pos++] = (uint16_t)(e.low >> kShiftBits);
         e.range <<= 8;
         e.low = (e.low << 8) & (kTop - 1);
-        e.count++;
     }
 }
 
@@ -92,7 +80,7 @@ __device__ __forceinline__ void enc_renorm(Enc& e)
 __device__ __forceinline__ void enc_marker(Enc& e, uint32_t bit)
 {
     enc_renorm(e);
-    uint32_t r = e.range >> 1;
+    const uint32_t r = e.range >> 1;
     if (bit) { e.low += r; e.range -= r; }   // sy=1, lt=1: lt+sy == tot
     else     { e.range = r; }                // sy=1, lt=0
 }
@@ -101,25 +89,40 @@ __device__ __forceinline__ void enc_marker(Enc& e, uint32_t bit)
 __device__ __forceinline__ void enc_short(Enc& e, uint32_t v)
 {
     enc_renorm(e);
-    uint32_t r = e.range >> 16, t = r * v;
+    const uint32_t r = e.range >> 16, t = r * v;
     e.low += t;
     if ((v + 1) >> 16) e.range -= t; else e.range = r;
 }
 
-// rangecod.c:254-276
+// rangecod.c:254-276.  bytecount of the reference == number of shifts == pos - 1.
 __device__ __forceinline__ void enc_finish(Enc& e)
 {
     enc_renorm(e);
-    e.count += 5;
+    const uint32_t count = (e.pos - 1) + 5;
     uint32_t t = e.low >> kShiftBits;
-    if (!((e.low & (kBottom - 1)) < ((e.count & 0xFFFFFFu) >> 1))) t += 1;
-    if (t > 0xFF) { e.out.put(e.held + 1); for (; e.pending; e.pending--) e.out.put(0x00); }
-    else          { e.out.put(e.held);     for (; e.pending; e.pending--) e.out.put(0xFF); }
-    e.out.put(t);
-    e.out.put(e.count >> 16);
-    e.out.put(e.count >> 8);
-    e.out.put(e.count);
-    e.out.flush();
+    if (!((e.low & (kBottom - 1)) < ((count & 0xFFFFFFu) >> 1))) t += 1;
+    e.raw[e.pos++] = (uint16_t)(t | kTerm);                    // carries like any entry (t > 0xFF)
+    e.raw[e.pos++] = (uint16_t)(((count >> 16) & 0xFFu) | kTerm);
+    e.raw[e.pos++] = (uint16_t)(((count >> 8) & 0xFFu) | kTerm);
+    e.raw[e.pos++] = (uint16_t)((count & 0xFFu) | kTerm);
+}
+
+// Code one symbol (rangecod.c:217-229).  ent = cum << 16 | count; `last`: the symbol is the last
+// one with a non-zero count, the only one with lt + sy == tot.
+__device__ __forceinline__ void enc_symbol(Enc& e, uint32_t ent, bool last, const Magic& mg)
+{
+    const bool k1 = e.range <= kBottom, k2 = e.range <= (kBottom >> 8);
+    uint16_t* w = e.raw + e.pos;
+    if (k1) w[0] = (uint16_t)(e.low >> kShiftBits);
+    if (k2) w[1] = (uint16_t)((e.low >> (kShiftBits - 8)) & 0xFFu);
+    const uint32_t k = (k1 ? 1u : 0u) + (k2 ? 1u : 0u);
+    e.pos += k;
+    e.range <<= 8 * k;
+    e.low = (e.low << (8 * k)) & (k1 ? (kTop - 1) : 0xFFFFFFFFu);   // the carry bit survives when nothing shifts
+    const uint32_t r = div_magic(e.range, mg);               // exact range / bs
+    const uint32_t t = r * (ent >> 16);
+    e.low += t;
+    e.range = last ? e.range - t : r * (ent & 0xFFFFu);
 }
 
 // grid (ceil(nchunks/32), layers), block 32: lane == chunk
@@ -129,7 +132,8 @@ __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restr
                                                           unsigned long long hist_layer_stride, ChunkGeom g,
                                                           const int* __restrict__ active, uint8_t* __restrict__ slots,
                                                           unsigned long long slot_pitch,
-                                                          unsigned long long* __restrict__ lens)
+                                                          unsigned long long* __restrict__ lens,
+                                                          uint32_t* __restrict__ seek)
 {
     const int layer = blockIdx.y;
     if (active != nullptr && !active[layer]) return;
@@ -137,69 +141,111 @@ __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restr
     const unsigned int lane = threadIdx.x;
     const unsigned int chunk = blockIdx.x * 32 + lane;
     if (chunk >= g.nchunks) return;
+    const unsigned long long id = (unsigned long long)layer * g.nchunks + chunk;
     const unsigned long long cstart = (unsigned long long)chunk * g.chunk_len;
     const unsigned long long clen = (g.ntot - cstart < g.chunk_len) ? g.ntot - cstart : g.chunk_len;
     const uint8_t* __restrict__ in = sym + (unsigned long long)layer * sym_layer_stride + (unsigned long long)chunk * g.pitch;
     const uint32_t* __restrict__ hrow = hist + (unsigned long long)layer * hist_layer_stride +
                                         (unsigned long long)chunk * g.blocks_per_chunk * 256;
+    uint32_t* __restrict__ sk = seek + id * g.nseek * 3;
     Enc e;
-    e.low = 0; e.range = kTop; e.pending = 0; e.count = 0; e.held = 0;     // rangecod.c:170-176
-    e.out.base = slots + ((unsigned long long)layer * g.nchunks + chunk) * slot_pitch;
-    e.out.acc = 0; e.out.pos = 0;
+    e.low = 0; e.range = kTop;                                             // rangecod.c:170-176
+    e.raw = reinterpret_cast<uint16_t*>(slots + id * slot_pitch);
+    e.raw[0] = 0;                                                          // lead byte
+    e.pos = 1;
+    const uint32_t* __restrict__ tl = tab + lane;
+    const uint32_t sub16 = g.sub_len >> 4;        // seek interval in 16-symbol groups (0: none)
     unsigned long long done = 0;
     for (;;) {                                                              // wrappers.cpp:85-128
         const uint32_t bs = (clen - done < kBlock) ? (uint32_t)(clen - done) : kBlock;
         enc_marker(e, 1);
-        uint32_t cum = 0;
-        for (int s = 0; s < 256; s++) {
-            uint32_t c = hrow[s];
-            enc_short(e, c);
-            tab[s * 32 + lane] = (cum << 16) | c;
-            cum += c;
-        }
-        const Magic mg = make_magic(bs);
-        const uint4* __restrict__ p = reinterpret_cast<const uint4*>(in + done);
-        for (uint32_t i = 0; i < bs; i += 16) {
-            uint4 w = p[i >> 4];
-            uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+        uint32_t cum = 0, lastsym = 0;
+        for (int s = 0; s < 256; s += 4) {
+            const uint4 c4 = *reinterpret_cast<const uint4*>(hrow + s);
+            const uint32_t cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                if (i + k < bs) {
-                    uint32_t c = (ww[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
-                    uint32_t ent = tab[c * 32 + lane];
-                    uint32_t sy = ent & 0xFFFFu, lt = ent >> 16;
-                    enc_renorm(e);                                         // rangecod.c:217-229
-                    uint32_t r = div_magic(e.range, mg), t = r * lt;
-                    e.low += t;
-                    if (lt + sy < bs) e.range = r * sy; else e.range -= t;
-                }
+            for (int k = 0; k < 4; k++) {
+                enc_short(e, cc[k]);
+                tab[(s + k) * 32 + lane] = (cum << 16) | cc[k];
+                cum += cc[k];
+                if (cc[k]) lastsym = s + k;
             }
         }
+        enc_renorm(e);                            // up to three shifts may be pending after a raw short
+        const Magic mg = make_magic(bs);
+        const uint4* __restrict__ p = reinterpret_cast<const uint4*>(in + done);
+        const uint32_t nfull = bs >> 4;
+        uint4 w = (bs > 0) ? p[0] : make_uint4(0, 0, 0, 0);
+        uint32_t until_seek = sub16, nsk = 0;
+        for (uint32_t i = 0; i < nfull; i++) {
+            if (g.nseek) {                                                 // seek point before symbol 16*i
+                if (until_seek == 0) {
+                    if (nsk < g.nseek) { sk[nsk * 3 + 0] = e.low; sk[nsk * 3 + 1] = e.range; sk[nsk * 3 + 2] = e.pos; nsk++; }
+                    until_seek = sub16;
+                }
+                until_seek--;
+            }
+            const uint4 wn = p[i + 1];                                     // next 16 symbols (pitch slack covers it)
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            uint32_t cs[16], ent[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                cs[k] = (ww[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
+                ent[k] = tl[cs[k] * 32];
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) enc_symbol(e, ent[k], cs[k] == lastsym, mg);
+            w = wn;
+        }
+        {
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            const uint32_t rem = bs & 15u;
+            if (g.nseek && rem && until_seek == 0 && nsk < g.nseek) {     // seek point at the remainder's first symbol
+                sk[nsk * 3 + 0] = e.low; sk[nsk * 3 + 1] = e.range; sk[nsk * 3 + 2] = e.pos; nsk++;
+            }
+            for (uint32_t k = 0; k < rem; k++) {
+                const uint32_t c = (ww[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
+                enc_symbol(e, tl[c * 32], c == lastsym, mg);
+            }
+        }
+        for (; g.nseek && nsk < g.nseek; nsk++) { sk[nsk * 3 + 0] = 0; sk[nsk * 3 + 1] = 0; sk[nsk * 3 + 2] = 0; }
         done += bs;
         hrow += 256;
         if (bs < kBlock) break;
     }
     enc_marker(e, 0);
     enc_finish(e);
-    lens[(unsigned long long)layer * g.nchunks + chunk] = e.out.pos;
+    lens[id] = (unsigned long long)e.pos;
 }
 
 void range_encode_chunks(const uint8_t* sym, unsigned long long sym_layer_stride, const uint32_t* hist,
                          unsigned long long hist_layer_stride, const ChunkGeom& g, int nlayers, const int* active,
-                         uint8_t* slots, unsigned long long slot_pitch, unsigned long long* lens, cudaStream_t s)
+                         uint8_t* slots, unsigned long long slot_pitch, unsigned long long* lens, uint32_t* seek,
+                         cudaStream_t s)
 {
     dim3 grid((g.nchunks + 31) / 32, nlayers, 1);
-    range_encode_kernel<<<grid, 32, 0, s>>>(sym, sym_layer_stride, hist, hist_layer_stride, g, active, slots, slot_pitch, lens);
+    range_encode_kernel<<<grid, 32, 0, s>>>(sym, sym_layer_stride, hist, hist_layer_stride, g, active, slots, slot_pitch,
+                                            lens, seek);
     note_launch(1);
 }
 
 // ------------------------------------------------------------------------------------------
-// container assembly: layer blob = [header 32 B][u32 len per chunk][chunk streams back to back]
-// (chunked mode), or the bare stream (single-stream mode, identical to the reference's layer).
+// container assembly.  Layer blob (chunked mode):
+//   [ 0] "WRCK"  [ 4] u32 version = 2  [ 8] u64 chunk_len  [16] u64 symbols in layer
+//   [24] u32 nchunks  [28] u32 nseek (seek points per chunk)
+//   u32 len[nchunks]                      byte length of every chunk stream
+//   u32 seek[nchunks][nseek][3]           (low, range, stream position) before symbol (j+1)*sub_len
+//   chunk streams back to back
+// Single-stream mode: the bare stream (identical to the reference's layer).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void put_le(uint8_t* p, unsigned long long v, int nbytes)
 {
     for (int k = 0; k < nbytes; k++) p[k] = (uint8_t)(v >> (8 * k));
+}
+
+__host__ __device__ inline unsigned long long container_header_bytes(const ChunkGeom& g, int chunked)
+{
+    return chunked ? 32ull + 4ull * g.nchunks + 12ull * g.nseek * g.nchunks : 0ull;
 }
 
 __global__ void __launch_bounds__(1024) assemble_scan_kernel(const unsigned long long* __restrict__ lens, ChunkGeom g,
@@ -221,27 +267,26 @@ __global__ void __launch_bounds__(1024) assemble_scan_kernel(const unsigned long
         for (unsigned int c = c0; c < c1; c++) sum += ll[c];
         s_part[t] = sum;
         __syncthreads();
-        // exclusive scan of 1024 partials (Hillis-Steele on shared memory)
-        for (int o = 1; o < 1024; o <<= 1) {
+        for (int o = 1; o < 1024; o <<= 1) {          // inclusive scan of the 1024 partial sums
             unsigned long long v = (t >= o) ? s_part[t - o] : 0;
             __syncthreads();
             s_part[t] += v;
             __syncthreads();
         }
         const unsigned long long total = s_part[1023];
-        unsigned long long off = s_part[t] - sum;          // exclusive prefix of this thread's run
+        unsigned long long off = s_part[t] - sum;
         const unsigned long long base = s_base;
-        const unsigned long long hdr = chunked ? 32ull + 4ull * g.nchunks : 0ull;
+        const unsigned long long hdr = container_header_bytes(g, chunked);
         const bool fits = base + hdr + total <= cap;
         if (fits) {
             if (chunked && t == 0) {
                 uint8_t* h = blob + base;
                 h[0] = 'W'; h[1] = 'R'; h[2] = 'C'; h[3] = 'K';
-                put_le(h + 4, 1, 4);
+                put_le(h + 4, 2, 4);
                 put_le(h + 8, g.chunk_len, 8);
                 put_le(h + 16, g.ntot, 8);
                 put_le(h + 24, g.nchunks, 4);
-                put_le(h + 28, 0, 4);
+                put_le(h + 28, g.nseek, 4);
             }
             for (unsigned int c = c0; c < c1; c++) {
                 dst_off[(unsigned long long)l * g.nchunks + c] = base + hdr + off;
@@ -252,6 +297,7 @@ __global__ void __launch_bounds__(1024) assemble_scan_kernel(const unsigned long
         __syncthreads();
         if (t == 0) {
             if (!fits) st->error = 1;                       // wrappers.cpp:422-426 (overflow)
+            st->lay_off[l] = base;
             st->len_enc[l] = hdr + total;
             s_base = base + hdr + total;
         }
@@ -260,83 +306,53 @@ __global__ void __launch_bounds__(1024) assemble_scan_kernel(const unsigned long
     if (t == 0) st->ntot_enc = s_base;
 }
 
+// carry of a raw entry: 1 if its 9/10-bit value exceeds 0xFF
+__device__ __forceinline__ uint32_t raw_carry(uint32_t v) { return ((v & 0x7FFFu) > 0xFFu) ? 1u : 0u; }
+
+// one CTA per (chunk, layer): resolve carries and move the stream to its place in the blob
 __global__ void __launch_bounds__(256) assemble_copy_kernel(const uint8_t* __restrict__ slots,
                                                             unsigned long long slot_pitch,
                                                             const unsigned long long* __restrict__ lens,
-                                                            const unsigned long long* __restrict__ dst_off, ChunkGeom g,
+                                                            const unsigned long long* __restrict__ dst_off,
+                                                            const uint32_t* __restrict__ seek, ChunkGeom g, int chunked,
                                                             const DevState* st, uint8_t* __restrict__ blob)
 {
     const int l = blockIdx.y;
     if (l >= st->nlay || st->error) return;
     const unsigned long long id = (unsigned long long)l * g.nchunks + blockIdx.x;
-    const uint8_t* __restrict__ src = slots + id * slot_pitch;
+    const uint16_t* __restrict__ raw = reinterpret_cast<const uint16_t*>(slots + id * slot_pitch);
     uint8_t* __restrict__ dst = blob + dst_off[id];
-    const unsigned long long n = lens[id];
-    // align the destination, then move 16 bytes per thread with funnel-shifted aligned loads
-    unsigned long long head = (16 - ((unsigned long long)dst & 15ull)) & 15ull;
-    if (head > n) head = n;
-    for (unsigned long long i = threadIdx.x; i < head; i += blockDim.x) dst[i] = src[i];
-    const unsigned long long body = (n - head) & ~15ull;
-    const uint8_t* sb = src + head;
-    uint8_t* db = dst + head;
-    const unsigned int sh = (unsigned int)((unsigned long long)sb & 3ull);
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(sb - sh);
-    for (unsigned long long i = (unsigned long long)threadIdx.x * 16; i < body; i += (unsigned long long)blockDim.x * 16) {
-        const uint32_t* q = sw + (i >> 2);
-        uint32_t a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = sh ? q[4] : 0;
-        uint4 o;
-        o.x = __funnelshift_r(a0, a1, sh * 8);
-        o.y = __funnelshift_r(a1, a2, sh * 8);
-        o.z = __funnelshift_r(a2, a3, sh * 8);
-        o.w = __funnelshift_r(a3, a4, sh * 8);
-        *reinterpret_cast<uint4*>(db + i) = o;
+    const uint32_t n = (uint32_t)lens[id];
+    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+        const uint32_t v = raw[j];
+        uint32_t k = j + 1, cin = 0;
+        while (k < n) {                              // first later entry that is not a plain 0xFF decides
+            const uint32_t u = raw[k];
+            if ((u & kTerm) || (u & 0x7FFFu) != 0xFFu) { cin = raw_carry(u); break; }
+            k++;
+        }
+        dst[j] = (uint8_t)((v & 0x7FFFu) + cin);
     }
-    for (unsigned long long i = head + body + threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    if (chunked && g.nseek) {
+        uint8_t* sdst = blob + st->lay_off[l] + 32 + 4ull * g.nchunks + 12ull * g.nseek * blockIdx.x;
+        const uint32_t* ssrc = seek + id * g.nseek * 3;
+        for (uint32_t t = threadIdx.x; t < g.nseek * 3; t += blockDim.x) put_le(sdst + 4ull * t, ssrc[t], 4);
+    }
 }
 
 void assemble_container(const uint8_t* slots, unsigned long long slot_pitch, const unsigned long long* lens,
-                        const ChunkGeom& g, int chunked, DevState* st, uint8_t* blob, unsigned long long cap,
-                        unsigned long long* dst_off, cudaStream_t s)
+                        const uint32_t* seek, const ChunkGeom& g, int chunked, DevState* st, uint8_t* blob,
+                        unsigned long long cap, unsigned long long* dst_off, cudaStream_t s)
 {
     assemble_scan_kernel<<<1, 1024, 0, s>>>(lens, g, chunked, st, blob, cap, dst_off);
     dim3 grid(g.nchunks, kNLayMax, 1);
-    assemble_copy_kernel<<<grid, 256, 0, s>>>(slots, slot_pitch, lens, dst_off, g, st, blob);
+    assemble_copy_kernel<<<grid, 256, 0, s>>>(slots, slot_pitch, lens, dst_off, seek, g, chunked, st, blob);
     note_launch(2);
 }
 
 // ------------------------------------------------------------------------------------------
 // decoder
 // ------------------------------------------------------------------------------------------
-struct Dec {
-    uint32_t low, range, help, held;
-    const uint8_t* in;
-    unsigned long long pos;
-};
-
-// rangecod.c:293-300
-__device__ __forceinline__ void dec_renorm(Dec& d)
-{
-    while (d.range <= kBottom) {
-        d.low = (d.low << 8) | ((d.held << kExtraBits) & 0xFFu);
-        d.held = d.in[d.pos++];
-        d.low |= d.held >> (8 - kExtraBits);
-        d.range <<= 8;
-    }
-}
-
-// rangecod.c:321-331 + :362-366 (decode_short), :339-351 (decode_update)
-__device__ __forceinline__ uint32_t dec_short(Dec& d)
-{
-    dec_renorm(d);
-    d.help = d.range >> 16;
-    uint32_t t = d.low / d.help;
-    if (t >> 16) t = 0xFFFFu;
-    uint32_t tmp = d.help * t;
-    d.low -= tmp;
-    if (t + 1 < (1u << 16)) d.range = d.help; else d.range -= tmp;
-    return t;
-}
-
 // per-layer chunk offsets from the container tables: offs[l*nchunks + c] = byte offset of the
 // chunk's stream inside the blob
 __global__ void __launch_bounds__(1024) parse_container_kernel(const uint8_t* __restrict__ blob, ChunkGeom g,
@@ -351,6 +367,7 @@ __global__ void __launch_bounds__(1024) parse_container_kernel(const uint8_t* __
         const unsigned long long base = lay_off[l];
         if (!chunked) { if (t == 0) offs[l] = base; continue; }
         const uint8_t* tabp = blob + base + 32;
+        const unsigned long long hdr = container_header_bytes(g, 1);
         unsigned long long sum = 0;
         for (unsigned int c = c0; c < c1; c++) {
             const uint8_t* q = tabp + 4ull * c;
@@ -371,92 +388,193 @@ __global__ void __launch_bounds__(1024) parse_container_kernel(const uint8_t* __
             const uint8_t* q = tabp + 4ull * c;
             unsigned long long len = (unsigned long long)q[0] | ((unsigned long long)q[1] << 8) |
                                      ((unsigned long long)q[2] << 16) | ((unsigned long long)q[3] << 24);
-            offs[(unsigned long long)l * g.nchunks + c] = base + 32 + 4ull * g.nchunks + off;
+            offs[(unsigned long long)l * g.nchunks + c] = base + hdr + off;
             off += len;
         }
-        if (t == 0 && base + 32 + 4ull * g.nchunks + total != lay_off[l + 1]) *error = 2;   // table / length mismatch
+        if (t == 0 && base + hdr + total != lay_off[l + 1]) *error = 2;       // table / length mismatch
         __syncthreads();
     }
 }
 
-// grid (ceil(nchunks/32), layers), block 32: lane == chunk.   wrappers.cpp:153-224
+// floor(a / b) for a < 2^31, 0 < b, a / b < 2^17: float reciprocal estimate, exact fix-up
+__device__ __forceinline__ uint32_t div_small_quot(uint32_t a, uint32_t b)
+{
+    float rb;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(__uint2float_rn(b)));      // <= 1 ulp
+    uint32_t q = __float2uint_rz(__uint2float_rz(a) * rb);                        // |q - a/b| < 1
+    uint32_t p = q * b;
+    if (p > a) { q--; p -= b; }          // estimate one too high
+    if (a - p >= b) q++;                 // estimate one too low
+    return q;
+}
+
+// Decoder state in "X form": X = (low << 1) | (lowest bit of the last byte read), i.e. the last four
+// stream bytes read minus twice the coder's cumulative low; a renormalisation step (rangecod.c:293-300)
+// is then X = X << 8 | next byte.
+struct Dec {
+    uint32_t X, range;
+    uint32_t ip;                    // index of the next stream byte
+    const uint8_t* p;               // stream start
+};
+
+__device__ __forceinline__ void dec_renorm(Dec& d)
+{
+    while (d.range <= kBottom) { d.X = (d.X << 8) | d.p[d.ip++]; d.range <<= 8; }
+}
+
+// rangecod.c:321-331 + :362-366 (decode_short), :339-351 (decode_update)
+__device__ __forceinline__ uint32_t dec_short(Dec& d)
+{
+    dec_renorm(d);
+    const uint32_t help = d.range >> 16;
+    uint32_t t = (d.X >> 1) / help;
+    if (t >> 16) t = 0xFFFFu;
+    const uint32_t tmp = help * t;
+    d.X -= 2 * tmp;
+    if (t + 1 < (1u << 16)) d.range = help; else d.range -= tmp;
+    return t;
+}
+
+constexpr int kLutShift = 6;
+constexpr int kLutSize = (kBlock >> kLutShift) + 1;           // 938 buckets
+
+// grid (ceil(nchunks/cpw), layers), block 32: lane == (chunk column, sub-chunk), cpw = 32/nsub chunks per warp.   wrappers.cpp:153-224
+// Symbol search: the reference builds a 60001-entry inverse table per block (wrappers.cpp:191-196);
+// here a per-lane 1-byte LUT over cf >> 6 gives the first symbol whose interval meets the bucket,
+// followed by a short forward scan over the packed (cum, count) table (zero-count symbols are
+// skipped by the same scan, wrappers.cpp:205).
 __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restrict__ blob,
-                                                          const unsigned long long* __restrict__ offs, ChunkGeom g,
+                                                          const unsigned long long* __restrict__ offs,
+                                                          const unsigned long long* __restrict__ lay_off, ChunkGeom g,
                                                           uint8_t* __restrict__ sym, unsigned long long sym_layer_stride,
                                                           int* error)
 {
-    __shared__ uint32_t cumt[257 * 32];           // [symbol][lane] exclusive cumulative counts
+    // The lanes that share a chunk share its tables: column = chunk slot inside the warp.  All of
+    // them decode the identical table and store identical values (benign same-value writes).
+    extern __shared__ __align__(16) uint8_t smem_raw[];
     const int layer = blockIdx.y;
     const unsigned int lane = threadIdx.x;
-    const unsigned int chunk = blockIdx.x * 32 + lane;
-    if (chunk >= g.nchunks) return;
+    const unsigned int nsub = g.nseek + 1;
+    const unsigned int cpw = 32 / nsub;                       // chunks per warp (columns)
+    uint32_t* tab = reinterpret_cast<uint32_t*>(smem_raw);    // [symbol][column] = cum << 16 | count
+    uint8_t* lut = smem_raw + 256 * cpw * 4;                  // [bucket][column]
+    const unsigned int col = lane / nsub, sub = lane % nsub;
+    const unsigned int chunk = blockIdx.x * cpw + col;
+    if (col >= cpw || chunk >= g.nchunks) return;
     const unsigned long long cstart = (unsigned long long)chunk * g.chunk_len;
     const unsigned long long clen = (g.ntot - cstart < g.chunk_len) ? g.ntot - cstart : g.chunk_len;
-    uint8_t* __restrict__ out = sym + (unsigned long long)layer * sym_layer_stride + (unsigned long long)chunk * g.pitch;
+    if (sub > 0 && (unsigned long long)sub * g.sub_len >= clen) return;       // nothing for this lane
+    uint8_t* __restrict__ outb = sym + (unsigned long long)layer * sym_layer_stride + (unsigned long long)chunk * g.pitch;
     Dec d;
-    d.in = blob + offs[(unsigned long long)layer * g.nchunks + chunk];
-    d.pos = 1;                                    // lead byte (rangecod.c:283)
-    d.held = d.in[d.pos++];
-    d.low = d.held >> (8 - kExtraBits);
-    d.range = 1u << kExtraBits;
-    d.help = 0;
+    d.p = blob + offs[(unsigned long long)layer * g.nchunks + chunk];
+    d.X = d.p[1];                                 // lead byte skipped (rangecod.c:283-288)
+    d.ip = 2;
+    d.range = 1u << 7;
+    const uint32_t* tl = tab + col;
     unsigned long long n = 0;
+    unsigned int nblocks = 0;
     bool bad = false;
     for (;;) {
         dec_renorm(d);                            // decode_culfreq(rc, 2)  (wrappers.cpp:174)
-        d.help = d.range >> 1;
-        uint32_t bit = d.low / d.help;
-        if (bit >= 2) bit = 1;
-        if (!bit) break;
-        d.low -= d.help; d.range -= d.help;       // decode_update(rc,1,1,2)
+        uint32_t help = d.range >> 1;
+        if ((d.X >> 1) < help) break;             // marker 0: no further block
+        d.X -= 2 * help; d.range -= help;         // decode_update(rc,1,1,2)
+        if (++nblocks > g.blocks_per_chunk) { bad = true; break; }
         uint32_t acc = 0;
+        int nextb = 0;                            // first bucket not yet assigned
         for (int s = 0; s < 256; s++) {           // readcounts (rangecod.c:400-404) + prefix sums
-            uint32_t c = dec_short(d);
-            cumt[s * 32 + lane] = acc;
+            const uint32_t c = dec_short(d);
+            tab[s * cpw + col] = (acc << 16) | c;
+            if (c) {
+                const int lastb = (int)((acc + c - 1) >> kLutShift);
+                if (lastb < kLutSize) for (; nextb <= lastb; nextb++) lut[nextb * cpw + col] = (uint8_t)s;
+            }
             acc += c;
+            if (acc > kBlock) { bad = true; break; }
         }
-        cumt[256 * 32 + lane] = acc;
+        if (bad) break;
         const uint32_t bs = acc;
         if (n + bs > clen) { bad = true; break; }
-        const Magic mg = make_magic(bs ? bs : 1);
-        unsigned long long pack = 0;
-        for (uint32_t i = 0; i < bs; i++) {
-            dec_renorm(d);                        // decode_culfreq(rc, bs)
-            d.help = div_magic(d.range, mg);
-            uint32_t cf = d.low / d.help;
-            if (cf >= bs) cf = bs - 1;
-            uint32_t lo = 0, hi = 256;            // largest s with cum[s] <= cf  (wrappers.cpp:203-205)
-#pragma unroll
-            for (int it = 0; it < 8; it++) {
-                uint32_t mid = (lo + hi) >> 1;
-                if (cumt[mid * 32 + lane] <= cf) lo = mid; else hi = mid;
+        uint32_t s0 = 0, s1 = bs;
+        if (g.nseek) {                            // this lane's share of the (single) block
+            if (bs != clen) { bad = true; break; }
+            s0 = sub * g.sub_len;
+            s1 = (s0 + g.sub_len < bs) ? s0 + g.sub_len : bs;
+            if (sub > 0) {                        // restart from the seek point: X = W - 2*low
+                const uint8_t* sp = blob + lay_off[layer] + 32 + 4ull * g.nchunks +
+                                    12ull * ((unsigned long long)chunk * g.nseek + (sub - 1));
+                const uint32_t slow = sp[0] | (sp[1] << 8) | (sp[2] << 16) | ((uint32_t)sp[3] << 24);
+                const uint32_t srng = sp[4] | (sp[5] << 8) | (sp[6] << 16) | ((uint32_t)sp[7] << 24);
+                const uint32_t spos = sp[8] | (sp[9] << 8) | (sp[10] << 16) | ((uint32_t)sp[11] << 24);
+                const uint8_t* q = d.p + spos;
+                const uint32_t W = ((uint32_t)q[0] << 24) | (q[1] << 16) | (q[2] << 8) | q[3];
+                d.X = W - 2 * slow;
+                d.range = srng;
+                d.ip = spos + 4;
+                if (srng == 0) { bad = true; break; }
             }
-            uint32_t lt = cumt[lo * 32 + lane], nx = cumt[(lo + 1) * 32 + lane];
-            while (nx <= cf) { lo++; lt = nx; nx = cumt[(lo + 1) * 32 + lane]; }
-            uint32_t sy = nx - lt;
-            uint32_t tmp = d.help * lt;           // decode_update (rangecod.c:339-351)
-            d.low -= tmp;
-            if (lt + sy < bs) d.range = d.help * sy; else d.range -= tmp;
-            pack |= (unsigned long long)lo << ((n & 7ull) * 8);
-            n++;
-            if ((n & 7ull) == 0) { *reinterpret_cast<unsigned long long*>(out + n - 8) = pack; pack = 0; }
         }
-        if (n & 7ull) {                            // flush partial word (block ends are 8-aligned except the last)
-            unsigned long long r = n & 7ull;
-            for (unsigned long long k = 0; k < r; k++) out[n - r + k] = (uint8_t)(pack >> (8 * k));
+        dec_renorm(d);                            // up to three shifts may be pending after a raw short
+        const Magic mg = make_magic(bs);
+        // stream window: aligned words w0 w1 (w2 prefetched) hold the next bytes; win = next 4, big-endian
+        const unsigned long long pa = (unsigned long long)d.p;
+        const uint32_t* __restrict__ wbase = reinterpret_cast<const uint32_t*>(pa & ~3ull);
+        const uint32_t boff = (uint32_t)(pa & 3ull);
+        uint32_t a = boff + d.ip;
+        uint32_t widx = a >> 2;
+        uint32_t w0 = wbase[widx], w1 = wbase[widx + 1], w2 = wbase[widx + 2];
+        uint32_t win = __byte_perm(w0, w1, 0x0123u + 0x1111u * (a & 3u));
+        uint32_t X = d.X, range = d.range;
+        unsigned long long pack = 0;
+        unsigned long long* wp = reinterpret_cast<unsigned long long*>(outb + n + s0);   // 8-aligned: s0 % 16 == 0
+        uint32_t i = s0;
+        for (; i < s1; i++) {
+            const uint32_t k = (range <= kBottom ? 1u : 0u) + (range <= (kBottom >> 8) ? 1u : 0u);
+            X = __funnelshift_l(win, X, 8 * k);   // k renormalisation steps at once
+            range <<= 8 * k;
+            a += k;
+            if ((a >> 2) != widx) { widx++; w0 = w1; w1 = w2; w2 = wbase[widx + 2]; }
+            win = __byte_perm(w0, w1, 0x0123u + 0x1111u * (a & 3u));
+            help = div_magic(range, mg);          // decode_culfreq(rc, bs)
+            uint32_t cf = div_small_quot(X >> 1, help);
+            cf = cf >= bs ? bs - 1 : cf;
+            uint32_t s = lut[(cf >> kLutShift) * cpw + col];
+            uint32_t ent = tl[s * cpw];
+            uint32_t lt = ent >> 16, sy = ent & 0xFFFFu;
+            while (lt + sy <= cf && s < 255u) { s++; ent = tl[s * cpw]; lt = ent >> 16; sy = ent & 0xFFFFu; }
+            const uint32_t tmp = help * lt;       // decode_update (rangecod.c:339-351)
+            X -= 2 * tmp;
+            range = (lt + sy < bs) ? help * sy : range - tmp;
+            pack |= (unsigned long long)s << ((i & 7u) * 8);
+            if ((i & 7u) == 7u) { *wp++ = pack; pack = 0; }
         }
-        if (bs < kBlock) {
-            // the reference keeps reading markers; a well-formed chunk has its end marker next
+        if (i & 7u) *wp = pack;                   // partial word: only at the end of a chunk (pitch slack)
+        d.X = X; d.range = range; d.ip = a - boff;
+        n += bs;
+        if (g.nseek) {
+            if (s1 == bs) {                       // owner of the chunk's last symbol checks the end marker
+                dec_renorm(d);
+                if (!((d.X >> 1) < (d.range >> 1))) bad = true;
+            }
+            break;
         }
     }
     if (bad || n != clen) atomicExch(error, 3);
 }
 
-void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, const ChunkGeom& g, int nlay, uint8_t* sym,
-                         unsigned long long sym_layer_stride, int* error, cudaStream_t s)
+void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, const unsigned long long* lay_off,
+                         const ChunkGeom& g, int nlay, uint8_t* sym, unsigned long long sym_layer_stride, int* error,
+                         cudaStream_t s)
 {
-    dim3 grid((g.nchunks + 31) / 32, nlay, 1);
-    range_decode_kernel<<<grid, 32, 0, s>>>(blob, offs, g, sym, sym_layer_stride, error);
+    const unsigned int cpw = 32 / (g.nseek + 1);
+    dim3 grid((g.nchunks + cpw - 1) / cpw, nlay, 1);
+    const int smem = 256 * 32 * 4 + kLutSize * 32;      // sized for cpw == 32; fewer columns use less
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(range_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    range_decode_kernel<<<grid, 32, (256 * 4 + kLutSize) * cpw, s>>>(blob, offs, lay_off, g, sym, sym_layer_stride, error);
     note_launch(1);
 }
 

@@ -43,6 +43,7 @@ struct DevState {
     int    error;
     unsigned long long ntot_enc;
     unsigned long long len_enc[kNLayMax];
+    unsigned long long lay_off[kNLayMax + 1];   // byte offset of every layer inside the blob
 };
 
 __host__ __device__ inline unsigned long long dkey(double x)

@@ -25,8 +25,11 @@ struct ChunkGeom {
     unsigned int nchunks;
     unsigned int blocks_per_chunk;  // coder blocks in a full chunk (incl. a possible empty one)
     unsigned int nblocks;           // total coder blocks in the layer
+    unsigned int nseek;             // seek points per chunk (decoder entry points inside a chunk); 0 = none
+    unsigned int sub_len;           // symbols between seek points (multiple of 16); 0 when nseek == 0
 };
-ChunkGeom make_geom(unsigned long long ntot, unsigned long long chunk_len);
+// nseek_req seek points are granted only to single-block chunks (chunk_len < 60000)
+ChunkGeom make_geom(unsigned long long ntot, unsigned long long chunk_len, unsigned int nseek_req);
 
 void state_init(DevState* st, cudaStream_t s);
 void state_prepare(DevState* st, double tolrel, cudaStream_t s);          // after field extrema are known
@@ -41,14 +44,16 @@ void dequantise(const uint8_t* sym, unsigned long long layer_stride, const Chunk
 unsigned long long chunk_slot_pitch(const ChunkGeom& g);
 void range_encode_chunks(const uint8_t* sym, unsigned long long sym_layer_stride, const uint32_t* hist,
                          unsigned long long hist_layer_stride, const ChunkGeom& g, int nlayers, const int* active,
-                         uint8_t* slots, unsigned long long slot_pitch, unsigned long long* lens, cudaStream_t s);
+                         uint8_t* slots, unsigned long long slot_pitch, unsigned long long* lens, uint32_t* seek,
+                         cudaStream_t s);
 void assemble_container(const uint8_t* slots, unsigned long long slot_pitch, const unsigned long long* lens,
-                        const ChunkGeom& g, int chunked, DevState* st, uint8_t* blob, unsigned long long cap,
-                        unsigned long long* dst_off, cudaStream_t s);
+                        const uint32_t* seek, const ChunkGeom& g, int chunked, DevState* st, uint8_t* blob,
+                        unsigned long long cap, unsigned long long* dst_off, cudaStream_t s);
 void parse_container(const uint8_t* blob, const ChunkGeom& g, int chunked, int nlay, const unsigned long long* lay_off,
                      unsigned long long* offs, int* error, cudaStream_t s);
-void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, const ChunkGeom& g, int nlay, uint8_t* sym,
-                         unsigned long long sym_layer_stride, int* error, cudaStream_t s);
+void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, const unsigned long long* lay_off,
+                         const ChunkGeom& g, int nlay, uint8_t* sym, unsigned long long sym_layer_stride, int* error,
+                         cudaStream_t s);
 
 // ---- codec.cu -----------------------------------------------------------------------------
 void note_launch(int n);   // kernel-launch accounting (wrb_launch_count)
