@@ -28,12 +28,12 @@ ChunkGeom make_geom(unsigned long long ntot, unsigned long long chunk_len, unsig
     g.nblocks = (g.nchunks - 1) * g.blocks_per_chunk + (unsigned int)(last / kBlock + 1);
     g.nseek = 0;
     g.sub_len = 0;
+    if (nseek_req >= 7) nseek_req = 7; else if (nseek_req >= 3) nseek_req = 3; else if (nseek_req >= 1) nseek_req = 1;   // 2, 4 or 8 lanes per chunk
     if (nseek_req > 0 && g.blocks_per_chunk == 1 && g.chunk_len >= 64ull * (nseek_req + 1)) {
         g.nseek = nseek_req;
         unsigned long long sub = (g.chunk_len + nseek_req) / (nseek_req + 1);      // ceil(chunk_len / nsub)
         g.sub_len = (unsigned int)((sub + 15ull) & ~15ull);
-        while (g.nseek > 0 && (unsigned long long)g.nseek * g.sub_len >= g.chunk_len) g.nseek--;   // drop empty tails
-        if (g.nseek == 0) g.sub_len = 0;
+        if ((unsigned long long)g.nseek * g.sub_len >= g.chunk_len) { g.nseek = 0; g.sub_len = 0; }   // no empty tails
     }
     return g;
 }

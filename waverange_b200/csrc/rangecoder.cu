@@ -108,21 +108,30 @@ __device__ __forceinline__ void enc_finish(Enc& e)
 }
 
 // Code one symbol (rangecod.c:217-229).  ent = cum << 16 | count; `last`: the symbol is the last
-// one with a non-zero count, the only one with lt + sy == tot.
+// one with a non-zero count, the only one with lt + sy == tot.  Branch-free: the (at most two) raw
+// entries go out through predicated stores and the shifted state is chosen with selects.
 __device__ __forceinline__ void enc_symbol(Enc& e, uint32_t ent, bool last, const Magic& mg)
 {
-    const bool k1 = e.range <= kBottom, k2 = e.range <= (kBottom >> 8);
+    const uint32_t range = e.range, low = e.low;
     uint16_t* w = e.raw + e.pos;
-    if (k1) w[0] = (uint16_t)(e.low >> kShiftBits);
-    if (k2) w[1] = (uint16_t)((e.low >> (kShiftBits - 8)) & 0xFFu);
-    const uint32_t k = (k1 ? 1u : 0u) + (k2 ? 1u : 0u);
-    e.pos += k;
-    e.range <<= 8 * k;
-    e.low = (e.low << (8 * k)) & (k1 ? (kTop - 1) : 0xFFFFFFFFu);   // the carry bit survives when nothing shifts
-    const uint32_t r = div_magic(e.range, mg);               // exact range / bs
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p1, p2;\n\t"
+        "setp.le.u32 p1, %1, 0x800000;\n\t"
+        "setp.le.u32 p2, %1, 0x8000;\n\t"
+        "@p1 st.global.u16 [%0], %2;\n\t"
+        "@p2 st.global.u16 [%0+2], %3;\n\t"
+        "}"
+        :: "l"(w), "r"(range), "h"((uint16_t)(low >> kShiftBits)), "h"((uint16_t)((low >> (kShiftBits - 8)) & 0xFFu))
+        : "memory");
+    const bool k1 = range <= kBottom, k2 = range <= (kBottom >> 8);
+    e.pos += (k1 ? 1u : 0u) + (k2 ? 1u : 0u);
+    const uint32_t rs = k2 ? (range << 16) : (k1 ? (range << 8) : range);
+    const uint32_t ls = k2 ? ((low << 16) & (kTop - 1)) : (k1 ? ((low << 8) & (kTop - 1)) : low);   // carry bit survives k == 0
+    const uint32_t r = div_magic(rs, mg);                    // exact range / bs
     const uint32_t t = r * (ent >> 16);
-    e.low += t;
-    e.range = last ? e.range - t : r * (ent & 0xFFFFu);
+    e.low = ls + t;
+    e.range = last ? rs - t : r * (ent & 0xFFFFu);
 }
 
 // grid (ceil(nchunks/32), layers), block 32: lane == chunk
@@ -396,16 +405,15 @@ __global__ void __launch_bounds__(1024) parse_container_kernel(const uint8_t* __
     }
 }
 
-// floor(a / b) for a < 2^31, 0 < b, a / b < 2^17: float reciprocal estimate, exact fix-up
+// floor(a / b) for a < 2^31, 0 < b, a / b < 2^17.  The float estimate is biased low (operands rounded
+// towards a smaller quotient, reciprocal nudged two ulps down), so it is q or q - 1: one fix-up.
 __device__ __forceinline__ uint32_t div_small_quot(uint32_t a, uint32_t b)
 {
     float rb;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(__uint2float_rn(b)));      // <= 1 ulp
-    uint32_t q = __float2uint_rz(__uint2float_rz(a) * rb);                        // |q - a/b| < 1
-    uint32_t p = q * b;
-    if (p > a) { q--; p -= b; }          // estimate one too high
-    if (a - p >= b) q++;                 // estimate one too low
-    return q;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(__uint2float_ru(b)));      // <= 1 ulp off
+    rb = __int_as_float(__float_as_int(rb) - 2);                                  // now <= 1 / b
+    uint32_t q = __float2uint_rz(__fmul_rz(__uint2float_rz(a), rb));              // q_true - 1 <= q <= q_true
+    return q + ((a - q * b >= b) ? 1u : 0u);
 }
 
 // Decoder state in "X form": X = (low << 1) | (lowest bit of the last byte read), i.e. the last four
@@ -438,29 +446,29 @@ __device__ __forceinline__ uint32_t dec_short(Dec& d)
 constexpr int kLutShift = 6;
 constexpr int kLutSize = (kBlock >> kLutShift) + 1;           // 938 buckets
 
-// grid (ceil(nchunks/cpw), layers), block 32: lane == (chunk column, sub-chunk), cpw = 32/nsub chunks per warp.   wrappers.cpp:153-224
+// grid (ceil(nchunks/CPW), layers), block 32: lane == (chunk column, sub-chunk); NSUB lanes decode one
+// chunk, CPW = 32/NSUB chunks per warp.   wrappers.cpp:153-224
 // Symbol search: the reference builds a 60001-entry inverse table per block (wrappers.cpp:191-196);
-// here a per-lane 1-byte LUT over cf >> 6 gives the first symbol whose interval meets the bucket,
-// followed by a short forward scan over the packed (cum, count) table (zero-count symbols are
-// skipped by the same scan, wrappers.cpp:205).
+// here a 1-byte LUT over cf >> 6 gives the first symbol whose interval meets the bucket, followed by
+// a short forward scan over the packed (cum, count) table (zero-count symbols are skipped by the
+// same scan, wrappers.cpp:205).  The lanes that share a chunk share its tables (column = chunk slot
+// inside the warp): all of them decode the identical table and store identical values.
+template <int NSUB>
 __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restrict__ blob,
                                                           const unsigned long long* __restrict__ offs,
                                                           const unsigned long long* __restrict__ lay_off, ChunkGeom g,
                                                           uint8_t* __restrict__ sym, unsigned long long sym_layer_stride,
                                                           int* error)
 {
-    // The lanes that share a chunk share its tables: column = chunk slot inside the warp.  All of
-    // them decode the identical table and store identical values (benign same-value writes).
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    constexpr unsigned int CPW = 32 / NSUB;
+    extern __shared__ __align__(16) uint32_t smem_dyn[];
+    uint32_t* tab = smem_dyn;                                             // [symbol][column] = cum << 16 | count (+ sentinel row)
+    uint8_t* lut = reinterpret_cast<uint8_t*>(smem_dyn + 257 * CPW);      // [bucket][column]
     const int layer = blockIdx.y;
     const unsigned int lane = threadIdx.x;
-    const unsigned int nsub = g.nseek + 1;
-    const unsigned int cpw = 32 / nsub;                       // chunks per warp (columns)
-    uint32_t* tab = reinterpret_cast<uint32_t*>(smem_raw);    // [symbol][column] = cum << 16 | count
-    uint8_t* lut = smem_raw + 256 * cpw * 4;                  // [bucket][column]
-    const unsigned int col = lane / nsub, sub = lane % nsub;
-    const unsigned int chunk = blockIdx.x * cpw + col;
-    if (col >= cpw || chunk >= g.nchunks) return;
+    const unsigned int col = lane / NSUB, sub = lane % NSUB;
+    const unsigned int chunk = blockIdx.x * CPW + col;
+    if (chunk >= g.nchunks) return;
     const unsigned long long cstart = (unsigned long long)chunk * g.chunk_len;
     const unsigned long long clen = (g.ntot - cstart < g.chunk_len) ? g.ntot - cstart : g.chunk_len;
     if (sub > 0 && (unsigned long long)sub * g.sub_len >= clen) return;       // nothing for this lane
@@ -471,6 +479,7 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
     d.ip = 2;
     d.range = 1u << 7;
     const uint32_t* tl = tab + col;
+    const uint8_t* ll = lut + col;
     unsigned long long n = 0;
     unsigned int nblocks = 0;
     bool bad = false;
@@ -484,19 +493,20 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
         int nextb = 0;                            // first bucket not yet assigned
         for (int s = 0; s < 256; s++) {           // readcounts (rangecod.c:400-404) + prefix sums
             const uint32_t c = dec_short(d);
-            tab[s * cpw + col] = (acc << 16) | c;
+            tab[s * CPW + col] = (acc << 16) | c;
             if (c) {
                 const int lastb = (int)((acc + c - 1) >> kLutShift);
-                if (lastb < kLutSize) for (; nextb <= lastb; nextb++) lut[nextb * cpw + col] = (uint8_t)s;
+                if (lastb < kLutSize) for (; nextb <= lastb; nextb++) lut[nextb * CPW + col] = (uint8_t)s;
             }
             acc += c;
             if (acc > kBlock) { bad = true; break; }
         }
         if (bad) break;
+        tab[256 * CPW + col] = 0xFFFF0000u;       // sentinel: never satisfies cum + count <= cf
         const uint32_t bs = acc;
         if (n + bs > clen) { bad = true; break; }
         uint32_t s0 = 0, s1 = bs;
-        if (g.nseek) {                            // this lane's share of the (single) block
+        if (NSUB > 1) {                           // this lane's share of the (single) block
             if (bs != clen) { bad = true; break; }
             s0 = sub * g.sub_len;
             s1 = (s0 + g.sub_len < bs) ? s0 + g.sub_len : bs;
@@ -516,42 +526,57 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
         }
         dec_renorm(d);                            // up to three shifts may be pending after a raw short
         const Magic mg = make_magic(bs);
-        // stream window: aligned words w0 w1 (w2 prefetched) hold the next bytes; win = next 4, big-endian
+        // stream window: win = next 4 stream bytes, big-endian, assembled from the two aligned words that
+        // hold them.  The words for the NEXT symbol are loaded (L1 hits) as soon as this symbol's byte
+        // consumption is known and are only touched at the top of the next iteration, so the loads
+        // overlap the division / table look-ups; a prefetch runs one cache line ahead.
         const unsigned long long pa = (unsigned long long)d.p;
         const uint32_t* __restrict__ wbase = reinterpret_cast<const uint32_t*>(pa & ~3ull);
         const uint32_t boff = (uint32_t)(pa & 3ull);
         uint32_t a = boff + d.ip;
-        uint32_t widx = a >> 2;
-        uint32_t w0 = wbase[widx], w1 = wbase[widx + 1], w2 = wbase[widx + 2];
-        uint32_t win = __byte_perm(w0, w1, 0x0123u + 0x1111u * (a & 3u));
+        uint32_t w0 = wbase[a >> 2], w1 = wbase[(a >> 2) + 1];
+        uint32_t sel = 0x0123u + 0x1111u * (a & 3u);
         uint32_t X = d.X, range = d.range;
-        unsigned long long pack = 0;
-        unsigned long long* wp = reinterpret_cast<unsigned long long*>(outb + n + s0);   // 8-aligned: s0 % 16 == 0
+        uint32_t pack = 0;
+        uint32_t* wp = reinterpret_cast<uint32_t*>(outb + n + s0);   // 4-aligned: s0 % 16 == 0, n % 60000 == 0
         uint32_t i = s0;
+#pragma unroll 1
         for (; i < s1; i++) {
-            const uint32_t k = (range <= kBottom ? 1u : 0u) + (range <= (kBottom >> 8) ? 1u : 0u);
-            X = __funnelshift_l(win, X, 8 * k);   // k renormalisation steps at once
-            range <<= 8 * k;
-            a += k;
-            if ((a >> 2) != widx) { widx++; w0 = w1; w1 = w2; w2 = wbase[widx + 2]; }
-            win = __byte_perm(w0, w1, 0x0123u + 0x1111u * (a & 3u));
+            const uint32_t win = __byte_perm(w0, w1, sel);
+            const bool k1 = range <= kBottom, k2 = range <= (kBottom >> 8);
+            X = k2 ? __funnelshift_l(win, X, 16) : (k1 ? __funnelshift_l(win, X, 8) : X);   // renormalise
+            range = k2 ? (range << 16) : (k1 ? (range << 8) : range);
+            const uint32_t an = a + (k1 ? 1u : 0u) + (k2 ? 1u : 0u);
+            if ((an ^ a) & 0x80u) asm volatile("prefetch.global.L1 [%0];" :: "l"(wbase + (an >> 2) + 64));
+            a = an;
+            w0 = wbase[a >> 2];
+            w1 = wbase[(a >> 2) + 1];
+            sel = 0x0123u + 0x1111u * (a & 3u);
             help = div_magic(range, mg);          // decode_culfreq(rc, bs)
             uint32_t cf = div_small_quot(X >> 1, help);
-            cf = cf >= bs ? bs - 1 : cf;
-            uint32_t s = lut[(cf >> kLutShift) * cpw + col];
-            uint32_t ent = tl[s * cpw];
+            cf = min(cf, bs - 1);
+            uint32_t s = ll[(cf >> kLutShift) * CPW];
+            uint32_t e0, e1;                      // both probes issued together (volatile: keep them unconditional)
+            {
+                const uint32_t sa = (uint32_t)__cvta_generic_to_shared(tl + s * CPW);
+                asm volatile("ld.shared.u32 %0, [%2];\n\tld.shared.u32 %1, [%2+%3];"
+                             : "=r"(e0), "=r"(e1) : "r"(sa), "n"(CPW * 4));
+            }
+            const bool adv = (e0 >> 16) + (e0 & 0xFFFFu) <= cf;
+            uint32_t ent = adv ? e1 : e0;
+            s += adv ? 1u : 0u;
             uint32_t lt = ent >> 16, sy = ent & 0xFFFFu;
-            while (lt + sy <= cf && s < 255u) { s++; ent = tl[s * cpw]; lt = ent >> 16; sy = ent & 0xFFFFu; }
+            while (lt + sy <= cf && s < 255u) { s++; ent = tl[s * CPW]; lt = ent >> 16; sy = ent & 0xFFFFu; }
             const uint32_t tmp = help * lt;       // decode_update (rangecod.c:339-351)
             X -= 2 * tmp;
             range = (lt + sy < bs) ? help * sy : range - tmp;
-            pack |= (unsigned long long)s << ((i & 7u) * 8);
-            if ((i & 7u) == 7u) { *wp++ = pack; pack = 0; }
+            pack |= s << ((i & 3u) * 8);
+            if ((i & 3u) == 3u) { *wp++ = pack; pack = 0; }
         }
-        if (i & 7u) *wp = pack;                   // partial word: only at the end of a chunk (pitch slack)
+        if (i & 3u) *wp = pack;                   // partial word: only at the end of a chunk (pitch slack)
         d.X = X; d.range = range; d.ip = a - boff;
         n += bs;
-        if (g.nseek) {
+        if (NSUB > 1) {
             if (s1 == bs) {                       // owner of the chunk's last symbol checks the end marker
                 dec_renorm(d);
                 if (!((d.X >> 1) < (d.range >> 1))) bad = true;
@@ -566,15 +591,21 @@ void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, co
                          const ChunkGeom& g, int nlay, uint8_t* sym, unsigned long long sym_layer_stride, int* error,
                          cudaStream_t s)
 {
-    const unsigned int cpw = 32 / (g.nseek + 1);
+    const unsigned int nsub = g.nseek + 1;        // make_geom grants 0, 1, 3 or 7 seek points
+    const unsigned int cpw = 32 / nsub;
     dim3 grid((g.nchunks + cpw - 1) / cpw, nlay, 1);
-    const int smem = 256 * 32 * 4 + kLutSize * 32;      // sized for cpw == 32; fewer columns use less
+    const int smem = (257 * 4 + kLutSize) * (int)cpw;
     static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(range_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (!configured) {                            // 62.9 KB for one lane per chunk: above the 48 KB default
+        cudaFuncSetAttribute(range_decode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (257 * 4 + kLutSize) * 32);
         configured = true;
     }
-    range_decode_kernel<<<grid, 32, (256 * 4 + kLutSize) * cpw, s>>>(blob, offs, lay_off, g, sym, sym_layer_stride, error);
+    switch (nsub) {
+    case 1: range_decode_kernel<1><<<grid, 32, smem, s>>>(blob, offs, lay_off, g, sym, sym_layer_stride, error); break;
+    case 2: range_decode_kernel<2><<<grid, 32, smem, s>>>(blob, offs, lay_off, g, sym, sym_layer_stride, error); break;
+    case 4: range_decode_kernel<4><<<grid, 32, smem, s>>>(blob, offs, lay_off, g, sym, sym_layer_stride, error); break;
+    default: range_decode_kernel<8><<<grid, 32, smem, s>>>(blob, offs, lay_off, g, sym, sym_layer_stride, error); break;
+    }
     note_launch(1);
 }
 
