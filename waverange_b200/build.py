@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwaverange_b200.so")
-SOURCES = ["codec.cu", "wavelet.cu", "quant.cu", "rangecoder.cu", "compat.cpp"]
-HEADERS = ["wr_common.cuh", "wr_kernels.h", "../../include/waverange_b200.h", "../../include/waverange.h"]
+SOURCES = ["codec.cu", "wavelet.cu", "wavelet_fused.cu", "quant.cu", "rangecoder.cu", "compat.cpp"]
+HEADERS = ["wr_common.cuh", "wr_kernels.h", "wavelet_pairs.cuh", "../../include/waverange_b200.h", "../../include/waverange.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

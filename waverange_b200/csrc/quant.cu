@@ -85,6 +85,27 @@ __global__ void layer_params_kernel(DevState* st, int l)
 void layer_params(DevState* st, int layer, cudaStream_t s) { layer_params_kernel<<<1, 1, 0, s>>>(st, layer); note_launch(1); }
 
 // One CTA per coder block (<= 60000 symbols).  reference wrappers.cpp:384-398 + rangecod.c:389-397
+// Each thread keeps four independent 8-byte loads in flight (HBM latency needs ~35 KB in flight per
+// SM); extrema are tracked as doubles (fmin/fmax are order-independent, as in the reference) and
+// turned into ordered keys once per thread.
+template <int LAYER>
+__device__ __forceinline__ double quantise_one(double r, const double* s_a, const double* s_b, const double* s_d,
+                                               const double* s_m, int layer, unsigned int& q)
+{
+    const int nl = (LAYER >= 0) ? LAYER : layer;
+#pragma unroll
+    for (int m = 0; m < (LAYER >= 0 ? LAYER : kNLayMax - 1); m++) {          // replay earlier layers (:387-398)
+        if (LAYER < 0 && m >= nl) break;
+        const double fq = s_a[m] * r + s_b[m];
+        const unsigned int qm = (unsigned int)(unsigned char)__double2int_rz(fq);
+        r = r - ((double)qm * s_d[m] + s_m[m]);
+    }
+    const double fq = s_a[nl] * r + s_b[nl];
+    q = (unsigned int)(unsigned char)__double2int_rz(fq);
+    return r - ((double)q * s_d[nl] + s_m[nl]);
+}
+
+template <int LAYER>
 __global__ void __launch_bounds__(256) quantise_kernel(const double* __restrict__ coef, ChunkGeom g, int layer,
                                                        DevState* st, uint8_t* __restrict__ sym,
                                                        uint32_t* __restrict__ hist)
@@ -104,43 +125,53 @@ __global__ void __launch_bounds__(256) quantise_kernel(const double* __restrict_
     const unsigned int bs = (clen - boff < kBlock) ? (unsigned int)(clen - boff) : kBlock;
     const double* __restrict__ in = coef + cstart + boff;
     uint8_t* __restrict__ out = sym + (unsigned long long)c * g.pitch + boff;
-    unsigned long long kmin = kKeyMinInit, kmax = kKeyMaxInit;
+    double rmin = 0, rmax = 0;
+    bool any = false;
     const unsigned int lane = tid & 31;
-    for (unsigned int i0 = 0; i0 < bs; i0 += 256) {
-        unsigned int i = i0 + tid;
-        bool ok = i < bs;
-        unsigned int q = 0;
-        if (ok) {
-            double r = in[i];
-            for (int m = 0; m < layer; m++) {                // replay earlier layers (:387-398)
-                double fq = s_a[m] * r + s_b[m];
-                unsigned int qm = (unsigned int)(unsigned char)__double2int_rz(fq);
-                r = r - ((double)qm * s_d[m] + s_m[m]);
-            }
-            double fq = s_a[layer] * r + s_b[layer];
-            q = (unsigned int)(unsigned char)__double2int_rz(fq);
-            r = r - ((double)q * s_d[layer] + s_m[layer]);
-            out[i] = (uint8_t)q;
-            unsigned long long k = dkey(r);
-            kmin = k < kmin ? k : kmin;
-            kmax = k > kmax ? k : kmax;
+    for (unsigned int i0 = 0; i0 < bs; i0 += 1024) {
+        double r[4];
+        bool ok[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned int i = i0 + k * 256 + tid;
+            ok[k] = i < bs;
+            r[k] = ok[k] ? in[i] : 0.0;
         }
-        // warp-aggregated histogram update (peaked distributions would serialise plain atomics)
-        unsigned int act = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-            unsigned int peers = __match_any_sync(act, q);
-            if ((unsigned int)(__ffs(peers) - 1) == lane) atomicAdd(&s_hist[q], (unsigned int)__popc(peers));
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned int i = i0 + k * 256 + tid;
+            unsigned int q = 0;
+            if (ok[k]) {
+                const double res = quantise_one<LAYER>(r[k], s_a, s_b, s_d, s_m, layer, q);
+                out[i] = (uint8_t)q;
+                rmin = any ? fmin(rmin, res) : res;
+                rmax = any ? fmax(rmax, res) : res;
+                any = true;
+            }
+            // warp-aggregated histogram update (peaked distributions would serialise plain atomics)
+            const unsigned int act = __ballot_sync(0xffffffffu, ok[k]);
+            if (ok[k]) {
+                const unsigned int peers = __match_any_sync(act, q);
+                if ((unsigned int)(__ffs(peers) - 1) == lane) atomicAdd(&s_hist[q], (unsigned int)__popc(peers));
+            }
         }
     }
     __syncthreads();
     hist[(unsigned long long)b * 256 + tid] = s_hist[tid];
-    block_minmax_commit(kmin, kmax, &st->rmin_key[layer + 1], &st->rmax_key[layer + 1]);
+    block_minmax_commit(any ? dkey(rmin) : kKeyMinInit, any ? dkey(rmax) : kKeyMaxInit, &st->rmin_key[layer + 1],
+                        &st->rmax_key[layer + 1]);
 }
 
 void quantise_layer(const double* coef, const ChunkGeom& g, int layer, DevState* st, uint8_t* sym, uint32_t* hist,
                     cudaStream_t s)
 {
-    quantise_kernel<<<g.nblocks, 256, 0, s>>>(coef, g, layer, st, sym, hist);
+    switch (layer) {
+    case 0: quantise_kernel<0><<<g.nblocks, 256, 0, s>>>(coef, g, layer, st, sym, hist); break;
+    case 1: quantise_kernel<1><<<g.nblocks, 256, 0, s>>>(coef, g, layer, st, sym, hist); break;
+    case 2: quantise_kernel<2><<<g.nblocks, 256, 0, s>>>(coef, g, layer, st, sym, hist); break;
+    case 3: quantise_kernel<3><<<g.nblocks, 256, 0, s>>>(coef, g, layer, st, sym, hist); break;
+    default: quantise_kernel<-1><<<g.nblocks, 256, 0, s>>>(coef, g, layer, st, sym, hist); break;
+    }
     note_launch(1);
 }
 
@@ -151,18 +182,27 @@ __global__ void __launch_bounds__(256) dequantise_kernel(const uint8_t* __restri
                                                          ChunkGeom g, int nlay, DequantParams p,
                                                          double* __restrict__ coef)
 {
+    __shared__ double s_d[kNLayMax], s_m[kNLayMax];
+    if (threadIdx.x < kNLayMax) { s_d[threadIdx.x] = p.deps[threadIdx.x]; s_m[threadIdx.x] = p.minval[threadIdx.x]; }
+    __syncthreads();
     const unsigned int c = blockIdx.x;
     const unsigned long long cstart = (unsigned long long)c * g.chunk_len;
-    const unsigned long long clen = (g.ntot - cstart < g.chunk_len) ? g.ntot - cstart : g.chunk_len;
+    const unsigned int clen = (unsigned int)((g.ntot - cstart < g.chunk_len) ? g.ntot - cstart : g.chunk_len);
     const uint8_t* __restrict__ in = sym + (unsigned long long)c * g.pitch;
-    for (unsigned long long i = blockIdx.y * (unsigned long long)blockDim.x + threadIdx.x; i < clen;
-         i += (unsigned long long)gridDim.y * blockDim.x) {
-        double f = 0;
+    double* __restrict__ out = coef + cstart;
+    for (unsigned long long i0 = blockIdx.y * 1024ull; i0 < clen; i0 += (unsigned long long)gridDim.y * 1024ull) {
+        double f[4] = {0, 0, 0, 0};
         for (int l = 0; l < nlay; l++) {
-            double q = (double)in[(unsigned long long)l * layer_stride + i];
-            f = f + (q * p.deps[l] + p.minval[l]);
+            const uint8_t* __restrict__ il = in + (unsigned long long)l * layer_stride + i0 + threadIdx.x;
+            unsigned int q[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) q[k] = (i0 + k * 256 + threadIdx.x < clen) ? il[k * 256] : 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) f[k] = f[k] + ((double)q[k] * s_d[l] + s_m[l]);
         }
-        coef[cstart + i] = f;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (i0 + k * 256 + threadIdx.x < clen) out[i0 + k * 256 + threadIdx.x] = f[k];
     }
 }
 
@@ -171,9 +211,12 @@ void dequantise(const uint8_t* sym, unsigned long long layer_stride, const Chunk
 {
     DequantParams p{};
     for (int l = 0; l < nlay; l++) { p.deps[l] = deps[l]; p.minval[l] = minval[l]; }
-    unsigned long long per = (g.chunk_len + 255) / 256;
-    unsigned int gy = (unsigned int)(per < 64 ? (per ? per : 1) : 64);
-    if (g.nchunks == 1) gy = (unsigned int)(per < 148 * 32 ? (per ? per : 1) : 148 * 32);
+    unsigned long long per = (g.chunk_len + 1023) / 1024;
+    unsigned int gy = (unsigned int)(per < 8 ? (per ? per : 1) : 8);
+    if (g.nchunks < 148 * 4) {
+        unsigned long long want = (148ull * 16 + g.nchunks - 1) / g.nchunks;
+        gy = (unsigned int)(per < want ? (per ? per : 1) : want);
+    }
     dim3 grid(g.nchunks, gy, 1);
     dequantise_kernel<<<grid, 256, 0, s>>>(sym, layer_stride, g, nlay, p, coef);
     note_launch(1);

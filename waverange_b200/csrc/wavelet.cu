@@ -14,99 +14,9 @@
 // every final coefficient to the coefficient array, reducing their min/max on the way.
 #include "wr_common.cuh"
 #include "wr_kernels.h"
+#include "wavelet_pairs.cuh"
 
 namespace wrb {
-
-// ------------------------------------------------------------------------------------------
-// Forward lifting of output pairs [i0, i0+R) of a line of N > 1 samples.
-// reference: waveletcdf97_3d.c:101-132 (split, phantom :109, stages :112-125, scale :128-132)
-// ------------------------------------------------------------------------------------------
-template <int R, class LD>
-__device__ __forceinline__ void fwd_pairs(LD ld, int N, int i0, double (&so)[R], double (&dd)[R])
-{
-    const int M = (N + 1) >> 1;
-    double s0[R + 4], d0[R + 3];
-#pragma unroll
-    for (int t = 0; t < R + 4; t++) {
-        int j = i0 - 2 + t;
-        s0[t] = (j >= 0 && j < M) ? ld(2 * j) : 0.0;
-    }
-#pragma unroll
-    for (int t = 0; t < R + 3; t++) {
-        int j = i0 - 2 + t;
-        double v = 0.0;
-        if (j >= 0 && 2 * j + 1 < N) v = ld(2 * j + 1);
-        else if (t >= 1 && j == M - 1)            // N odd: phantom sample (:109)
-            v = (s0[t - 1] * WRB_E0 + d0[t >= 1 ? t - 1 : 0] * WRB_E1) + s0[t] * WRB_E2;
-        d0[t] = v;
-    }
-    double d1[R + 3], s1[R + 2], d2[R + 1];
-#pragma unroll
-    for (int t = 0; t < R + 3; t++) {
-        int j = i0 - 2 + t;
-        d1[t] = (j < M - 1) ? d0[t] + WRB_LA * (s0[t + 1] + s0[t]) : d0[t] + (WRB_LA * 2) * s0[t];
-    }
-#pragma unroll
-    for (int t = 0; t < R + 2; t++) {
-        int j = i0 - 1 + t;
-        s1[t] = (j == 0) ? s0[t + 1] + (WRB_LB * 2) * d1[t + 1] : s0[t + 1] + WRB_LB * (d1[t + 1] + d1[t]);
-    }
-#pragma unroll
-    for (int t = 0; t < R + 1; t++) {
-        int j = i0 - 1 + t;
-        d2[t] = (j < M - 1) ? d1[t + 1] + WRB_LC * (s1[t + 1] + s1[t]) : d1[t + 1] + (WRB_LC * 2) * s1[t];
-    }
-#pragma unroll
-    for (int t = 0; t < R; t++) {
-        int j = i0 + t;
-        double s2 = (j == 0) ? s1[t + 1] + (WRB_LD * 2) * d2[t + 1] : s1[t + 1] + WRB_LD * (d2[t + 1] + d2[t]);
-        so[t] = s2 * WRB_SCL;
-        dd[t] = d2[t + 1] * WRB_PSCL;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Inverse lifting: samples x[2j], x[2j+1] for j in [i0, i0+R) of a line of M > 1 coefficients
-// stored low half [0,Q) then high half [Q,M).   reference: waveletcdf97_3d.c:311-337
-// ------------------------------------------------------------------------------------------
-template <int R, class LD>
-__device__ __forceinline__ void inv_pairs(LD ld, int M, int i0, double (&ev)[R], double (&od)[R])
-{
-    const int Q = (M + 1) >> 1, NH = M - Q;
-    double h[R + 4], l[R + 3];
-#pragma unroll
-    for (int t = 0; t < R + 4; t++) {
-        int j = i0 - 2 + t;
-        h[t] = (j >= 0 && j < NH) ? ld(Q + j) * WRB_SCL : 0.0;      // phantom detail = 0 (:314)
-    }
-#pragma unroll
-    for (int t = 0; t < R + 3; t++) {
-        int j = i0 - 1 + t;
-        l[t] = (j >= 0 && j < Q) ? ld(j) * WRB_PSCL : 0.0;
-    }
-    double s1[R + 3], d1[R + 2], s2[R + 1];
-#pragma unroll
-    for (int t = 0; t < R + 3; t++) {
-        int j = i0 - 1 + t;
-        s1[t] = (j == 0) ? l[t] - (WRB_LD * 2) * h[t + 1] : l[t] - WRB_LD * (h[t + 1] + h[t]);
-    }
-#pragma unroll
-    for (int t = 0; t < R + 2; t++) {
-        int j = i0 - 1 + t;
-        d1[t] = (j < Q - 1) ? h[t + 1] - WRB_LC * (s1[t + 1] + s1[t]) : h[t + 1] - (WRB_LC * 2) * s1[t];
-    }
-#pragma unroll
-    for (int t = 0; t < R + 1; t++) {
-        int j = i0 + t;
-        s2[t] = (j == 0) ? s1[t + 1] - (WRB_LB * 2) * d1[t + 1] : s1[t + 1] - WRB_LB * (d1[t + 1] + d1[t]);
-    }
-#pragma unroll
-    for (int t = 0; t < R; t++) {
-        int j = i0 + t;
-        ev[t] = s2[t];
-        od[t] = (j < Q - 1) ? d1[t + 1] - WRB_LA * (s2[t + 1] + s2[t]) : d1[t + 1] - (WRB_LA * 2) * s2[t];
-    }
-}
 
 // ------------------------------------------------------------------------------------------
 // Pass kernels.  Thread (tx, ty, tz): for DIM 0 tx indexes groups of R pairs along x; for
@@ -325,6 +235,13 @@ void wavelet_forward(const void* src, int src_is_f32, double* coef, double* tmp,
         const int m0 = half_up(n0), m1 = half_up(n1), m2 = half_up(n2);
         const bool last = (k == levels);
         double* lll = last ? nullptr : ((k & 1) ? lllA : lllB);
+        if (fused_forward_supported(n0, n1, n2)) {          // one HBM round trip for this level
+            fused_forward_level(cur, cur_f32 ? 1 : 0, csy, csz, coef, ay, az, lll, n0, n1, n2, (k == 1) ? fmin : nullptr,
+                                (k == 1) ? fmax : nullptr, cmin, cmax, s);
+            cur = lll; csy = m0; csz = (long long)m0 * m1; cur_f32 = false;
+            n0 = m0; n1 = m1; n2 = m2;
+            continue;
+        }
         FwdPassArgs a{};
         a.n0 = n0; a.n1 = n1; a.n2 = n2; a.m0 = m0; a.m1 = m1;
         // x: cur -> coef (box region used as scratch)

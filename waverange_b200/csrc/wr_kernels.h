@@ -12,6 +12,13 @@ void wavelet_forward(const void* src, int src_is_f32, double* coef, double* tmp,
 void wavelet_inverse(double* coef, double* tmp, double* lllA, double* lllB, void* out, int out_is_f32,
                      int nx, int ny, int nz, int levels, cudaStream_t s);
 
+// ---- wavelet_fused.cu ---------------------------------------------------------------------
+bool fused_forward_supported(int n0, int n1, int n2);
+void fused_forward_level(const void* src, int src_is_f32, long long ssy, long long ssz, double* coef, long long ay,
+                         long long az, double* lll, int n0, int n1, int n2, unsigned long long* in_min,
+                         unsigned long long* in_max, unsigned long long* out_min, unsigned long long* out_max,
+                         cudaStream_t s);
+
 // ---- quant.cu -----------------------------------------------------------------------------
 // Geometry of the chunked symbol container of one layer.
 //   chunk c covers symbols [c*chunk_len, min(ntot,(c+1)*chunk_len)); each chunk is cut into coder
