@@ -48,7 +48,7 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def synth_field(torch, n, seed, device, dtype, nm=48, expo=-5.0 / 6.0):
+def synth_field(torch, n, seed, device, dtype, nm=48, expo=-5.0 / 6.0, nz_total=None, z0=0, nzl=None):
     """Turbulence-like field: sum of nm plane waves with random integer wavevectors, random phases,
     amplitude |k|^expo, evaluated in f64 on the device slab by slab through
     separable complex tables, then rounded to `dtype`.  Deterministic for a given seed."""
@@ -59,18 +59,22 @@ def synth_field(torch, n, seed, device, dtype, nm=48, expo=-5.0 / 6.0):
     ph = rng.uniform(0, 2 * np.pi, nm)
     amp = (k ** 2).sum(1) ** (expo / 2.0 * 1.0)
     x = np.arange(n, dtype=np.float64) / n
-    tab = [np.exp(2j * np.pi * np.outer(k[:, d], x)) for d in range(3)]          # (nm, n)
+    nz_total = nz_total or n
+    nzl = nzl or nz_total
+    zc = (z0 + np.arange(nzl, dtype=np.float64)) / n        # same wave numbers per unit length along z
+    tab = [np.exp(2j * np.pi * np.outer(k[:, 0], x)), np.exp(2j * np.pi * np.outer(k[:, 1], x)),
+           np.exp(2j * np.pi * np.outer(k[:, 2], zc))]
     coef = torch.from_numpy(amp * np.exp(1j * ph)).to(device)
     X = torch.from_numpy(tab[0]).to(device)
     Y = torch.from_numpy(tab[1]).to(device)
     Z = torch.from_numpy(tab[2]).to(device)
-    out = torch.empty((n, n, n), dtype=dtype, device=device)
+    out = torch.empty((nzl, n, n), dtype=dtype, device=device)
     slab = 16
-    for z0 in range(0, n, slab):
-        zc = Z[:, z0:z0 + slab] * coef[:, None]                                  # (nm, slab)
+    for zs in range(0, nzl, slab):
+        zc = Z[:, zs:zs + slab] * coef[:, None]                                  # (nm, slab)
         yz = torch.einsum("mz,my->mzy", zc, Y)                                   # (nm, slab, n)
         f = torch.einsum("mzy,mx->zyx", yz, X).imag
-        out[z0:z0 + slab] = f.to(dtype)
+        out[zs:zs + slab] = f.to(dtype)
     return out
 
 
@@ -90,7 +94,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile(prefix="wrb_clocks_", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -190,12 +194,29 @@ def run_ours(args, rank, world, local_rank):
     n = args.size
     nz = ny = nx = n
     ntot = n ** 3
-    field = synth_field(torch, n, 1234 + rank, dev, torch.float32)
+    slab_mode = world > 1
+    nz_total, z0 = n * world, n * rank       # N > 1: ONE field of n x n x (n*N), z-slab partitioned (weak scaling)
+    field = synth_field(torch, n, 1234, dev, torch.float32, nz_total=nz_total, z0=z0, nzl=n)
     nbytes = ntot * 4
 
     stream = torch.cuda.current_stream()
     codec = api.Codec(device=local_rank, stream=stream.cuda_stream)
     codec.set_timing(True)
+    hooks = None
+    if slab_mode:
+        from waverange_b200 import slab
+        hooks = slab.DistHooks(torch, dist, cuda=True)
+        codec.set_slab(rank, world, hooks.halo_cb, hooks.reduce_cb)
+
+    def encode_dev(src_ptr, dst_ptr):
+        if slab_mode:
+            return codec.encode_slab_device(src_ptr, api.F32, nx, ny, nz_total, z0, nz, TOL, dst_ptr, cap)
+        return codec.encode_device(src_ptr, api.F32, nx, ny, nz, TOL, dst_ptr, cap)
+
+    def decode_dev(dst_ptr, hh, src_ptr):
+        if slab_mode:
+            return codec.decode_slab_device(dst_ptr, api.F32, nx, ny, nz_total, z0, nz, hh, src_ptr)
+        return codec.decode_device(dst_ptr, api.F32, nx, ny, nz, hh, src_ptr)
     _, cap = api.setup_wr(nx, ny, nz)
     cap = min(cap, ntot * 5 + (1 << 20))          # f32 field at tol 1e-4 codes to < 2 B/pt; keep HBM use modest
     blob = torch.empty(cap + 64, dtype=torch.uint8, device=dev)
@@ -211,8 +232,8 @@ def run_ours(args, rank, world, local_rank):
     h = None
     # ---- device-resident arm ----------------------------------------------------------------
     for it in range(args.warmup):
-        h = codec.encode_device(field.data_ptr(), api.F32, nx, ny, nz, TOL, blob.data_ptr(), cap)
-        codec.decode_device(recon.data_ptr(), api.F32, nx, ny, nz, h, blob.data_ptr())
+        h = encode_dev(field.data_ptr(), blob.data_ptr())
+        decode_dev(recon.data_ptr(), h, blob.data_ptr())
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -224,10 +245,10 @@ def run_ours(args, rank, world, local_rank):
     tot_ev0.record(stream)
     for it in range(args.steps):
         ev[0].record(stream)
-        h = codec.encode_device(field.data_ptr(), api.F32, nx, ny, nz, TOL, blob.data_ptr(), cap)
+        h = encode_dev(field.data_ptr(), blob.data_ptr())
         se = codec.stage_ms()
         ev[1].record(stream)
-        codec.decode_device(recon.data_ptr(), api.F32, nx, ny, nz, h, blob.data_ptr())
+        decode_dev(recon.data_ptr(), h, blob.data_ptr())
         sd = codec.stage_ms()
         ev[2].record(stream)
         torch.cuda.synchronize()
@@ -241,8 +262,10 @@ def run_ours(args, rank, world, local_rank):
     wall_ms = (time.perf_counter() - t_wall0) * 1e3 / args.steps
 
     # correctness guard inside the bench: the reconstruction meets the requested tolerance
-    err = (recon.view(n, n, n).double() - field.double()).abs().max().item()
-    amax = field.double().abs().max().item()
+    errt = torch.stack([(recon.view(n, n, n).double() - field.double()).abs().max(), field.double().abs().max()])
+    if world > 1:
+        dist.all_reduce(errt, op=dist.ReduceOp.MAX)
+    err, amax = errt[0].item(), errt[1].item()
     assert err <= TOL * amax * 1.0000001, "reconstruction error %.3e exceeds tolerance" % (err / amax)
 
     # ---- end-to-end arm: host buffers through the C ABI (pinned memory, copies timed) ---------
@@ -255,8 +278,17 @@ def run_ours(args, rank, world, local_rank):
     for it in range(0 if args.no_e2e else max(1, min(args.warmup, 2)) + args.steps):
         barrier()
         t0 = time.perf_counter()
-        hh, data = codec.encode_host(np_field, TOL, out=np_blob)
-        codec.decode_host((n, n, n), hh, data, out=np_rec)
+        if slab_mode:     # same traffic as wrb_encode_host / wrb_decode_host: H2D field, D2H stream, H2D stream, D2H field
+            d_in = h_field.to(dev, non_blocking=True)
+            hh = encode_dev(d_in.data_ptr(), blob.data_ptr())
+            h_blob[:hh.ntot_enc].copy_(blob[:hh.ntot_enc], non_blocking=True)
+            torch.cuda.synchronize()
+            blob[:hh.ntot_enc].copy_(h_blob[:hh.ntot_enc], non_blocking=True)
+            decode_dev(recon.data_ptr(), hh, blob.data_ptr())
+            h_rec.copy_(recon.view(n, n, n), non_blocking=True)
+        else:
+            hh, data = codec.encode_host(np_field, TOL, out=np_blob)
+            codec.decode_host((n, n, n), hh, data, out=np_rec)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         if it >= max(1, min(args.warmup, 2)):
@@ -299,7 +331,9 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": "%d^3 float32 turbulence-like field, tol 1e-4%s" % (n, " (BASELINE.json configs[1])" if n == N_FIELD else " (profiling size)"),
                    "field_bytes": nbytes, "tolerance": TOL, "nlay": nlay, "ntot_enc": int(h.ntot_enc),
                    "ratio_vs_f32": nbytes / max(1, int(h.ntot_enc)), "chunk_symbols": 59999,
-                   "fields": "%d independent field(s), one per GPU" % world,
+                   "fields": ("one %dx%dx%d field" % (n, n, n)) if world == 1 else
+                             ("one %dx%dx%d field, z-slab partitioned over %d GPUs: NCCL halo exchange per level "
+                              "(4 planes below / 3 above), all_reduce of extrema per layer" % (n, n, n * world, world)),
                    "l2": "working set (0.5 GB field + 2 GB scratch) exceeds the 126 MB L2; no explicit flush"},
         "compress_gbs": world * nbytes / (enc_mean * 1e-3) / 1e9,
         "decompress_gbs": world * nbytes / (dec_mean * 1e-3) / 1e9,
@@ -310,9 +344,10 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "scope": "forward wavelet + quantise kernels of one compress (stage events)",
                      "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
                      "algorithmic_bytes": a_c, "peak_source": peak_src},
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes + int(h.ntot_enc),
-                "d2h_bytes_per_step": nbytes + int(h.ntot_enc), "ms_per_step": e2e_step,
-                "api": "wrb_encode_host + wrb_decode_host (f32 pinned host buffers)"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": world * (nbytes + int(h.ntot_enc)),
+                "d2h_bytes_per_step": world * (nbytes + int(h.ntot_enc)), "ms_per_step": e2e_step,
+                "api": "wrb_encode_host + wrb_decode_host (f32 pinned host buffers)" if world == 1 else
+                       "pinned H2D + wrb_encode_slab_device + D2H, H2D + wrb_decode_slab_device + D2H per rank"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "host_wall_ms_per_step": wall_ms,

@@ -92,6 +92,29 @@ int wrb_encode_device(wrb_codec* c, const void* d_field, int dtype, int nx, int 
 int wrb_decode_device(wrb_codec* c, void* d_field_out, int dtype, int nx, int ny, int nz, const wrb_header* hdr,
                       const unsigned char* d_data_enc);
 
+/* ---- z-slab partition of one large field across the GPUs of a box -------- */
+/* Rank r of n owns the planes [z0, z0+nzl) of an (nx, ny, nz) field (nz % 16 == 0, z0 and nzl multiples
+ * of 32).  x/y lifting is slab-local; the z lifting of every level reads 4 planes from below and 3
+ * from above (inverse: 2 + 2 per band) that `halo` fetches from the z-neighbours, and the field /
+ * coefficient / per-layer residual extrema go through `reduce` (the codec packs them so that one
+ * MIN reduction of two int64 values is enough).  Both callbacks must be ordered
+ * with the codec's stream (torch.distributed over NCCL in waverange_b200/slab.py).  Each rank gets
+ * its own container: the coefficients of the global transform that live on its slab, in the
+ * wavelet-space order of a local (nx, ny, nzl) array; deps_vec / minval_vec / nlay are identical on
+ * all ranks.  Decompression uses the same partition. */
+typedef int (*wrb_halo_fn)(void* user, void* d_buf, int elem_bytes, long long plane_elems, int nplanes_own,
+                           int halo_lo, int halo_hi);
+/* in-place global MIN over `count` signed 64-bit integers on the device (one all_reduce) */
+typedef int (*wrb_reduce_fn)(void* user, long long* d_buf, int count);
+int wrb_set_slab(wrb_codec* c, int rank, int nranks, wrb_halo_fn halo, wrb_reduce_fn reduce, void* user);
+int wrb_encode_slab_device(wrb_codec* c, const void* d_field_slab, int dtype, int nx, int ny, int nz, int z0, int nzl,
+                           int wtflag, double tolrel, wrb_header* hdr, unsigned char* d_data_enc, unsigned long cap);
+int wrb_decode_slab_device(wrb_codec* c, void* d_field_slab_out, int dtype, int nx, int ny, int nz, int z0, int nzl,
+                           const wrb_header* hdr, const unsigned char* d_data_enc);
+/* stage-level variant of wrb_quantise_device for a slab (rank-local coefficient / symbol order) */
+int wrb_quantise_slab_device(wrb_codec* c, const void* d_field_slab, int dtype, int nx, int ny, int nz, int z0, int nzl,
+                             int wtflag, double tolrel, wrb_header* hdr, double* d_coef, unsigned char* d_sym);
+
 /* ---- host-buffer path (copies inside) ------------------------------------------------------- */
 int wrb_encode_host(wrb_codec* c, const void* field, int dtype, int nx, int ny, int nz, int wtflag, double tolrel,
                     wrb_header* hdr, unsigned char* data_enc, unsigned long cap);

@@ -41,12 +41,17 @@ class WaveRangeError(RuntimeError):
     pass
 
 
+# callbacks of the z-slab partition (include/waverange_b200.h: wrb_halo_fn, wrb_reduce_fn)
+HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int)
+REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)
+
+
 _lib = None
 
 # every symbol include/waverange_b200.h and include/waverange.h declare
 EXPORTS = ["wrb_create", "wrb_destroy", "wrb_last_error", "wrb_set_stream", "wrb_set_chunk_blocks", "wrb_set_seek_points",
            "wrb_launch_count", "wrb_trim", "wrb_setup", "wrb_encode_device", "wrb_decode_device",
-           "wrb_encode_host", "wrb_decode_host", "wrb_wavelet3d_device", "wrb_quantise_device",
+           "wrb_encode_host", "wrb_decode_host", "wrb_set_slab", "wrb_encode_slab_device", "wrb_decode_slab_device", "wrb_quantise_slab_device", "wrb_wavelet3d_device", "wrb_quantise_device",
            "wrb_range_encode_device", "wrb_range_decode_device", "wrb_ind_p2w_3d", "wrb_set_timing",
            "wrb_last_stage_ms",
            "encoding_wrap", "decoding_wrap", "setup_wr", "encoding_wrap_f", "decoding_wrap_f", "setup_wr_f"]
@@ -79,6 +84,10 @@ def lib():
     L.wrb_decode_device.argtypes = [vp, vp, i, i, i, i, H, vp]
     L.wrb_encode_host.argtypes = [vp, vp, i, i, i, i, i, d, H, vp, ul]
     L.wrb_decode_host.argtypes = [vp, vp, i, i, i, i, H, vp]
+    L.wrb_set_slab.argtypes = [vp, i, i, HALO_FN, REDUCE_FN, vp]
+    L.wrb_encode_slab_device.argtypes = [vp, vp, i, i, i, i, i, i, i, d, H, vp, ul]
+    L.wrb_decode_slab_device.argtypes = [vp, vp, i, i, i, i, i, i, H, vp]
+    L.wrb_quantise_slab_device.argtypes = [vp, vp, i, i, i, i, i, i, i, d, H, vp, vp]
     L.wrb_wavelet3d_device.argtypes = [vp, vp, i, i, i, i]
     L.wrb_quantise_device.argtypes = [vp, vp, i, i, i, i, i, d, H, vp, vp]
     L.wrb_range_encode_device.argtypes = [vp, vp, ul, ul, vp, ul, C.POINTER(ul), C.POINTER(ul)]
@@ -238,6 +247,24 @@ class Codec:
 
     def decode_device(self, d_out, dtype, nx, ny, nz, h, d_data):
         self._ck(self.L.wrb_decode_device(self.h, d_out, dtype, nx, ny, nz, C.byref(h), d_data))
+
+    # ---- z-slab partition -----------------------------------------------------------------
+    def set_slab(self, rank, nranks, halo_cb, reduce_cb):
+        """halo_cb / reduce_cb: HALO_FN / REDUCE_FN instances (kept alive by the caller)"""
+        self._ck(self.L.wrb_set_slab(self.h, rank, nranks, halo_cb, reduce_cb, None))
+
+    def encode_slab_device(self, d_field, dtype, nx, ny, nz, z0, nzl, tol, d_out, cap, wtflag=1):
+        h = Header()
+        self._ck(self.L.wrb_encode_slab_device(self.h, d_field, dtype, nx, ny, nz, z0, nzl, wtflag, tol, C.byref(h), d_out, cap))
+        return h
+
+    def quantise_slab_device(self, d_field, dtype, nx, ny, nz, z0, nzl, tol, wtflag=1, d_coef=None, d_sym=None):
+        h = Header()
+        self._ck(self.L.wrb_quantise_slab_device(self.h, d_field, dtype, nx, ny, nz, z0, nzl, wtflag, tol, C.byref(h), d_coef, d_sym))
+        return h
+
+    def decode_slab_device(self, d_out, dtype, nx, ny, nz, z0, nzl, h, d_data):
+        self._ck(self.L.wrb_decode_slab_device(self.h, d_out, dtype, nx, ny, nz, z0, nzl, C.byref(h), d_data))
 
     # ---- host path -------------------------------------------------------------------------
     def encode_host(self, fld, tol, wtflag=1, out=None):

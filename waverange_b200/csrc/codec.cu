@@ -45,7 +45,8 @@ struct wrb_codec {
     int chunk_blocks = 1;
     int seek_points = 3;             // decoder entry points inside a chunk (4 lanes decode one chunk)
     std::string err;
-    DevBuf coef, tmp, lllA, lllB, sym, hist, slots, lens, dstoff, seek, state, blob, field, offs, layoff, misc;
+    DevBuf coef, tmp, lllA, lllB, sym, hist, slots, lens, dstoff, seek, state, blob, field, offs, layoff, misc, ext;
+    SlabHooks hooks;                  // z-slab partition collectives (nranks == 1: none)
     DevState* h_state = nullptr;      // pinned
     unsigned long long* h_u64 = nullptr;   // pinned scratch (64 KiB)
     int timing = 0;
@@ -102,7 +103,7 @@ int wrb_trim(wrb_codec* c)
     if (!c) return WRB_E_ARG;
     cudaSetDevice(c->device);
     DevBuf* all[] = {&c->coef, &c->tmp, &c->lllA, &c->lllB, &c->sym, &c->hist, &c->slots, &c->lens,
-                     &c->dstoff, &c->seek, &c->blob, &c->field, &c->offs, &c->layoff, &c->misc};
+                     &c->dstoff, &c->seek, &c->blob, &c->field, &c->offs, &c->layoff, &c->misc, &c->ext};
     for (DevBuf* b : all) b->release();
     return 0;
 }
@@ -192,6 +193,19 @@ __global__ void __launch_bounds__(256) pad_hist_kernel(const uint8_t* __restrict
     hist[(unsigned long long)b * 256 + tid] = s_hist[tid];
 }
 
+// extrema keys <-> one signed-comparable buffer: buf[0] = min key, buf[1] = ~max key, both with the top
+// bit flipped so that signed MIN orders them like the unsigned keys; max = ~min(~max)
+__global__ void pack_keys_kernel(const unsigned long long* kmin, const unsigned long long* kmax, long long* buf)
+{
+    buf[0] = (long long)(*kmin ^ 0x8000000000000000ull);
+    buf[1] = (long long)(~*kmax ^ 0x8000000000000000ull);
+}
+__global__ void unpack_keys_kernel(unsigned long long* kmin, unsigned long long* kmax, const long long* buf)
+{
+    *kmin = (unsigned long long)buf[0] ^ 0x8000000000000000ull;
+    *kmax = ~((unsigned long long)buf[1] ^ 0x8000000000000000ull);
+}
+
 __global__ void set_nlay_kernel(DevState* st, int nlay) { st->nlay = nlay; st->error = 0; }
 
 static int grid_for(unsigned long long n)
@@ -205,15 +219,19 @@ static int grid_for(unsigned long long n)
 // ------------------------------------------------------------------------------------------
 // buffer sizing
 // ------------------------------------------------------------------------------------------
-static int ensure_transform_buffers(wrb_codec* c, int nx, int ny, int nz)
+struct SlabGeom { int nz_global, z0; };   // slab mode: the nz passed around is the LOCAL plane count
+
+static int ensure_transform_buffers(wrb_codec* c, int nx, int ny, int nz, bool slab = false)
 {
     const size_t ntot = (size_t)nx * ny * nz;
     const size_t m1 = (size_t)half_up(nx) * half_up(ny) * half_up(nz);
     const size_t m2 = (size_t)half_up(half_up(nx)) * half_up(half_up(ny)) * half_up(half_up(nz));
     CK(c->coef.ensure(ntot * 8));
-    CK(c->tmp.ensure(ntot * 8));
-    CK(c->lllA.ensure(m1 * 8 + 64));
-    CK(c->lllB.ensure(m2 * 8 + 64));
+    CK(c->tmp.ensure((ntot + (slab ? 7ull * nx * ny : 0ull)) * 8));
+    if (slab) CK(c->ext.ensure(((size_t)nz + 8) * nx * ny * 8));
+    const size_t h1 = slab ? 7ull * half_up(nx) * half_up(ny) : 0, h2 = slab ? 7ull * half_up(half_up(nx)) * half_up(half_up(ny)) : 0;
+    CK(c->lllA.ensure((m1 + h1) * 8 + 64));      // slab mode: room for 4 + 3 halo planes
+    CK(c->lllB.ensure((m2 + h2) * 8 + 64));
     CK(c->state.ensure(sizeof(DevState)));
     return 0;
 }
@@ -253,20 +271,41 @@ static void header_from_state(const DevState& s, int wtflag, wrb_header* hdr)
 
 // transform + all layers; leaves coefficients in c->coef, symbols (padded) in c->sym, histograms
 // in c->hist and layer parameters in the device state
+// global min / max of one extrema pair across the ranks of a slab partition
+static int reduce_extrema(wrb_codec* c, unsigned long long* kmin, unsigned long long* kmax)
+{
+    long long* buf = (long long*)((char*)c->misc.p + 64);
+    pack_keys_kernel<<<1, 1, 0, c->stream>>>(kmin, kmax, buf);
+    if (c->hooks.reduce(c->hooks.user, buf, 2)) return 1;
+    unpack_keys_kernel<<<1, 1, 0, c->stream>>>(kmin, kmax, buf);
+    note_launch(2);
+    return 0;
+}
+
 static int run_transform_and_quantise(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag,
-                                      double tolrel, const ChunkGeom& g)
+                                      double tolrel, const ChunkGeom& g, const SlabGeom* sg = nullptr)
 {
     DevState* st = (DevState*)c->state.p;
     cudaStream_t s = c->stream;
     state_init(st, s);
     if (c->timing) cudaEventRecord(c->ev[0], s);
-    wavelet_forward(d_field, dtype == WRB_F32, (double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p,
-                    (double*)c->lllB.p, nx, ny, nz, wtflag ? kWavLvl : 0, st, s);
+    const bool dist = sg != nullptr && c->hooks.nranks > 1;
+    if (sg != nullptr && wtflag) {
+        int rc = wavelet_forward_slab(d_field, dtype == WRB_F32, (double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p,
+                                      (double*)c->lllB.p, nx, ny, sg->nz_global, sg->z0, nz, kWavLvl, st, c->hooks, s);
+        if (rc) return fail(c, WRB_E_CUDA, "halo exchange callback failed");
+    } else {
+        wavelet_forward(d_field, dtype == WRB_F32, (double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p,
+                        (double*)c->lllB.p, nx, ny, nz, wtflag ? kWavLvl : 0, st, s);
+    }
+    if (dist && reduce_extrema(c, &st->fmin_key, &st->fmax_key)) return fail(c, WRB_E_CUDA, "reduce callback failed");
     state_prepare(st, tolrel, s);
     if (c->timing) cudaEventRecord(c->ev[1], s);
     const unsigned long long lstride = (unsigned long long)g.nchunks * g.pitch;
     const unsigned long long hstride = (unsigned long long)g.nblocks * 256;
     for (int l = 0; l < kNLayMax; l++) {
+        // global extrema of the coefficients (l == 0) / of the residual left by layer l-1 (wrappers.cpp:308-314)
+        if (dist && reduce_extrema(c, &st->rmin_key[l], &st->rmax_key[l])) return fail(c, WRB_E_CUDA, "reduce callback failed");
         layer_params(st, l, s);
         quantise_layer((const double*)c->coef.p, g, l, st, (uint8_t*)c->sym.p + l * lstride,
                        (uint32_t*)c->hist.p + l * hstride, s);
@@ -278,8 +317,10 @@ static int run_transform_and_quantise(wrb_codec* c, const void* d_field, int dty
 
 extern "C" {
 
-int wrb_encode_device(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag, double tolrel,
-                      wrb_header* hdr, unsigned char* d_data_enc, unsigned long cap)
+}  // extern "C"
+
+static int encode_impl(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag, double tolrel,
+                       wrb_header* hdr, unsigned char* d_data_enc, unsigned long cap, const SlabGeom* sg)
 {
     if (!c || !d_field || !hdr || !d_data_enc || nx < 1 || ny < 1 || nz < 1 || (dtype != WRB_F64 && dtype != WRB_F32))
         return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
@@ -288,11 +329,11 @@ int wrb_encode_device(wrb_codec* c, const void* d_field, int dtype, int nx, int 
     const ChunkGeom g = make_geom(ntot, chunk_len_of(c), (unsigned)c->seek_points);
     const int chunked = c->chunk_blocks > 0;
     int rc;
-    if ((rc = ensure_transform_buffers(c, nx, ny, nz))) return rc;
+    if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr))) return rc;
     if ((rc = ensure_coder_buffers(c, g, kNLayMax, true))) return rc;
     DevState* st = (DevState*)c->state.p;
     cudaStream_t s = c->stream;
-    if ((rc = run_transform_and_quantise(c, d_field, dtype, nx, ny, nz, wtflag, tolrel, g))) return rc;
+    if ((rc = run_transform_and_quantise(c, d_field, dtype, nx, ny, nz, wtflag, tolrel, g, sg))) return rc;
     const unsigned long long lstride = (unsigned long long)g.nchunks * g.pitch;
     const unsigned long long hstride = (unsigned long long)g.nblocks * 256;
     const unsigned long long sp = chunk_slot_pitch(g);
@@ -311,8 +352,43 @@ int wrb_encode_device(wrb_codec* c, const void* d_field, int dtype, int nx, int 
     return 0;
 }
 
-int wrb_quantise_device(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag,
-                        double tolrel, wrb_header* hdr, double* d_coef, unsigned char* d_sym)
+extern "C" {
+
+int wrb_encode_device(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag, double tolrel,
+                      wrb_header* hdr, unsigned char* d_data_enc, unsigned long cap)
+{
+    return encode_impl(c, d_field, dtype, nx, ny, nz, wtflag, tolrel, hdr, d_data_enc, cap, nullptr);
+}
+
+int wrb_set_slab(wrb_codec* c, int rank, int nranks, wrb_halo_fn halo, wrb_reduce_fn reduce, void* user)
+{
+    if (!c || nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && (!halo || !reduce))) return c ? fail(c, WRB_E_ARG, "bad slab setup") : WRB_E_ARG;
+    c->hooks.rank = rank; c->hooks.nranks = nranks; c->hooks.halo = halo; c->hooks.reduce = reduce; c->hooks.user = user;
+    return 0;
+}
+
+static int slab_check(wrb_codec* c, int nx, int ny, int nz, int z0, int nzl, int levels)
+{
+    if (nzl < 1 || z0 < 0 || z0 + nzl > nz) return fail(c, WRB_E_ARG, "slab outside the field");
+    if (!wavelet_slab_supported(nx, ny, nz, z0, nzl, levels))
+        return fail(c, WRB_E_ARG, "z-slab mode needs nz % 16 == 0 and slab start/size multiples of 32");
+    return 0;
+}
+
+int wrb_encode_slab_device(wrb_codec* c, const void* d_field_slab, int dtype, int nx, int ny, int nz, int z0, int nzl,
+                           int wtflag, double tolrel, wrb_header* hdr, unsigned char* d_data_enc, unsigned long cap)
+{
+    if (!c) return WRB_E_ARG;
+    int rc = slab_check(c, nx, ny, nz, z0, nzl, wtflag ? kWavLvl : 0);
+    if (rc) return rc;
+    SlabGeom sg{nz, z0};
+    return encode_impl(c, d_field_slab, dtype, nx, ny, nzl, wtflag, tolrel, hdr, d_data_enc, cap, &sg);
+}
+
+}  // extern "C"
+
+static int quantise_impl(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag,
+                         double tolrel, wrb_header* hdr, double* d_coef, unsigned char* d_sym, const SlabGeom* sg)
 {
     if (!c || !d_field || nx < 1 || ny < 1 || nz < 1 || (dtype != WRB_F64 && dtype != WRB_F32))
         return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
@@ -320,11 +396,11 @@ int wrb_quantise_device(wrb_codec* c, const void* d_field, int dtype, int nx, in
     const unsigned long long ntot = (unsigned long long)nx * ny * nz;
     const ChunkGeom g = make_geom(ntot, chunk_len_of(c), (unsigned)c->seek_points);
     int rc;
-    if ((rc = ensure_transform_buffers(c, nx, ny, nz))) return rc;
+    if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr))) return rc;
     if ((rc = ensure_coder_buffers(c, g, kNLayMax, false))) return rc;
     DevState* st = (DevState*)c->state.p;
     cudaStream_t s = c->stream;
-    if ((rc = run_transform_and_quantise(c, d_field, dtype, nx, ny, nz, wtflag, tolrel, g))) return rc;
+    if ((rc = run_transform_and_quantise(c, d_field, dtype, nx, ny, nz, wtflag, tolrel, g, sg))) return rc;
     CK(cudaMemcpyAsync(c->h_state, st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (hdr) { header_from_state(*c->h_state, wtflag, hdr); hdr->ntot_enc = 0; }
@@ -341,8 +417,28 @@ int wrb_quantise_device(wrb_codec* c, const void* d_field, int dtype, int nx, in
     return 0;
 }
 
-int wrb_decode_device(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int nz, const wrb_header* hdr,
-                      const unsigned char* d_data_enc)
+extern "C" {
+
+int wrb_quantise_device(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag,
+                        double tolrel, wrb_header* hdr, double* d_coef, unsigned char* d_sym)
+{
+    return quantise_impl(c, d_field, dtype, nx, ny, nz, wtflag, tolrel, hdr, d_coef, d_sym, nullptr);
+}
+
+int wrb_quantise_slab_device(wrb_codec* c, const void* d_field_slab, int dtype, int nx, int ny, int nz, int z0, int nzl,
+                             int wtflag, double tolrel, wrb_header* hdr, double* d_coef, unsigned char* d_sym)
+{
+    if (!c) return WRB_E_ARG;
+    int rc = slab_check(c, nx, ny, nz, z0, nzl, wtflag ? kWavLvl : 0);
+    if (rc) return rc;
+    SlabGeom sg{nz, z0};
+    return quantise_impl(c, d_field_slab, dtype, nx, ny, nzl, wtflag, tolrel, hdr, d_coef, d_sym, &sg);
+}
+
+}  // extern "C"
+
+static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int nz, const wrb_header* hdr,
+                       const unsigned char* d_data_enc, const SlabGeom* sg)
 {
     if (!c || !d_out || !hdr || nx < 1 || ny < 1 || nz < 1 || (dtype != WRB_F64 && dtype != WRB_F32))
         return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
@@ -383,7 +479,7 @@ int wrb_decode_device(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int 
     const ChunkGeom g = make_geom(ntot, chunk_len, (unsigned)nseek);
     if (g.nseek != nseek) return fail(c, WRB_E_FORMAT, "seek table does not match the chunk geometry");
     int rc;
-    if ((rc = ensure_transform_buffers(c, nx, ny, nz))) return rc;
+    if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr))) return rc;
     if ((rc = ensure_coder_buffers(c, g, nlay, false))) return rc;
     int* d_err = (int*)c->misc.p;
     CK(cudaMemsetAsync(d_err, 0, sizeof(int), s));
@@ -396,8 +492,14 @@ int wrb_decode_device(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int 
     if (c->timing) cudaEventRecord(c->ev[2], s);
     dequantise((const uint8_t*)c->sym.p, lstride, g, nlay, hdr->deps_vec, hdr->minval_vec, (double*)c->coef.p, s);
     if (c->timing) cudaEventRecord(c->ev[3], s);
-    wavelet_inverse((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, d_out, dtype == WRB_F32,
-                    nx, ny, nz, (int)hdr->wlev, s);
+    if (sg != nullptr && hdr->wlev > 0) {
+        if (wavelet_inverse_slab((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, (double*)c->ext.p,
+                                 d_out, dtype == WRB_F32, nx, ny, sg->nz_global, sg->z0, nz, (int)hdr->wlev, c->hooks, s))
+            return fail(c, WRB_E_CUDA, "halo exchange callback failed");
+    } else {
+        wavelet_inverse((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, d_out, dtype == WRB_F32,
+                        nx, ny, nz, (int)hdr->wlev, s);
+    }
     if (c->timing) cudaEventRecord(c->ev[4], s);
     int* h_err = (int*)(c->h_u64 + 128);
     CK(cudaMemcpyAsync(h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -406,6 +508,24 @@ int wrb_decode_device(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int 
     if (c->timing) for (int i = 0; i < 4; i++) cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]);
     if (*h_err) return fail(c, WRB_E_FORMAT, "range decoder: malformed chunk stream");
     return 0;
+}
+
+extern "C" {
+
+int wrb_decode_device(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int nz, const wrb_header* hdr,
+                      const unsigned char* d_data_enc)
+{
+    return decode_impl(c, d_out, dtype, nx, ny, nz, hdr, d_data_enc, nullptr);
+}
+
+int wrb_decode_slab_device(wrb_codec* c, void* d_out_slab, int dtype, int nx, int ny, int nz, int z0, int nzl,
+                           const wrb_header* hdr, const unsigned char* d_data_enc)
+{
+    if (!c || !hdr) return WRB_E_ARG;
+    int rc = slab_check(c, nx, ny, nz, z0, nzl, (int)hdr->wlev);
+    if (rc) return rc;
+    SlabGeom sg{nz, z0};
+    return decode_impl(c, d_out_slab, dtype, nx, ny, nzl, hdr, d_data_enc, &sg);
 }
 
 int wrb_encode_host(wrb_codec* c, const void* field, int dtype, int nx, int ny, int nz, int wtflag, double tolrel,

@@ -261,6 +261,34 @@ void wavelet_forward(const void* src, int src_is_f32, double* coef, double* tmp,
     }
 }
 
+// x- then y-lifting of a local box: cur -> scratch (x), scratch -> dst (y).  Used by the slab path, which
+// does its own z-lifting across slabs (wavelet_slab.cu).
+void wavelet_xy_passes(const void* cur, int cur_is_f32, long long csy, long long csz, double* scratch, long long ay,
+                       long long az, double* dst, long long dsy, long long dsz, int n0, int n1, int n2,
+                       unsigned long long* in_min, unsigned long long* in_max, cudaStream_t s)
+{
+    FwdPassArgs a{};
+    a.n0 = n0; a.n1 = n1; a.n2 = n2; a.m0 = (n0 + 1) / 2; a.m1 = (n1 + 1) / 2;
+    a.src = cur; a.ssy = csy; a.ssz = csz; a.dst = scratch; a.dsy = ay; a.dsz = az;
+    a.in_min = in_min; a.in_max = in_max;
+    if (cur_is_f32) launch_fwd_pass<0, float>(a, s); else launch_fwd_pass<0, double>(a, s);
+    a.in_min = a.in_max = nullptr;
+    a.src = scratch; a.ssy = ay; a.ssz = az; a.dst = dst; a.dsy = dsy; a.dsz = dsz;
+    launch_fwd_pass<1, double>(a, s);
+}
+
+// inverse y- then x-lifting of a local box: src -> scratch (y), scratch -> out (x)
+void wavelet_yx_inverse_passes(const double* src, double* scratch, long long ay, long long az, int n0, int n1, int n2,
+                               void* out, int out_is_f32, long long osy, long long osz, cudaStream_t s)
+{
+    InvPassArgs a{};
+    a.n0 = n0; a.n1 = n1; a.n2 = n2; a.q0 = (n0 + 1) / 2; a.q1 = (n1 + 1) / 2; a.q2 = (n2 + 1) / 2;
+    a.src = src; a.ssy = ay; a.ssz = az; a.dst = scratch; a.dsy = ay; a.dsz = az;
+    launch_inv_pass<1, double>(a, s);
+    a.src = scratch; a.dst = out; a.dsy = osy; a.dsz = osz;
+    if (out_is_f32) launch_inv_pass<0, float>(a, s); else launch_inv_pass<0, double>(a, s);
+}
+
 static inline int ceil_shift(int n, int k) { return (int)(((long long)n + (1ll << k) - 1) >> k); }
 
 // Inverse transform.  coef: coefficient array (destroyed), tmp: scratch, out: result (f32/f64,

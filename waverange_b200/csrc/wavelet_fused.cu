@@ -32,7 +32,9 @@ struct FusedFwdArgs {
     const void* src; long long ssy, ssz;       // level input (x stride 1)
     double* coef;    long long ay, az;          // coefficient array (array strides)
     double* lll;     long long lsy, lsz;        // compact low-low-low scratch, or null on the last level
-    int n0, n1, n2;                             // box extents (even)
+    int n0, n1, n2;                             // box extents (even); n2 is the GLOBAL z extent
+    int zoff;                                   // slab mode: global z of plane 0 of src (0 otherwise)
+    int pair_lo, nl;                            // owned global pairs [pair_lo, pair_lo + nl) (0, n2/2 otherwise)
     int zpairs;                                 // output pairs per z-segment
     unsigned long long* in_min;  unsigned long long* in_max;     // field extrema keys (or null)
     unsigned long long* out_min; unsigned long long* out_max;    // coefficient extrema keys
@@ -61,10 +63,10 @@ __global__ void __launch_bounds__(FTHREADS, 2) fwd_level_fused_kernel(FusedFwdAr
     __shared__ double tx[FTY][2 * FPX + 1];     // after x-lifting: [row][low 32 | high 32] (pitch 65)
     const TIN* __restrict__ src = (const TIN*)a.src;
     const int tid = threadIdx.x, wrp = tid >> 5, lane = tid & 31;
-    const int m0 = a.n0 >> 1, m1 = a.n1 >> 1, m2 = a.n2 >> 1;
+    const int m0 = a.n0 >> 1, m1 = a.n1 >> 1;
     const int px0 = blockIdx.x * FPX, py0 = blockIdx.y * FPY;
-    const int e0 = blockIdx.z * a.zpairs;
-    const int e1 = (e0 + a.zpairs < m2) ? e0 + a.zpairs : m2;
+    const int e0 = a.pair_lo + blockIdx.z * a.zpairs;
+    const int e1 = (e0 + a.zpairs < a.pair_lo + a.nl) ? e0 + a.zpairs : a.pair_lo + a.nl;
     const int x0 = 2 * px0 - 4, y0 = 2 * py0 - 4;           // tile origin in input coordinates
     // ---- tile slots of this thread: rows wrp, wrp+8, wrp+16; columns lane, lane+32, lane+64 ----
     int toff[9];
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) fwd_level_fused_kernel(FusedFwdAr
 
     TIN nxt[9];
     auto load_plane = [&](int z) {
-        const TIN* __restrict__ plane = src + (long long)mirror_idx(z, a.n2) * a.ssz;
+        const TIN* __restrict__ plane = src + (long long)(mirror_idx(z, a.n2) - a.zoff) * a.ssz;
 #pragma unroll
         for (int k = 0; k < 9; k++) nxt[k] = (toff[k] >= 0) ? plane[toff[k]] : (TIN)0;
     };
@@ -152,12 +154,12 @@ __global__ void __launch_bounds__(FTHREADS, 2) fwd_level_fused_kernel(FusedFwdAr
             d2p[v] = d2; d1p[v] = d1; s1p[v] = s1; s0p[v] = s0n;
             if (out && ooff[v] >= 0) {
                 const double lo = s2 * WRB_SCL, hi = d2 * WRB_PSCL;
-                a.coef[ooff[v] + (long long)(m2 + mo) * a.az] = hi;        // z-high: always a final coefficient
+                a.coef[ooff[v] + (long long)(a.nl + mo - a.pair_lo) * a.az] = hi;   // z-high: always a final coefficient
                 omn = fmin(omn, hi); omx = fmax(omx, hi);
                 if (v < 2 && loff[v & 1] >= 0) {
-                    a.lll[loff[v & 1] + (long long)mo * a.lsz] = lo;       // low-low-low: next level's input
+                    a.lll[loff[v & 1] + (long long)(mo - a.pair_lo) * a.lsz] = lo;   // low-low-low: next level's input
                 } else {
-                    a.coef[ooff[v] + (long long)mo * a.az] = lo;
+                    a.coef[ooff[v] + (long long)(mo - a.pair_lo) * a.az] = lo;
                     omn = fmin(omn, lo); omx = fmax(omx, lo);
                 }
             }
@@ -177,18 +179,21 @@ bool fused_forward_supported(int n0, int n1, int n2)
     return (n0 % 2 == 0) && (n1 % 2 == 0) && (n2 % 2 == 0) && n0 >= 8 && n1 >= 8 && n2 >= 8;
 }
 
-// One level: src box (n0,n1,n2) -> coef (detail octants, final) + lll (or coef when lll == null)
+// One level: src box (n0,n1,n2) -> coef (detail octants, final) + lll (or coef when lll == null).
+// Slab mode (zoff/pair_lo/nl): n2 is the global z extent, src holds the owned planes plus the halo
+// (local plane = global z - zoff) and outputs use rank-local plane indices.
 void fused_forward_level(const void* src, int src_is_f32, long long ssy, long long ssz, double* coef, long long ay,
                          long long az, double* lll, int n0, int n1, int n2, unsigned long long* in_min,
                          unsigned long long* in_max, unsigned long long* out_min, unsigned long long* out_max,
-                         cudaStream_t s)
+                         cudaStream_t s, int zoff, int pair_lo, int nl)
 {
     FusedFwdArgs a{};
     a.src = src; a.ssy = ssy; a.ssz = ssz; a.coef = coef; a.ay = ay; a.az = az;
     a.lll = lll; a.lsy = n0 / 2; a.lsz = (long long)(n0 / 2) * (n1 / 2);
     a.n0 = n0; a.n1 = n1; a.n2 = n2;
+    a.zoff = zoff; a.pair_lo = pair_lo; a.nl = (nl < 0) ? n2 / 2 : nl;
     a.in_min = in_min; a.in_max = in_max; a.out_min = out_min; a.out_max = out_max;
-    const int m0 = n0 / 2, m1 = n1 / 2, m2 = n2 / 2;
+    const int m0 = n0 / 2, m1 = n1 / 2, m2 = a.nl;
     const int gx = (m0 + FPX - 1) / FPX, gy = (m1 + FPY - 1) / FPY;
     // z-segments: enough CTAs to fill the machine (148 SMs x 2 resident), but segments of >= 16 pairs
     int zp = m2;

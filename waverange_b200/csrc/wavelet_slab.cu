@@ -1,0 +1,244 @@
+// wavelet_slab.cu -- z-slab partitioned transform (one large field across the GPUs of a box).
+//
+// Rank g owns the physical planes [z0, z0 + nzl) of the field.  x- and y-lifting are slab-local (the
+// general pass kernels of wavelet.cu on the local box); only the z-lifting reaches across slabs:
+//   forward : outputs for the owned pairs need 4 planes from below and 3 from above of the
+//             (x,y)-transformed level input            (waveletcdf97_3d.c:112-125)
+//   inverse : the owned samples need 2 low-band + 2 high-band planes from either side
+// Those planes come from the neighbours through the halo callback (NCCL send/recv in production,
+// gloo in the CPU tests).  Every rank keeps its coefficients in a *rank-local* wavelet-space array
+// laid out exactly like the transform of an independent (nx, ny, nzl) field, so quantiser and coder
+// run unchanged on it; the coefficient VALUES are those of the global transform, bit for bit,
+// because the kernels below evaluate the same register windows (fwd_pairs / inv_pairs) with global
+// line indices and only remap where a plane is stored.
+#include "wr_common.cuh"
+#include "wr_kernels.h"
+#include "wavelet_pairs.cuh"
+
+namespace wrb {
+
+constexpr int kSR = 2;          // pairs per thread (local pair counts are even)
+constexpr int kHaloLo = 4;      // forward: planes needed from below
+constexpr int kHaloHi = 3;      // forward: planes needed from above
+constexpr int kHaloInv = 2;     // inverse: planes per band and side
+
+struct FwdSlabArgs {
+    const double* src; long long ssy, ssz;   // (x,y)-transformed level input incl. halo; local plane p = global z - zoff
+    double* dst; long long dsy, dsz;         // rank-local coefficient array
+    double* lll; long long lsy, lsz;         // rank-local low-low-low scratch (or null on the last level)
+    int n0, n1, N;                           // box extents in x, y; GLOBAL extent in z
+    int zoff;                                // global z of local plane 0 of src
+    int pair_lo, pair_hi;                    // owned global pairs [pair_lo, pair_hi)
+    int m0, m1;                              // low extents in x, y (lll routing)
+    unsigned long long* out_min; unsigned long long* out_max;
+};
+
+__global__ void __launch_bounds__(128) fwd_zslab_kernel(FwdSlabArgs a)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int i0 = a.pair_lo + blockIdx.z * kSR;
+    const int M = (a.N + 1) >> 1, nl = a.pair_hi - a.pair_lo;
+    unsigned long long omin = kKeyMinInit, omax = kKeyMaxInit;
+    if (x < a.n0 && i0 < a.pair_hi) {
+        const long long sbase = x + (long long)y * a.ssy;
+        auto ld = [&](int j) -> double { return a.src[sbase + (long long)(j - a.zoff) * a.ssz]; };
+        double so[kSR], dd[kSR];
+        fwd_pairs<kSR>(ld, a.N, i0, so, dd);
+#pragma unroll
+        for (int t = 0; t < kSR; t++) {
+            const int j = i0 + t;
+            if (j >= a.pair_hi || j >= M) continue;
+            const int pl = j - a.pair_lo;                       // local plane of the low output
+            if (a.lll != nullptr && x < a.m0 && y < a.m1) {
+                a.lll[x + (long long)y * a.lsy + (long long)pl * a.lsz] = so[t];
+            } else {
+                a.dst[x + (long long)y * a.dsy + (long long)pl * a.dsz] = so[t];
+                const unsigned long long k = dkey(so[t]); omin = k < omin ? k : omin; omax = k > omax ? k : omax;
+            }
+            if (2 * j + 1 < a.N) {
+                a.dst[x + (long long)y * a.dsy + (long long)(nl + pl) * a.dsz] = dd[t];
+                const unsigned long long k = dkey(dd[t]); omin = k < omin ? k : omin; omax = k > omax ? k : omax;
+            }
+        }
+    }
+    block_minmax_commit(omin, omax, a.out_min, a.out_max);
+}
+
+struct InvSlabArgs {
+    const double* lowx; const double* highx; long long bsy, bsz;   // band buffers, own planes start at kHaloInv
+    double* dst; long long dsy, dsz;                               // local output (interleaved along z)
+    int n0, n1, M;                                                 // box extents x, y; GLOBAL extent in z
+    int pair_lo, pair_hi;
+};
+
+__global__ void __launch_bounds__(128) inv_zslab_kernel(InvSlabArgs a)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int i0 = a.pair_lo + blockIdx.z * kSR;
+    if (x >= a.n0 || i0 >= a.pair_hi) return;
+    const int Q = (a.M + 1) >> 1;
+    const long long b = x + (long long)y * a.bsy;
+    auto ld = [&](int j) -> double {
+        return (j < Q) ? a.lowx[b + (long long)(j - a.pair_lo + kHaloInv) * a.bsz]
+                       : a.highx[b + (long long)(j - Q - a.pair_lo + kHaloInv) * a.bsz];
+    };
+    double ev[kSR], od[kSR];
+    inv_pairs<kSR>(ld, a.M, i0, ev, od);
+#pragma unroll
+    for (int t = 0; t < kSR; t++) {
+        const int j = i0 + t;
+        if (j >= a.pair_hi || j >= Q) continue;
+        const long long o = x + (long long)y * a.dsy + (long long)(2 * (j - a.pair_lo)) * a.dsz;
+        a.dst[o] = ev[t];
+        if (2 * j + 1 < a.M) a.dst[o + a.dsz] = od[t];
+    }
+}
+
+// band buffers of one inverse level: lowx[kHaloInv + p] = local box plane p, highx[kHaloInv + p] = plane nl + p;
+// the low-low-low octant of the box is the previous (coarser) level's output held in `lll`
+__global__ void __launch_bounds__(128) build_bands_kernel(const double* __restrict__ coef, long long ay, long long az,
+                                                          const double* __restrict__ lll, long long lsy, long long lsz,
+                                                          int q0, int q1, int n0, int n1, int nl,
+                                                          double* __restrict__ lowx, double* __restrict__ highx,
+                                                          long long bsy, long long bsz)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, p = blockIdx.z;                   // p in [0, 2*nl)
+    if (x >= n0) return;
+    double v;
+    if (lll != nullptr && x < q0 && y < q1 && p < nl) v = lll[x + (long long)y * lsy + (long long)p * lsz];
+    else v = coef[x + (long long)y * ay + (long long)p * az];
+    double* band = (p < nl) ? lowx : highx;
+    const int pp = (p < nl) ? p : p - nl;
+    band[x + (long long)y * bsy + (long long)(pp + kHaloInv) * bsz] = v;
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) copy_convert_kernel(const double* __restrict__ src, T* __restrict__ dst, unsigned long long n)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        dst[i] = (T)src[i];
+}
+
+static int slab_levels_ok(int nx, int ny, int nz, int nzl, int z0, int levels)
+{
+    if (levels == 0) return 1;
+    if (nzl % (1 << (levels + 1)) != 0 || z0 % (1 << (levels + 1)) != 0) return 0;   // even local pair counts at every level
+    if (nz % (1 << levels) != 0) return 0;
+    (void)nx; (void)ny;
+    return 1;
+}
+
+int wavelet_slab_supported(int nx, int ny, int nz, int z0, int nzl, int levels)
+{
+    return slab_levels_ok(nx, ny, nz, nzl, z0, levels);
+}
+
+// Forward, slab mode.  src: this rank's nzl planes (f32/f64, array strides nx, nx*ny).  tmp must hold
+// (nzl + 7) * nx * ny doubles.  halo(user, buf, elem_bytes, plane_elems, nplanes_own, lo, hi) fills the lo planes
+// before and hi planes after the own planes (which start at plane `lo` of buf) from the z-neighbours.
+int wavelet_forward_slab(const void* src, int src_is_f32, double* coef, double* tmp, double* lllA, double* lllB, int nx,
+                         int ny, int nz, int z0, int nzl, int levels, DevState* st, const SlabHooks& hk, cudaStream_t s)
+{
+    const long long ay = nx, az = (long long)nx * ny;
+    int n0 = nx, n1 = ny, n2l = nzl, n2g = nz, zg = z0;
+    const void* cur = src;            // own planes of the level input
+    void* cur_base = nullptr;         // same data inside a buffer with halo room (own planes at +kHaloLo), or null
+    long long csy = ay, csz = az;
+    bool cur_f32 = src_is_f32 != 0;
+    for (int k = 1; k <= levels; k++) {
+        const int m0 = (n0 + 1) / 2, m1 = (n1 + 1) / 2;
+        const bool last = (k == levels);
+        double* lll_base = last ? nullptr : ((k & 1) ? lllA : lllB);            // next level's input, with halo room
+        const long long lsz = (long long)m0 * m1;
+        double* lll = last ? nullptr : lll_base + kHaloLo * lsz;
+        const int esz = cur_f32 ? 4 : 8;
+        if (fused_forward_supported(n0, n1, n2g) && n2l >= 2) {
+            // one pass: raw level input (+ halo planes from the neighbours) -> octants
+            if (cur_base == nullptr) {                                         // level 1: the caller's slab has no halo room
+                cur_base = tmp;
+                cudaMemcpyAsync((char*)tmp + (size_t)kHaloLo * csz * esz, cur, (size_t)n2l * csz * esz, cudaMemcpyDeviceToDevice, s);
+            }
+            if (hk.nranks > 1) {
+                int rc = hk.halo(hk.user, cur_base, esz, csz, n2l, kHaloLo, kHaloHi);
+                if (rc) return rc;
+            }
+            fused_forward_level(cur_base, cur_f32 ? 1 : 0, csy, csz, coef, ay, az, lll, n0, n1, n2g,
+                                (k == 1) ? &st->fmin_key : nullptr, (k == 1) ? &st->fmax_key : nullptr, &st->rmin_key[0],
+                                &st->rmax_key[0], s, zg - kHaloLo, zg / 2, n2l / 2);
+        } else {
+            // x: cur -> coef (local box used as scratch), y: coef -> tmp (compact, own planes after the lower halo)
+            const long long tsy = n0, tsz = (long long)n0 * n1;
+            wavelet_xy_passes(cur, cur_f32 ? 1 : 0, csy, csz, coef, ay, az, tmp + kHaloLo * tsz, tsy, tsz, n0, n1, n2l,
+                              (k == 1) ? &st->fmin_key : nullptr, (k == 1) ? &st->fmax_key : nullptr, s);
+            if (hk.nranks > 1) {
+                int rc = hk.halo(hk.user, tmp, 8, tsz, n2l, kHaloLo, kHaloHi);
+                if (rc) return rc;
+            }
+            FwdSlabArgs a{};
+            a.src = tmp; a.ssy = tsy; a.ssz = tsz; a.dst = coef; a.dsy = ay; a.dsz = az;
+            a.lll = lll; a.lsy = m0; a.lsz = lsz;
+            a.n0 = n0; a.n1 = n1; a.N = n2g; a.zoff = zg - kHaloLo;
+            a.pair_lo = zg / 2; a.pair_hi = (zg + n2l) / 2; a.m0 = m0; a.m1 = m1;
+            a.out_min = &st->rmin_key[0]; a.out_max = &st->rmax_key[0];
+            dim3 block(128, 1, 1), grid((n0 + 127) / 128, n1, (n2l / 2 + kSR - 1) / kSR);
+            fwd_zslab_kernel<<<grid, block, 0, s>>>(a);
+            note_launch(1);
+        }
+        cur = lll; cur_base = lll_base; csy = m0; csz = lsz; cur_f32 = false;
+        n0 = m0; n1 = m1; n2l /= 2; n2g /= 2; zg /= 2;
+    }
+    return 0;
+}
+
+// Inverse, slab mode.  ext must hold 2 * (nzl/2 + 4) * nx * ny doubles.
+int wavelet_inverse_slab(double* coef, double* tmp, double* lllA, double* lllB, double* ext, void* out, int out_is_f32,
+                         int nx, int ny, int nz, int z0, int nzl, int levels, const SlabHooks& hk, cudaStream_t s)
+{
+    const long long ay = nx, az = (long long)nx * ny;
+    const double* lll = nullptr; long long lsy = 0, lsz = 0;
+    for (int k = levels - 1; k >= 0; k--) {
+        const int n0 = (nx + (1 << k) - 1) >> k, n1 = (ny + (1 << k) - 1) >> k;
+        const int n2l = nzl >> k, n2g = nz >> k, zg = z0 >> k;
+        const int q0 = (n0 + 1) / 2, q1 = (n1 + 1) / 2, nl = n2l / 2;
+        const long long bsy = n0, bsz = (long long)n0 * n1;
+        double* lowx = ext;
+        double* highx = ext + (long long)(nl + 2 * kHaloInv) * bsz;
+        {
+            dim3 block(128, 1, 1), grid((n0 + 127) / 128, n1, 2 * nl);
+            build_bands_kernel<<<grid, block, 0, s>>>(coef, ay, az, lll, lsy, lsz, q0, q1, n0, n1, nl, lowx, highx, bsy, bsz);
+            note_launch(1);
+        }
+        if (hk.nranks > 1) {
+            int rc = hk.halo(hk.user, lowx, 8, bsz, nl, kHaloInv, kHaloInv);
+            if (rc) return rc;
+            rc = hk.halo(hk.user, highx, 8, bsz, nl, kHaloInv, kHaloInv);
+            if (rc) return rc;
+        }
+        InvSlabArgs a{};
+        a.lowx = lowx; a.highx = highx; a.bsy = bsy; a.bsz = bsz;
+        a.dst = tmp; a.dsy = ay; a.dsz = az; a.n0 = n0; a.n1 = n1; a.M = n2g;
+        a.pair_lo = zg / 2; a.pair_hi = (zg + n2l) / 2;
+        dim3 block(128, 1, 1), grid((n0 + 127) / 128, n1, (nl + kSR - 1) / kSR);
+        inv_zslab_kernel<<<grid, block, 0, s>>>(a);
+        note_launch(1);
+        // y: tmp -> coef (local box), x: coef -> next lll (compact) or the output slab
+        double* nxt = (k & 1) ? lllA : lllB;
+        wavelet_yx_inverse_passes(tmp, coef, ay, az, n0, n1, n2l, (k == 0) ? out : (void*)nxt, (k == 0) ? out_is_f32 : 0,
+                                  (k == 0) ? ay : (long long)n0, (k == 0) ? az : (long long)n0 * n1, s);
+        lll = nxt; lsy = n0; lsz = (long long)n0 * n1;
+    }
+    if (levels == 0) {
+        const unsigned long long n = (unsigned long long)nx * ny * nzl;
+        int blocks = (int)((n + 2047) / 2048); if (blocks > 148 * 16) blocks = 148 * 16; if (blocks < 1) blocks = 1;
+        if (out_is_f32) copy_convert_kernel<float><<<blocks, 256, 0, s>>>(coef, (float*)out, n);
+        else copy_convert_kernel<double><<<blocks, 256, 0, s>>>(coef, (double*)out, n);
+        note_launch(1);
+    }
+    return 0;
+}
+
+}  // namespace wrb

@@ -12,12 +12,35 @@ void wavelet_forward(const void* src, int src_is_f32, double* coef, double* tmp,
 void wavelet_inverse(double* coef, double* tmp, double* lllA, double* lllB, void* out, int out_is_f32,
                      int nx, int ny, int nz, int levels, cudaStream_t s);
 
+void wavelet_xy_passes(const void* cur, int cur_is_f32, long long csy, long long csz, double* scratch, long long ay,
+                       long long az, double* dst, long long dsy, long long dsz, int n0, int n1, int n2,
+                       unsigned long long* in_min, unsigned long long* in_max, cudaStream_t s);
+void wavelet_yx_inverse_passes(const double* src, double* scratch, long long ay, long long az, int n0, int n1, int n2,
+                               void* out, int out_is_f32, long long osy, long long osz, cudaStream_t s);
+
+// ---- wavelet_slab.cu ----------------------------------------------------------------------
+// Collectives of the z-slab partition are injected by the host (NCCL via torch.distributed in
+// production, gloo or an in-process emulation in tests):
+//   halo  : fill `lo` planes before and `hi` planes after the `nown` own planes of buf (own planes start at
+//           plane `lo`) with the adjacent own planes of the z-neighbours; nothing at the domain ends
+//   reduce: in-place global MIN over `count` signed 64-bit integers (the codec packs min keys and
+//           complemented max keys into one buffer so a single all_reduce(MIN) serves both)
+// Both are enqueued on / ordered with the codec's stream and return 0 on success.
+typedef int (*HaloFn)(void* user, void* d_buf, int elem_bytes, long long plane_elems, int nown, int lo, int hi);
+typedef int (*ReduceFn)(void* user, long long* d_buf, int count);
+struct SlabHooks { int rank = 0, nranks = 1; HaloFn halo = nullptr; ReduceFn reduce = nullptr; void* user = nullptr; };
+int wavelet_slab_supported(int nx, int ny, int nz, int z0, int nzl, int levels);
+int wavelet_forward_slab(const void* src, int src_is_f32, double* coef, double* tmp, double* lllA, double* lllB, int nx,
+                         int ny, int nz, int z0, int nzl, int levels, DevState* st, const SlabHooks& hk, cudaStream_t s);
+int wavelet_inverse_slab(double* coef, double* tmp, double* lllA, double* lllB, double* ext, void* out, int out_is_f32,
+                         int nx, int ny, int nz, int z0, int nzl, int levels, const SlabHooks& hk, cudaStream_t s);
+
 // ---- wavelet_fused.cu ---------------------------------------------------------------------
 bool fused_forward_supported(int n0, int n1, int n2);
 void fused_forward_level(const void* src, int src_is_f32, long long ssy, long long ssz, double* coef, long long ay,
                          long long az, double* lll, int n0, int n1, int n2, unsigned long long* in_min,
                          unsigned long long* in_max, unsigned long long* out_min, unsigned long long* out_max,
-                         cudaStream_t s);
+                         cudaStream_t s, int zoff = 0, int pair_lo = 0, int nl = -1);
 
 // ---- quant.cu -----------------------------------------------------------------------------
 // Geometry of the chunked symbol container of one layer.
