@@ -35,6 +35,9 @@ N_FIELD = 512
 TOL = 1e-4
 SAMPLE = 256            # edge of the CPU-baseline sample cube
 METRIC = "raw-field compress+decompress throughput (device-timed)"
+# DRAM bytes of the forward-wavelet + quantise kernels of one compress of the default workload, from ncu:
+# fused level 1: 0.555 + 1.028 GB, levels 2-4: 0.156 + 0.099 + ~0.04 GB, quantise 3 x (1.07 + 0.13) GB
+NCU_TRAFFIC_512 = int((0.555 + 1.028 + 0.156 + 0.099 + 0.04 + 3 * (1.07 + 0.13)) * 1e9)
 UNIT = "GB/s"
 
 
@@ -319,7 +322,11 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu:
         sample = field[:min(n, SAMPLE), :min(n, SAMPLE), :min(n, SAMPLE)].contiguous().cpu().numpy().astype(np.float64)
-        kind, te, td, _ = cpu_time_sample(sample, TOL)
+        kind, te, td, href = cpu_time_sample(sample, TOL)
+        # same sample through the GPU path: coded size against the reference's single-stream layers
+        hs, _ = codec.encode_host(sample.astype(np.float32), TOL)
+        ratio_check = {"sample": "%d^3 sub-cube" % min(n, SAMPLE), "reference_bytes": int(href.ntot_enc), "ours_bytes": int(hs.ntot_enc),
+                       "size_overhead": hs.ntot_enc / max(1, href.ntot_enc) - 1.0, "nlay_equal": int(hs.nlay) == int(href.nlay)}
         cpu = {"value": 2 * sample.size * 4 / (te + td) / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
                "sample": "%d^3 sub-cube of the same field, encoding_wrap %.2f s + decoding_wrap %.2f s, 1 thread "
                          "(reference is single-threaded); host has %d cores" % (SAMPLE, te, td, os.cpu_count())}
@@ -342,7 +349,10 @@ def run_ours(args, rank, world, local_rank):
                       "decode": dict(zip(["parse", "range_decode", "dequantise", "inverse_transform"], sd)),
                       "encode_total": enc_mean, "decode_total": dec_mean},
         "roofline": {"bound": "hbm", "scope": "forward wavelet + quantise kernels of one compress (stage events)",
-                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                     # dram__bytes_read+write of those kernels from the ncu --set full captures of this workload
+                     # (profiles/r1d_fused_forward_ncu_raw_512.csv + r1b_wavelet_quantise_ncu_raw_512.csv), per compress
+                     "traffic": (NCU_TRAFFIC_512 if (n == N_FIELD and nlay == 3 and not slab_mode) else None),
                      "algorithmic_bytes": a_c, "peak_source": peak_src},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": world * (nbytes + int(h.ntot_enc)),
                 "d2h_bytes_per_step": world * (nbytes + int(h.ntot_enc)), "ms_per_step": e2e_step,
@@ -354,6 +364,7 @@ def run_ours(args, rank, world, local_rank):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+        line["ratio_check"] = ratio_check
     print(json.dumps(line), flush=True)
 
 
@@ -374,6 +385,9 @@ def main():
         run_reference(args, rank, world)
         return
     if world > 1:
+        # stdout must carry exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and "NCCL_DEBUG_FILE" not in os.environ:
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
