@@ -490,15 +490,23 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
     range_decode_chunks(d_data_enc, (const unsigned long long*)c->offs.p, (const unsigned long long*)c->layoff.p, g, nlay,
                         (uint8_t*)c->sym.p, lstride, d_err, s);
     if (c->timing) cudaEventRecord(c->ev[2], s);
-    dequantise((const uint8_t*)c->sym.p, lstride, g, nlay, hdr->deps_vec, hdr->minval_vec, (double*)c->coef.p, s);
+    // The inverse z pass rebuilds the coefficients from the symbols itself; a separate dequantise pass is only
+    // needed without a transform, for extent-1 z, and in slab mode (its band buffers are built from coef).
+    const bool fuse_deq = sg == nullptr && hdr->wlev > 0 && nz >= (1 << hdr->wlev) && getenv("WRB_NO_FUSED_DEQUANT") == nullptr;
+    if (!fuse_deq) dequantise((const uint8_t*)c->sym.p, lstride, g, nlay, hdr->deps_vec, hdr->minval_vec, (double*)c->coef.p, s);
     if (c->timing) cudaEventRecord(c->ev[3], s);
     if (sg != nullptr && hdr->wlev > 0) {
         if (wavelet_inverse_slab((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, (double*)c->ext.p,
                                  d_out, dtype == WRB_F32, nx, ny, sg->nz_global, sg->z0, nz, (int)hdr->wlev, c->hooks, s))
             return fail(c, WRB_E_CUDA, "halo exchange callback failed");
     } else {
-        wavelet_inverse((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, d_out, dtype == WRB_F32,
-                        nx, ny, nz, (int)hdr->wlev, s);
+        if (fuse_deq)
+            wavelet_inverse((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, d_out, dtype == WRB_F32,
+                            nx, ny, nz, (int)hdr->wlev, s, (const uint8_t*)c->sym.p, lstride, g.chunk_len, g.pitch, nlay,
+                            hdr->deps_vec, hdr->minval_vec);
+        else
+            wavelet_inverse((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, d_out, dtype == WRB_F32,
+                            nx, ny, nz, (int)hdr->wlev, s);
     }
     if (c->timing) cudaEventRecord(c->ev[4], s);
     int* h_err = (int*)(c->h_u64 + 128);

@@ -164,6 +164,102 @@ __global__ void __launch_bounds__(256) narrow_copy_kernel(const double* __restri
 }
 
 // ------------------------------------------------------------------------------------------
+// Streaming inverse z-lifting.  One thread per (x, y) column of the level box; the pairs (low[m], high[m])
+// of its z-line are read once, in order, and the four inverse lifting stages roll through five doubles
+// of state (waveletcdf97_3d.c:311-337, same grouping as inv_pairs); every plane access is coalesced in x.
+// With FUSE the detail coefficients are not read from the coefficient array at all: they are rebuilt from
+// the decoded symbol planes, fld = (0 + (q0*deps0 + min0)) + (q1*deps1 + min1) ... (wrappers.cpp:480,513-514),
+// which removes the dequantise pass and 8 B/point of reads.  The low-low-low octant always comes from the
+// previous (coarser) level's output.
+// ------------------------------------------------------------------------------------------
+struct DequantSrc {
+    const uint8_t* sym;               // chunk-major padded symbol planes (null: read coefficients)
+    unsigned long long layer_stride, chunk_len, pitch;
+    int nlay;
+    double deps[kNLayMax], minval[kNLayMax];
+};
+
+struct InvZArgs {
+    const double* coef; long long ay, az;     // coefficient array (array strides)
+    const double* lll; long long lsy, lsz;    // previous level's output (compact) or null
+    double* dst; long long dsy, dsz;
+    int n0, n1, M;                            // level box
+    int q0, q1, q2;                           // low extents
+    int zpairs;                               // output pairs per z-segment
+};
+
+template <bool FUSE>
+__global__ void __launch_bounds__(128) inv_z_stream_kernel(InvZArgs a, DequantSrc dq)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= a.n0) return;
+    const int Q = a.q2, NH = a.M - Q;
+    const int e0 = blockIdx.z * a.zpairs, e1 = (e0 + a.zpairs < Q) ? e0 + a.zpairs : Q;
+    const int mstart = (e0 - 3 > 0) ? e0 - 3 : 0;            // the stencil reaches three pairs back
+    const bool in_lll = a.lll != nullptr && x < a.q0 && y < a.q1;
+    const long long col = x + (long long)y * a.ay;
+    // running (chunk, offset) of the low and the high element in the symbol container
+    unsigned long long cl = 0, ol = 0, ch = 0, oh = 0, dc = 0, dof = 0;
+    if (FUSE) {
+        const unsigned long long jl = (unsigned long long)col + (unsigned long long)mstart * a.az;
+        const unsigned long long jh = jl + (unsigned long long)Q * a.az;
+        cl = jl / dq.chunk_len; ol = jl % dq.chunk_len;
+        ch = jh / dq.chunk_len; oh = jh % dq.chunk_len;
+        dc = (unsigned long long)a.az / dq.chunk_len; dof = (unsigned long long)a.az % dq.chunk_len;
+    }
+    auto deq = [&](unsigned long long c, unsigned long long o) -> double {
+        const uint8_t* p = dq.sym + c * dq.pitch + o;
+        double f = 0;
+        for (int l = 0; l < dq.nlay; l++) f = f + ((double)p[(unsigned long long)l * dq.layer_stride] * dq.deps[l] + dq.minval[l]);
+        return f;
+    };
+    double hp = 0, s1p = 0, d1p = 0, d1pp = 0, s2p = 0;      // h[m-1], s1[m-1], d1[m-1], d1[m-2], s2[m-2]
+    double* __restrict__ out = a.dst + x + (long long)y * a.dsy;
+    for (int m = mstart; m < e1 + 2 && m <= Q; m++) {
+        if (m < Q) {
+            double lv, hv = 0.0;
+            if (in_lll) lv = a.lll[x + (long long)y * a.lsy + (long long)m * a.lsz];
+            else lv = FUSE ? deq(cl, ol) : a.coef[col + (long long)m * a.az];
+            if (m < NH) hv = FUSE ? deq(ch, oh) : a.coef[col + (long long)(Q + m) * a.az];      // phantom detail = 0 (:314)
+            if (FUSE) {
+                cl += dc; ol += dof; if (ol >= dq.chunk_len) { ol -= dq.chunk_len; cl++; }
+                ch += dc; oh += dof; if (oh >= dq.chunk_len) { oh -= dq.chunk_len; ch++; }
+            }
+            const double l = lv * WRB_PSCL, h = hv * WRB_SCL;
+            const double s1 = (m == 0) ? l - (WRB_LD * 2) * h : l - WRB_LD * (h + hp);                     // s1[m]
+            if (m >= 1) {
+                const double d1 = hp - WRB_LC * (s1 + s1p);                                                 // d1[m-1]
+                const double s2 = (m == 1) ? s1p - (WRB_LB * 2) * d1 : s1p - WRB_LB * (d1 + d1p);           // s2[m-1]
+                if (m >= 2) {
+                    const double d2 = d1p - WRB_LA * (s2 + s2p);                                            // d2[m-2]
+                    if (m - 2 >= e0 && m - 2 < e1) {
+                        out[(long long)(2 * (m - 2)) * a.dsz] = s2p;
+                        out[(long long)(2 * (m - 2) + 1) * a.dsz] = d2;
+                    }
+                }
+                d1pp = d1p; d1p = d1; s2p = s2;
+                (void)d1pp;
+            }
+            hp = h; s1p = s1;
+        } else {                                             // m == Q: end of the line, flush pairs Q-2 and Q-1
+            const double d1 = hp - (WRB_LC * 2) * s1p;                                                      // d1[Q-1]
+            const double s2 = (Q == 1) ? s1p - (WRB_LB * 2) * d1 : s1p - WRB_LB * (d1 + d1p);               // s2[Q-1]
+            if (Q >= 2) {
+                const double d2 = d1p - WRB_LA * (s2 + s2p);                                                // d2[Q-2]
+                if (Q - 2 >= e0 && Q - 2 < e1) {
+                    out[(long long)(2 * (Q - 2)) * a.dsz] = s2p;
+                    out[(long long)(2 * (Q - 2) + 1) * a.dsz] = d2;
+                }
+            }
+            if (Q - 1 >= e0 && Q - 1 < e1) {
+                out[(long long)(2 * (Q - 1)) * a.dsz] = s2;
+                if (2 * (Q - 1) + 1 < a.M) out[(long long)(2 * (Q - 1) + 1) * a.dsz] = d1 - (WRB_LA * 2) * s2;   // d2[Q-1]
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------
 constexpr int kR = 4;
@@ -294,8 +390,13 @@ static inline int ceil_shift(int n, int k) { return (int)(((long long)n + (1ll <
 // Inverse transform.  coef: coefficient array (destroyed), tmp: scratch, out: result (f32/f64,
 // array strides).  reference: waveletcdf97_3d.c:281-466 (levels coarsest first, z then y then x)
 void wavelet_inverse(double* coef, double* tmp, double* lllA, double* lllB, void* out, int out_is_f32,
-                     int nx, int ny, int nz, int levels, cudaStream_t s)
+                     int nx, int ny, int nz, int levels, cudaStream_t s, const uint8_t* sym,
+                     unsigned long long layer_stride, unsigned long long chunk_len, unsigned long long pitch, int nlay,
+                     const double* deps, const double* minval)
 {
+    DequantSrc dq{};
+    dq.sym = sym; dq.layer_stride = layer_stride; dq.chunk_len = chunk_len; dq.pitch = pitch; dq.nlay = nlay;
+    for (int l = 0; l < nlay && l < kNLayMax && sym != nullptr; l++) { dq.deps[l] = deps[l]; dq.minval[l] = minval[l]; }
     const long long ay = nx, az = (long long)nx * ny;
     if (levels == 0) {
         unsigned long long n = (unsigned long long)nx * ny * nz;
@@ -313,10 +414,25 @@ void wavelet_inverse(double* coef, double* tmp, double* lllA, double* lllB, void
         const int q0 = half_up(n0), q1 = half_up(n1), q2 = half_up(n2);
         InvPassArgs a{};
         a.n0 = n0; a.n1 = n1; a.n2 = n2; a.q0 = q0; a.q1 = q1; a.q2 = q2;
-        // z: coef (+lll) -> tmp
+        // z: coef or symbols (+lll) -> tmp
         a.src = coef; a.ssy = ay; a.ssz = az; a.lll = lll; a.lsy = lsy; a.lsz = lsz;
         a.dst = tmp; a.dsy = ay; a.dsz = az;
-        launch_inv_pass<2, double>(a, s);
+        if (n2 > 1) {
+            InvZArgs za{};
+            za.coef = coef; za.ay = ay; za.az = az; za.lll = lll; za.lsy = lsy; za.lsz = lsz;
+            za.dst = tmp; za.dsy = ay; za.dsz = az; za.n0 = n0; za.n1 = n1; za.M = n2; za.q0 = q0; za.q1 = q1; za.q2 = q2;
+            const int bx = (n0 >= 128) ? 128 : ((n0 + 31) / 32) * 32;
+            const int gx = (n0 + bx - 1) / bx;
+            int zp = q2;                              // z-segments only when the columns alone cannot fill the GPU
+            while (zp > 8 && (long long)gx * n1 * ((q2 + zp - 1) / zp) * bx < 148ll * 2048) zp = (zp + 1) / 2;
+            za.zpairs = zp;
+            dim3 grid(gx, n1, (q2 + zp - 1) / zp), block(bx, 1, 1);
+            if (sym != nullptr) inv_z_stream_kernel<true><<<grid, block, 0, s>>>(za, dq);
+            else inv_z_stream_kernel<false><<<grid, block, 0, s>>>(za, dq);
+            note_launch(1);
+        } else {
+            launch_inv_pass<2, double>(a, s);       // extent-1 direction: plain copy (needs coefficients)
+        }
         // y: tmp -> coef
         a.lll = nullptr;
         a.src = tmp; a.dst = coef;

@@ -9,8 +9,12 @@ namespace wrb {
 // ---- wavelet.cu ---------------------------------------------------------------------------
 void wavelet_forward(const void* src, int src_is_f32, double* coef, double* tmp, double* lllA, double* lllB,
                      int nx, int ny, int nz, int levels, DevState* st, cudaStream_t s);
+// sym != null: the detail coefficients are rebuilt from the symbol planes inside the z pass (coef is then only
+// scratch); requires nz > 1 at every level, otherwise dequantise into coef first and pass sym = null
 void wavelet_inverse(double* coef, double* tmp, double* lllA, double* lllB, void* out, int out_is_f32,
-                     int nx, int ny, int nz, int levels, cudaStream_t s);
+                     int nx, int ny, int nz, int levels, cudaStream_t s, const uint8_t* sym = nullptr,
+                     unsigned long long layer_stride = 0, unsigned long long chunk_len = 0, unsigned long long pitch = 0,
+                     int nlay = 0, const double* deps = nullptr, const double* minval = nullptr);
 
 void wavelet_xy_passes(const void* cur, int cur_is_f32, long long csy, long long csz, double* scratch, long long ay,
                        long long az, double* dst, long long dsy, long long dsz, int n0, int n1, int n2,
