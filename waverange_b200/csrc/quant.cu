@@ -85,9 +85,32 @@ __global__ void layer_params_kernel(DevState* st, int l)
 void layer_params(DevState* st, int layer, cudaStream_t s) { layer_params_kernel<<<1, 1, 0, s>>>(st, layer); note_launch(1); }
 
 // One CTA per coder block (<= 60000 symbols).  reference wrappers.cpp:384-398 + rangecod.c:389-397
-// Each thread keeps four independent 8-byte loads in flight (HBM latency needs ~35 KB in flight per
-// SM); extrema are tracked as doubles (fmin/fmax are order-independent, as in the reference) and
-// turned into ordered keys once per thread.
+//
+// The kernel has to move 9 bytes per coefficient and nothing else should cost: the first version issued
+// ~80 instructions per coefficient (per-element bounds branches, __match_any_sync + shared atomics for the
+// histogram, f64<->int conversions) and was issue-bound at 2.5 TB/s.  This one issues ~25-35:
+//   * floor by magic number: t = fq + 2^52 rounded DOWN holds floor(fq) in its low mantissa bits and
+//     t - 2^52 is that integer as a double -- what (unsigned char)fq followed by the int -> double
+//     conversion give for 0 <= fq < 256 (fq lies in [0.5, 255.5] by construction of aopt/bopt; only the
+//     low byte is kept, like the reference's cast) -- no conversion instructions;
+//   * histogram without atomics: every thread owns a private 256 x 1-byte counter set in shared memory
+//     (a thread sees at most ceil(60000/256) = 235 symbols, so a byte cannot overflow); thread t's counter
+//     for bin q is byte t>>6 of word q*64 + (t&63), so the 32 lanes of a warp always hit 32 different banks;
+//   * full tiles of 2048 coefficients run without predicates, eight 8-byte loads in flight per thread
+//     (HBM latency needs ~35 KB in flight per SM at three resident CTAs);
+//   * extrema are tracked as doubles (fmin/fmax are order-independent, as in the reference) and turned
+//     into ordered keys once per thread.
+constexpr int kQThreads = 256;
+constexpr int kQLoads = 8;                               // coefficients per thread and tile
+constexpr int kQTile = kQThreads * kQLoads;              // 2048
+constexpr int kQHistBytes = 256 * kQThreads;             // private byte counters: 64 KiB
+
+__device__ __forceinline__ double floor_magic(double fq)
+{
+    return __dadd_rd(fq, 4503599627370496.0);            // 2^52: low mantissa bits = floor(fq)
+}
+
+// residual after layer `nl` of coefficient r, symbol of layer nl in the low byte of q
 template <int LAYER>
 __device__ __forceinline__ double quantise_one(double r, const double* s_a, const double* s_b, const double* s_d,
                                                const double* s_m, int layer, unsigned int& q)
@@ -96,25 +119,28 @@ __device__ __forceinline__ double quantise_one(double r, const double* s_a, cons
 #pragma unroll
     for (int m = 0; m < (LAYER >= 0 ? LAYER : kNLayMax - 1); m++) {          // replay earlier layers (:387-398)
         if (LAYER < 0 && m >= nl) break;
-        const double fq = s_a[m] * r + s_b[m];
-        const unsigned int qm = (unsigned int)(unsigned char)__double2int_rz(fq);
-        r = r - ((double)qm * s_d[m] + s_m[m]);
+        const double t = floor_magic(s_a[m] * r + s_b[m]);
+        const double qd = t - 4503599627370496.0;                           // exact: the integer as a double
+        r = r - (qd * s_d[m] + s_m[m]);
     }
-    const double fq = s_a[nl] * r + s_b[nl];
-    q = (unsigned int)(unsigned char)__double2int_rz(fq);
-    return r - ((double)q * s_d[nl] + s_m[nl]);
+    const double t = floor_magic(s_a[nl] * r + s_b[nl]);
+    q = (unsigned int)__double2loint(t) & 0xFFu;
+    return r - ((t - 4503599627370496.0) * s_d[nl] + s_m[nl]);
 }
 
 template <int LAYER>
-__global__ void __launch_bounds__(256) quantise_kernel(const double* __restrict__ coef, ChunkGeom g, int layer,
-                                                       DevState* st, uint8_t* __restrict__ sym,
-                                                       uint32_t* __restrict__ hist)
+__global__ void __launch_bounds__(kQThreads, 3) quantise_kernel(const double* __restrict__ coef, ChunkGeom g, int layer,
+                                                               DevState* st, uint8_t* __restrict__ sym,
+                                                               uint32_t* __restrict__ hist)
 {
     if (!st->active[layer]) return;
-    __shared__ uint32_t s_hist[256];
+    extern __shared__ __align__(16) uint32_t s_cnt[];     // [256 bins][64 words], see above
     __shared__ double s_a[kNLayMax], s_b[kNLayMax], s_d[kNLayMax], s_m[kNLayMax];
     const int tid = threadIdx.x;
-    s_hist[tid] = 0;
+    {
+        uint4* z = reinterpret_cast<uint4*>(s_cnt);
+        for (int i = tid; i < kQHistBytes / 16; i += kQThreads) z[i] = make_uint4(0, 0, 0, 0);
+    }
     if (tid <= layer) { s_a[tid] = st->aopt[tid]; s_b[tid] = st->bopt[tid]; s_d[tid] = st->deps[tid]; s_m[tid] = st->minval[tid]; }
     __syncthreads();
     const unsigned int b = blockIdx.x;
@@ -123,54 +149,76 @@ __global__ void __launch_bounds__(256) quantise_kernel(const double* __restrict_
     const unsigned long long clen = (g.ntot - cstart < g.chunk_len) ? g.ntot - cstart : g.chunk_len;
     const unsigned long long boff = (unsigned long long)kb * kBlock;
     const unsigned int bs = (clen - boff < kBlock) ? (unsigned int)(clen - boff) : kBlock;
-    const double* __restrict__ in = coef + cstart + boff;
-    uint8_t* __restrict__ out = sym + (unsigned long long)c * g.pitch + boff;
-    double rmin = 0, rmax = 0;
-    bool any = false;
-    const unsigned int lane = tid & 31;
-    for (unsigned int i0 = 0; i0 < bs; i0 += 1024) {
-        double r[4];
-        bool ok[4];
+    const double* __restrict__ in = coef + cstart + boff + tid;
+    uint8_t* __restrict__ out = sym + (unsigned long long)c * g.pitch + boff + tid;
+    uint8_t* cnt = reinterpret_cast<uint8_t*>(s_cnt) + (tid & 63) * 4 + (tid >> 6);
+    const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+    double rmin = kInf, rmax = -kInf;
+    auto one = [&](double r, unsigned int i) {
+        unsigned int q;
+        const double res = quantise_one<LAYER>(r, s_a, s_b, s_d, s_m, layer, q);
+        out[i] = (uint8_t)q;
+        cnt[q * 256u] += 1;
+        rmin = fmin(rmin, res);
+        rmax = fmax(rmax, res);
+    };
+    unsigned int i0 = 0;
+    for (; i0 + kQTile <= bs; i0 += kQTile) {             // full tiles: no predicates
+        double r[kQLoads];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const unsigned int i = i0 + k * 256 + tid;
-            ok[k] = i < bs;
-            r[k] = ok[k] ? in[i] : 0.0;
-        }
+        for (int k = 0; k < kQLoads; k++) r[k] = in[i0 + k * kQThreads];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const unsigned int i = i0 + k * 256 + tid;
-            unsigned int q = 0;
-            if (ok[k]) {
-                const double res = quantise_one<LAYER>(r[k], s_a, s_b, s_d, s_m, layer, q);
-                out[i] = (uint8_t)q;
-                rmin = any ? fmin(rmin, res) : res;
-                rmax = any ? fmax(rmax, res) : res;
-                any = true;
-            }
-            // warp-aggregated histogram update (peaked distributions would serialise plain atomics)
-            const unsigned int act = __ballot_sync(0xffffffffu, ok[k]);
-            if (ok[k]) {
-                const unsigned int peers = __match_any_sync(act, q);
-                if ((unsigned int)(__ffs(peers) - 1) == lane) atomicAdd(&s_hist[q], (unsigned int)__popc(peers));
-            }
-        }
+        for (int k = 0; k < kQLoads; k++) one(r[k], i0 + k * kQThreads);
+    }
+    if (i0 < bs) {                                        // ragged tail
+        double r[kQLoads];
+#pragma unroll
+        for (int k = 0; k < kQLoads; k++) r[k] = (i0 + k * kQThreads + tid < bs) ? in[i0 + k * kQThreads] : 0.0;
+#pragma unroll
+        for (int k = 0; k < kQLoads; k++)
+            if (i0 + k * kQThreads + tid < bs) one(r[k], i0 + k * kQThreads);
     }
     __syncthreads();
-    hist[(unsigned long long)b * 256 + tid] = s_hist[tid];
+    {   // thread = bin: add up the 256 private counters of the bin (64 words, rotated start -> no bank conflicts)
+        const uint32_t* row = s_cnt + tid * 64;
+        uint32_t lo = 0, hi = 0;
+#pragma unroll 8
+        for (int w = 0; w < 64; w++) {
+            const uint32_t x = row[(w + tid) & 63];
+            lo += x & 0x00FF00FFu;
+            hi += (x >> 8) & 0x00FF00FFu;
+        }
+        hist[(unsigned long long)b * 256 + tid] = (lo & 0xFFFFu) + (lo >> 16) + (hi & 0xFFFFu) + (hi >> 16);
+    }
+    const bool any = (unsigned int)tid < bs;
     block_minmax_commit(any ? dkey(rmin) : kKeyMinInit, any ? dkey(rmax) : kKeyMaxInit, &st->rmin_key[layer + 1],
                         &st->rmax_key[layer + 1]);
+}
+
+template <int LAYER>
+static void launch_quantise(const double* coef, const ChunkGeom& g, int layer, DevState* st, uint8_t* sym, uint32_t* hist,
+                            cudaStream_t s)
+{
+    static bool configured = false;                       // 64 KiB dynamic shared memory: above the 48 KiB default
+    if (!configured) {
+        cudaFuncSetAttribute(quantise_kernel<LAYER>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQHistBytes);
+        configured = true;
+    }
+    quantise_kernel<LAYER><<<g.nblocks, kQThreads, kQHistBytes, s>>>(coef, g, layer, st, sym, hist);
 }
 
 void quantise_layer(const double* coef, const ChunkGeom& g, int layer, DevState* st, uint8_t* sym, uint32_t* hist,
                     cudaStream_t s)
 {
     switch (layer) {
-    case 0: quantise_kernel<0><<<g.nblocks, 256, 0, s>>>(coef, g, layer, st, sym, hist); break;
-    case 1: quantise_kernel<1><<<g.nblocks, 256, 0, s>>>(coef, g, layer, st, sym, hist); break;
-    case 2: quantise_kernel<2><<<g.nblocks, 256, 0, s>>>(coef, g, layer, st, sym, hist); break;
-    case 3: quantise_kernel<3><<<g.nblocks, 256, 0, s>>>(coef, g, layer, st, sym, hist); break;
-    default: quantise_kernel<-1><<<g.nblocks, 256, 0, s>>>(coef, g, layer, st, sym, hist); break;
+    case 0: launch_quantise<0>(coef, g, layer, st, sym, hist, s); break;
+    case 1: launch_quantise<1>(coef, g, layer, st, sym, hist, s); break;
+    case 2: launch_quantise<2>(coef, g, layer, st, sym, hist, s); break;
+    case 3: launch_quantise<3>(coef, g, layer, st, sym, hist, s); break;
+    case 4: launch_quantise<4>(coef, g, layer, st, sym, hist, s); break;
+    case 5: launch_quantise<5>(coef, g, layer, st, sym, hist, s); break;
+    case 6: launch_quantise<6>(coef, g, layer, st, sym, hist, s); break;
+    default: launch_quantise<7>(coef, g, layer, st, sym, hist, s); break;
     }
     note_launch(1);
 }

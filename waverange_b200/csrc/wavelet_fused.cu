@@ -49,78 +49,98 @@ __device__ __forceinline__ int mirror_idx(int i, int n)
     return min(max(i, 0), n - 1);
 }
 
+// running extrema in the input's own type: for f32 input fminf/fmaxf are single ALU instructions, and
+// widening to double afterwards is exact and monotonic
+__device__ __forceinline__ void track_ext(float v, float& mn, float& mx) { mn = fminf(mn, v); mx = fmaxf(mx, v); }
+__device__ __forceinline__ void track_ext(double v, double& mn, double& mx) { mn = fmin(mn, v); mx = fmax(mx, v); }
+
+constexpr int FTP = FTX + 2;                                        // row pitch of the input tile (73: odd)
+constexpr int FSLOTS = (FTY * FTX + FTHREADS - 1) / FTHREADS;       // tile elements per thread (7)
+
 // For even line lengths the reference's line-end formulas (waveletcdf97_3d.c:113,116,121,124) are what
 // the interior formula gives on the whole-sample symmetric extension of the line: V1[M-1] += a*2*V0[M-1]
 // is a*(V0[M]+V0[M-1]) with V0[M] := V0[M-1], bit for bit (s+s and 2a are exact).  So the halo of the
 // tile, and the planes fed to the z pipeline beyond the box, are fetched through mirrored indices and
 // no boundary code exists below.
-template <class TIN>
+//
+// Everything that does not change from plane to plane is computed once per thread: the (mirrored) global
+// offset and the shared-memory offset of its FSLOTS tile elements, the in-plane offsets and masks of its
+// eight outputs.  Per plane a load is then one IMAD.WIDE + LDG and a store one IMAD.WIDE + STG.
+template <class TIN, bool TRACK_IN>
 __global__ void __launch_bounds__(FTHREADS, 2) fwd_level_fused_kernel(FusedFwdArgs a)
 {
     // odd row pitches: the x-lifting tasks run with consecutive lanes on consecutive ROWS, so an odd
     // pitch (in doubles) spreads them over the banks; the y-lifting reads run along a row
-    __shared__ double tin[FTY][FTX + 2];        // input tile incl. halo (pitch 73)
+    __shared__ double tin[FTY * FTP];           // input tile incl. halo
     __shared__ double tx[FTY][2 * FPX + 1];     // after x-lifting: [row][low 32 | high 32] (pitch 65)
     const TIN* __restrict__ src = (const TIN*)a.src;
-    const int tid = threadIdx.x, wrp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int m0 = a.n0 >> 1, m1 = a.n1 >> 1;
     const int px0 = blockIdx.x * FPX, py0 = blockIdx.y * FPY;
     const int e0 = a.pair_lo + blockIdx.z * a.zpairs;
     const int e1 = (e0 + a.zpairs < a.pair_lo + a.nl) ? e0 + a.zpairs : a.pair_lo + a.nl;
     const int x0 = 2 * px0 - 4, y0 = 2 * py0 - 4;           // tile origin in input coordinates
-    // ---- tile slots of this thread: rows wrp, wrp+8, wrp+16; columns lane, lane+32, lane+64 ----
-    int toff[9];
+    // ---- tile elements of this thread: flat index tid + k*FTHREADS over FTY x FTX ----
+    int goff[FSLOTS], soff[FSLOTS];
 #pragma unroll
-    for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-            const int ry = wrp + 8 * r, rx = lane + 32 * q;
-            toff[r * 3 + q] = (ry < FTY && rx < FTX)
-                                  ? (int)(mirror_idx(x0 + rx, a.n0) + (long long)mirror_idx(y0 + ry, a.n1) * a.ssy) : -1;
-        }
+    for (int k = 0; k < FSLOTS; k++) {
+        const int idx = tid + k * FTHREADS;
+        const bool ok = idx < FTY * FTX;
+        const int ry = idx / FTX, rx = idx - ry * FTX;
+        // unused slots re-read element (0,0) of the plane (a real field value: harmless for the extrema)
+        // and park it in the pad column of row 0
+        goff[k] = ok ? (int)(mirror_idx(x0 + rx, a.n0) + (long long)mirror_idx(y0 + ry, a.n1) * a.ssy) : 0;
+        soff[k] = ok ? ry * FTP + rx : FTX;
+    }
     // ---- z-pipeline ownership: column c of tx, y pairs j0, j0+1 ----
     const int c = tid & 63;
     const int j0 = py0 + 2 * (tid >> 6);
-    const int xo = (c < FPX) ? px0 + c : m0 + px0 + (c - FPX);      // output x
-    const bool xok = ((c < FPX) ? px0 + c : px0 + c - FPX) < m0;
-    int ooff[4], loff[2];                          // output offsets inside a z-plane (< 2^31), -1: masked
+    const bool xlow = c < FPX;
+    const int xo = xlow ? px0 + c : m0 + px0 + (c - FPX);           // output x
+    const bool xok = (xlow ? px0 + c : px0 + c - FPX) < m0;
+    const bool to_lll = xlow && a.lll != nullptr;                    // v < 2: low-low-low, next level's input
+    int ooff[4], o01[2];                           // output offsets inside a z-plane (< 2^31)
+    bool ook[4];
 #pragma unroll
     for (int v = 0; v < 4; v++) {
         const int j = j0 + (v & 1);
         const int yo = (v < 2) ? j : m1 + j;
-        ooff[v] = (xok && j < m1) ? (int)(xo + (long long)yo * a.ay) : -1;
-        if (v < 2) loff[v] = (xok && j < m1 && c < FPX && a.lll != nullptr) ? (int)(xo + (long long)yo * a.lsy) : -1;
+        ook[v] = xok && j < m1;
+        ooff[v] = ook[v] ? (int)(xo + (long long)yo * a.ay) : 0;
+        if (v < 2) o01[v] = ook[v] ? (to_lll ? (int)(xo + (long long)yo * a.lsy) : ooff[v]) : 0;
     }
+    // plane pointers of output pair mo = e0 - 4 (advanced once per pair; dereferenced for mo >= e0 only)
+    const long long s01 = to_lll ? a.lsz : a.az;
+    double* plo = a.coef + (long long)(e0 - 4 - a.pair_lo) * a.az;
+    double* phi = plo + (long long)a.nl * a.az;
+    double* p01 = (to_lll ? a.lll : a.coef) + (long long)(e0 - 4 - a.pair_lo) * s01;
     double s0p[4] = {0, 0, 0, 0}, d0p[4] = {0, 0, 0, 0}, d1p[4] = {0, 0, 0, 0}, s1p[4] = {0, 0, 0, 0}, d2p[4] = {0, 0, 0, 0};
     const double kInf = __longlong_as_double(0x7ff0000000000000ll);
-    double fmn = kInf, fmx = -kInf, omn = kInf, omx = -kInf;      // fmin/fmax identities
-    const bool track_in = a.in_min != nullptr;
+    TIN fmn = (TIN)kInf, fmx = (TIN)(-kInf);                        // fmin/fmax identities
+    double omn = kInf, omx = -kInf;
 
-    TIN nxt[9];
+    TIN nxt[FSLOTS];
     auto load_plane = [&](int z) {
         const TIN* __restrict__ plane = src + (long long)(mirror_idx(z, a.n2) - a.zoff) * a.ssz;
 #pragma unroll
-        for (int k = 0; k < 9; k++) nxt[k] = (toff[k] >= 0) ? plane[toff[k]] : (TIN)0;
+        for (int k = 0; k < FSLOTS; k++) nxt[k] = plane[goff[k]];
     };
     // x- and y-lifting of the plane held in nxt[]; prefetches plane znext meanwhile; returns the four
     // (x, y, sub-band) values this thread feeds into its z pipelines
     auto lift_plane = [&](int znext, bool more, double (&yv)[4]) {
 #pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-            for (int q = 0; q < 3; q++)
-                if (toff[r * 3 + q] >= 0) {
-                    const double v = (double)nxt[r * 3 + q];
-                    tin[wrp + 8 * r][lane + 32 * q] = v;
-                    if (track_in) { fmn = fmin(fmn, v); fmx = fmax(fmx, v); }
-                }
+        for (int k = 0; k < FSLOTS; k++) {
+            const TIN v = nxt[k];
+            if (TRACK_IN) track_ext(v, fmn, fmx);
+            tin[soff[k]] = (double)v;
+        }
         __syncthreads();
         if (more) load_plane(znext);               // next plane in flight while this one is lifted
         // x-lifting: FXR pairs per task, consecutive lanes on consecutive rows
         for (int t = tid; t < FTY * (FPX / FXR); t += FTHREADS) {
             const int g = t / FTY, ry = t - g * FTY;
             double so[FXR], dd[FXR];
-            const double* row = &tin[ry][4 + 2 * g * FXR];         // sample 2*i0 of the line
+            const double* row = &tin[ry * FTP + 4 + 2 * g * FXR];   // sample 2*i0 of the line
             auto ld = [&](int j) -> double { return row[j]; };
             fwd_pairs_interior<FXR>(ld, 0, so, dd);
 #pragma unroll
@@ -142,8 +162,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) fwd_level_fused_kernel(FusedFwdAr
     for (int m = e0 - 2; m <= e1 + 1; m++) {
         double yv[4];
         lift_plane(2 * m + 1, m <= e1, yv);                      // even plane: s0[m]; pair m-2 completes
-        const int mo = m - 2;
-        const bool out = (mo >= e0);
+        const bool out = (m - 2 >= e0);
 #pragma unroll
         for (int v = 0; v < 4; v++) {
             const double s0n = yv[v];
@@ -152,25 +171,30 @@ __global__ void __launch_bounds__(FTHREADS, 2) fwd_level_fused_kernel(FusedFwdAr
             const double d2 = d1p[v] + WRB_LC * (s1 + s1p[v]);           // d2[m-2]
             const double s2 = s1p[v] + WRB_LD * (d2 + d2p[v]);           // s2[m-2]
             d2p[v] = d2; d1p[v] = d1; s1p[v] = s1; s0p[v] = s0n;
-            if (out && ooff[v] >= 0) {
+            if (out && ook[v]) {
                 const double lo = s2 * WRB_SCL, hi = d2 * WRB_PSCL;
-                a.coef[ooff[v] + (long long)(a.nl + mo - a.pair_lo) * a.az] = hi;   // z-high: always a final coefficient
+                phi[ooff[v]] = hi;                                       // z-high: always a final coefficient
                 omn = fmin(omn, hi); omx = fmax(omx, hi);
-                if (v < 2 && loff[v & 1] >= 0) {
-                    a.lll[loff[v & 1] + (long long)(mo - a.pair_lo) * a.lsz] = lo;   // low-low-low: next level's input
+                if (v < 2) {
+                    p01[o01[v]] = lo;
+                    if (!to_lll) { omn = fmin(omn, lo); omx = fmax(omx, lo); }
                 } else {
-                    a.coef[ooff[v] + (long long)(mo - a.pair_lo) * a.az] = lo;
+                    plo[ooff[v]] = lo;
                     omn = fmin(omn, lo); omx = fmax(omx, lo);
                 }
             }
         }
+        plo += a.az; phi += a.az; p01 += s01;
         if (m <= e1) {                                               // odd plane: d0[m]
             lift_plane(2 * m + 2, true, yv);
 #pragma unroll
             for (int v = 0; v < 4; v++) d0p[v] = yv[v];
         }
     }
-    if (track_in) block_minmax_commit(fmn <= fmx ? dkey(fmn) : kKeyMinInit, fmn <= fmx ? dkey(fmx) : kKeyMaxInit, a.in_min, a.in_max);
+    if (TRACK_IN) {
+        const double dmn = (double)fmn, dmx = (double)fmx;
+        block_minmax_commit(dmn <= dmx ? dkey(dmn) : kKeyMinInit, dmn <= dmx ? dkey(dmx) : kKeyMaxInit, a.in_min, a.in_max);
+    }
     block_minmax_commit(omn <= omx ? dkey(omn) : kKeyMinInit, omn <= omx ? dkey(omx) : kKeyMaxInit, a.out_min, a.out_max);
 }
 
@@ -200,8 +224,14 @@ void fused_forward_level(const void* src, int src_is_f32, long long ssy, long lo
     while (zp > 16 && (long long)gx * gy * ((m2 + zp - 1) / zp) < 148 * 4) zp = (zp + 1) / 2;
     a.zpairs = zp;
     dim3 grid(gx, gy, (m2 + zp - 1) / zp);
-    if (src_is_f32) fwd_level_fused_kernel<float><<<grid, FTHREADS, 0, s>>>(a);
-    else fwd_level_fused_kernel<double><<<grid, FTHREADS, 0, s>>>(a);
+    const bool track = in_min != nullptr;
+    if (src_is_f32) {
+        if (track) fwd_level_fused_kernel<float, true><<<grid, FTHREADS, 0, s>>>(a);
+        else fwd_level_fused_kernel<float, false><<<grid, FTHREADS, 0, s>>>(a);
+    } else {
+        if (track) fwd_level_fused_kernel<double, true><<<grid, FTHREADS, 0, s>>>(a);
+        else fwd_level_fused_kernel<double, false><<<grid, FTHREADS, 0, s>>>(a);
+    }
     note_launch(1);
 }
 
