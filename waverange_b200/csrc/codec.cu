@@ -303,6 +303,7 @@ static int run_transform_and_quantise(wrb_codec* c, const void* d_field, int dty
     if (c->timing) cudaEventRecord(c->ev[1], s);
     const unsigned long long lstride = (unsigned long long)g.nchunks * g.pitch;
     const unsigned long long hstride = (unsigned long long)g.nblocks * 256;
+    CK(cudaMemsetAsync(c->hist.p, 0, (size_t)kNLayMax * hstride * 4, s));     // the quantiser adds partial histograms
     for (int l = 0; l < kNLayMax; l++) {
         // global extrema of the coefficients (l == 0) / of the residual left by layer l-1 (wrappers.cpp:308-314)
         if (dist && reduce_extrema(c, &st->rmin_key[l], &st->rmax_key[l])) return fail(c, WRB_E_CUDA, "reduce callback failed");

@@ -103,7 +103,12 @@ void layer_params(DevState* st, int layer, cudaStream_t s) { layer_params_kernel
 constexpr int kQThreads = 256;
 constexpr int kQLoads = 8;                               // coefficients per thread and tile
 constexpr int kQTile = kQThreads * kQLoads;              // 2048
+constexpr int kQAhead = 3;                               // L2 prefetch distance in tiles
 constexpr int kQHistBytes = 256 * kQThreads;             // private byte counters: 64 KiB
+// A coder block is split over kQSub CTAs (partial histograms are added with global atomics): 2237 blocks at
+// 512^3 on 444 CTA slots would otherwise run 6 waves for 5.04 waves of work
+constexpr unsigned int kQSubLen = 8 * kQTile;            // 16384 coefficients
+constexpr unsigned int kQSub = (kBlock + kQSubLen - 1) / kQSubLen;   // 4
 
 __device__ __forceinline__ double floor_magic(double fq)
 {
@@ -129,68 +134,101 @@ __device__ __forceinline__ double quantise_one(double r, const double* s_a, cons
 }
 
 template <int LAYER>
-__global__ void __launch_bounds__(kQThreads, 3) quantise_kernel(const double* __restrict__ coef, ChunkGeom g, int layer,
+__global__ void __launch_bounds__(kQThreads, (LAYER <= 2) ? 3 : 2) quantise_kernel(const double* __restrict__ coef, ChunkGeom g, int layer,
                                                                DevState* st, uint8_t* __restrict__ sym,
                                                                uint32_t* __restrict__ hist)
 {
     if (!st->active[layer]) return;
-    extern __shared__ __align__(16) uint32_t s_cnt[];     // [256 bins][64 words], see above
-    __shared__ double s_a[kNLayMax], s_b[kNLayMax], s_d[kNLayMax], s_m[kNLayMax];
     const int tid = threadIdx.x;
-    {
-        uint4* z = reinterpret_cast<uint4*>(s_cnt);
-        for (int i = tid; i < kQHistBytes / 16; i += kQThreads) z[i] = make_uint4(0, 0, 0, 0);
-    }
-    if (tid <= layer) { s_a[tid] = st->aopt[tid]; s_b[tid] = st->bopt[tid]; s_d[tid] = st->deps[tid]; s_m[tid] = st->minval[tid]; }
-    __syncthreads();
     const unsigned int b = blockIdx.x;
     const unsigned int c = b / g.blocks_per_chunk, kb = b % g.blocks_per_chunk;
     const unsigned long long cstart = (unsigned long long)c * g.chunk_len;
     const unsigned long long clen = (g.ntot - cstart < g.chunk_len) ? g.ntot - cstart : g.chunk_len;
     const unsigned long long boff = (unsigned long long)kb * kBlock;
     const unsigned int bs = (clen - boff < kBlock) ? (unsigned int)(clen - boff) : kBlock;
-    const double* __restrict__ in = coef + cstart + boff + tid;
-    uint8_t* __restrict__ out = sym + (unsigned long long)c * g.pitch + boff + tid;
-    uint8_t* cnt = reinterpret_cast<uint8_t*>(s_cnt) + (tid & 63) * 4 + (tid >> 6);
+    const unsigned int sb0 = blockIdx.y * kQSubLen;       // this CTA's part of the coder block
+    if (sb0 >= bs) return;
+    const unsigned int n = (bs - sb0 < kQSubLen) ? bs - sb0 : kQSubLen;
+    extern __shared__ __align__(16) uint32_t s_cnt[];     // [256 bins][64 words], see above
+    __shared__ double s_a[kNLayMax], s_b[kNLayMax], s_d[kNLayMax], s_m[kNLayMax];
+    const double* __restrict__ in = coef + cstart + boff + sb0 + tid;
+    uint8_t* __restrict__ out = sym + (unsigned long long)c * g.pitch + boff + sb0 + tid;
+    // the first tile's loads and the L2 prefetch of the next ones go out before the counters are cleared
+    double r[kQLoads], rn[kQLoads];
+    const unsigned int nfull = n / kQTile;
+    if (nfull > 0) {
+#pragma unroll
+        for (int k = 0; k < kQLoads; k++) r[k] = in[k * kQThreads];
+        for (unsigned int t = 1; t <= kQAhead && t < nfull; t++) {
+#pragma unroll
+            for (int k = 0; k < kQLoads; k++) prefetch_l2(in + t * kQTile + k * kQThreads);
+        }
+    }
+    {
+        uint4* z = reinterpret_cast<uint4*>(s_cnt);
+        for (int i = tid; i < kQHistBytes / 16; i += kQThreads) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (tid <= layer) { s_a[tid] = st->aopt[tid]; s_b[tid] = st->bopt[tid]; s_d[tid] = st->deps[tid]; s_m[tid] = st->minval[tid]; }
+    __syncthreads();
+    uint8_t* const cnt = reinterpret_cast<uint8_t*>(s_cnt);
+    const unsigned int mine = (tid & 63) * 4 + (tid >> 6);      // < 256: byte 0 of a counter's offset, the bin is byte 1
     const double kInf = __longlong_as_double(0x7ff0000000000000ll);
     double rmin = kInf, rmax = -kInf;
-    auto one = [&](double r, unsigned int i) {
+    auto one = [&](double r, uint8_t* dst) {
         unsigned int q;
         const double res = quantise_one<LAYER>(r, s_a, s_b, s_d, s_m, layer, q);
-        out[i] = (uint8_t)q;
-        cnt[q * 256u] += 1;
-        rmin = fmin(rmin, res);
-        rmax = fmax(rmax, res);
+        *dst = (uint8_t)q;
+        cnt[__byte_perm(q, mine, 0x6504)] += 1;                  // offset = bin * 256 + mine in one PRMT
+        rmin = dmin2(rmin, res);
+        rmax = dmax2(rmax, res);
     };
-    unsigned int i0 = 0;
-    for (; i0 + kQTile <= bs; i0 += kQTile) {             // full tiles: no predicates
-        double r[kQLoads];
+    // full tiles: no predicates; the loads of tile t+1 are issued before tile t is processed (two register
+    // sets used alternately); running pointers keep every access at base + immediate
+    for (unsigned int t = 0; t < nfull; t += 2) {
+        if (t + kQAhead + 1 < nfull) {                    // two tiles per iteration: tiles t+kQAhead, t+kQAhead+1
 #pragma unroll
-        for (int k = 0; k < kQLoads; k++) r[k] = in[i0 + k * kQThreads];
+            for (int k = 0; k < 2 * kQLoads; k++) prefetch_l2(in + kQAhead * kQTile + k * kQThreads);
+        }
+        if (t + 1 < nfull) {
 #pragma unroll
-        for (int k = 0; k < kQLoads; k++) one(r[k], i0 + k * kQThreads);
+            for (int k = 0; k < kQLoads; k++) rn[k] = in[kQTile + k * kQThreads];
+        }
+#pragma unroll
+        for (int k = 0; k < kQLoads; k++) one(r[k], out + k * kQThreads);
+        in += kQTile; out += kQTile;
+        if (t + 1 < nfull) {
+            if (t + 2 < nfull) {
+#pragma unroll
+                for (int k = 0; k < kQLoads; k++) r[k] = in[kQTile + k * kQThreads];
+            }
+#pragma unroll
+            for (int k = 0; k < kQLoads; k++) one(rn[k], out + k * kQThreads);
+            in += kQTile; out += kQTile;
+        }
     }
-    if (i0 < bs) {                                        // ragged tail
-        double r[kQLoads];
+    const unsigned int i0 = nfull * kQTile;
+    if (i0 < n) {                                         // ragged tail
 #pragma unroll
-        for (int k = 0; k < kQLoads; k++) r[k] = (i0 + k * kQThreads + tid < bs) ? in[i0 + k * kQThreads] : 0.0;
+        for (int k = 0; k < kQLoads; k++) r[k] = (i0 + k * kQThreads + tid < n) ? in[k * kQThreads] : 0.0;
 #pragma unroll
         for (int k = 0; k < kQLoads; k++)
-            if (i0 + k * kQThreads + tid < bs) one(r[k], i0 + k * kQThreads);
+            if (i0 + k * kQThreads + tid < n) one(r[k], out + k * kQThreads);
     }
     __syncthreads();
     {   // thread = bin: add up the 256 private counters of the bin (64 words, rotated start -> no bank conflicts)
-        const uint32_t* row = s_cnt + tid * 64;
-        uint32_t lo = 0, hi = 0;
-#pragma unroll 8
-        for (int w = 0; w < 64; w++) {
-            const uint32_t x = row[(w + tid) & 63];
-            lo += x & 0x00FF00FFu;
-            hi += (x >> 8) & 0x00FF00FFu;
+        const uint4* row = reinterpret_cast<const uint4*>(s_cnt + tid * 64);
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < 16; w++) {
+            const uint4 x = row[(w + tid) & 15];
+            tot = __dp4a((int)x.x, 0x01010101, tot);      // sum of the four byte counters of a word
+            tot = __dp4a((int)x.y, 0x01010101, tot);
+            tot = __dp4a((int)x.z, 0x01010101, tot);
+            tot = __dp4a((int)x.w, 0x01010101, tot);
         }
-        hist[(unsigned long long)b * 256 + tid] = (lo & 0xFFFFu) + (lo >> 16) + (hi & 0xFFFFu) + (hi >> 16);
+        if (tot) atomicAdd(&hist[(unsigned long long)b * 256 + tid], (uint32_t)tot);      // hist is zeroed per encode
     }
-    const bool any = (unsigned int)tid < bs;
+    const bool any = (unsigned int)tid < n;
     block_minmax_commit(any ? dkey(rmin) : kKeyMinInit, any ? dkey(rmax) : kKeyMaxInit, &st->rmin_key[layer + 1],
                         &st->rmax_key[layer + 1]);
 }
@@ -204,7 +242,7 @@ static void launch_quantise(const double* coef, const ChunkGeom& g, int layer, D
         cudaFuncSetAttribute(quantise_kernel<LAYER>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQHistBytes);
         configured = true;
     }
-    quantise_kernel<LAYER><<<g.nblocks, kQThreads, kQHistBytes, s>>>(coef, g, layer, st, sym, hist);
+    quantise_kernel<LAYER><<<dim3(g.nblocks, kQSub, 1), kQThreads, kQHistBytes, s>>>(coef, g, layer, st, sym, hist);
 }
 
 void quantise_layer(const double* coef, const ChunkGeom& g, int layer, DevState* st, uint8_t* sym, uint32_t* hist,

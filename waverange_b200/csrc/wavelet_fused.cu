@@ -52,7 +52,7 @@ __device__ __forceinline__ int mirror_idx(int i, int n)
 // running extrema in the input's own type: for f32 input fminf/fmaxf are single ALU instructions, and
 // widening to double afterwards is exact and monotonic
 __device__ __forceinline__ void track_ext(float v, float& mn, float& mx) { mn = fminf(mn, v); mx = fmaxf(mx, v); }
-__device__ __forceinline__ void track_ext(double v, double& mn, double& mx) { mn = fmin(mn, v); mx = fmax(mx, v); }
+__device__ __forceinline__ void track_ext(double v, double& mn, double& mx) { mn = dmin2(mn, v); mx = dmax2(mx, v); }
 
 constexpr int FTP = FTX + 2;                                        // row pitch of the input tile (73: odd)
 constexpr int FSLOTS = (FTY * FTX + FTHREADS - 1) / FTHREADS;       // tile elements per thread (7)
@@ -174,13 +174,13 @@ __global__ void __launch_bounds__(FTHREADS, 2) fwd_level_fused_kernel(FusedFwdAr
             if (out && ook[v]) {
                 const double lo = s2 * WRB_SCL, hi = d2 * WRB_PSCL;
                 phi[ooff[v]] = hi;                                       // z-high: always a final coefficient
-                omn = fmin(omn, hi); omx = fmax(omx, hi);
+                omn = dmin2(omn, hi); omx = dmax2(omx, hi);
                 if (v < 2) {
                     p01[o01[v]] = lo;
-                    if (!to_lll) { omn = fmin(omn, lo); omx = fmax(omx, lo); }
+                    if (!to_lll) { omn = dmin2(omn, lo); omx = dmax2(omx, lo); }
                 } else {
                     plo[ooff[v]] = lo;
-                    omn = fmin(omn, lo); omx = fmax(omx, lo);
+                    omn = dmin2(omn, lo); omx = dmax2(omx, lo);
                 }
             }
         }

@@ -64,6 +64,15 @@ __host__ __device__ inline double dunkey(unsigned long long k)
     double x; memcpy(&x, &b, 8); return x;
 #endif
 }
+// min/max by plain comparison: fmin()/fmax() on doubles expand to ~10 instructions each (NaN
+// propagation); the reference assumes NaN-free data and so do these (result for a < b is a)
+__device__ __forceinline__ double dmin2(double a, double b) { return (b < a) ? b : a; }
+__device__ __forceinline__ double dmax2(double a, double b) { return (b > a) ? b : a; }
+
+// DRAM -> L2 prefetch: the bytes a streaming kernel needs in flight to cover HBM latency (~50-100 KB per
+// SM) are parked in L2 instead of registers; the register prefetch then only has to cover L2 latency
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
 constexpr unsigned long long kKeyMinInit = ~0ull;   // identity for min
 constexpr unsigned long long kKeyMaxInit = 0ull;    // identity for max
 
