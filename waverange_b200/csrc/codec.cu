@@ -477,8 +477,9 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
     } else if (npeek >= 1 && peek[0] != 0x00) {
         return fail(c, WRB_E_FORMAT, "layer is neither a WRCK container nor a reference stream");
     }
-    const ChunkGeom g = make_geom(ntot, chunk_len, (unsigned)nseek);
+    ChunkGeom g = make_geom(ntot, chunk_len, (unsigned)nseek);
     if (g.nseek != nseek) return fail(c, WRB_E_FORMAT, "seek table does not match the chunk geometry");
+    if (getenv("WRB_DEC_PADDED") == nullptr) g.pitch = g.chunk_len;        // decoded symbols are kept flat (array order): the inverse transform indexes them directly
     int rc;
     if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr))) return rc;
     if ((rc = ensure_coder_buffers(c, g, nlay, false))) return rc;

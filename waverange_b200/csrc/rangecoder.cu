@@ -23,6 +23,7 @@
 //    chunk.  From them and the final stream bytes W at that position a decoder state follows as
 //    X = W - 2*low (mod 2^32), X being the decoder's (low << 1 | last bit read), so several lanes
 //    decode one chunk concurrently.  The chunk stream itself is unchanged.
+#include <cstdlib>
 #include "wr_common.cuh"
 #include "wr_kernels.h"
 
@@ -443,6 +444,7 @@ __device__ __forceinline__ uint32_t dec_short(Dec& d)
     return t;
 }
 
+constexpr int kDecVariantDefault = 2;     // packed stores, eager stream loads (fastest measured at 512^3: 5.38 ms)     // see range_decode_kernel
 constexpr int kLutShift = 6;
 constexpr int kLutSize = (kBlock >> kLutShift) + 1;           // 938 buckets
 
@@ -453,7 +455,17 @@ constexpr int kLutSize = (kBlock >> kLutShift) + 1;           // 938 buckets
 // a short forward scan over the packed (cum, count) table (zero-count symbols are skipped by the
 // same scan, wrappers.cpp:205).  The lanes that share a chunk share its tables (column = chunk slot
 // inside the warp): all of them decode the identical table and store identical values.
-template <int NSUB>
+// The symbol loop is one dependency chain per lane and the warps are few (1-2 per scheduler), so what counts is
+// the length of that chain and the load/store unit time the warp's uncoalesced accesses take:
+//   * stream words come through the read-only path (ld.global.nc);
+//   * renormalisation is branch-free (one funnel shift by 0/8/16);
+//   * pair table: entry s holds (ent[s], ent[s+1]) so one 64-bit shared load serves both probes.
+// VAR selects further variants (WRB_DEC_VARIANT, for A/B timing; all bit-identical):
+//   bit 0: lazy stream loads -- a new word is fetched (predicated) only by the lanes that crossed a word
+//          boundary, instead of two 32-sector loads per symbol;
+//   bit 1: packed stores -- a lane stores a 32-bit word when its output address completes one, bytes only
+//          for a ragged head/tail, instead of one 32-sector byte store per symbol.
+template <int NSUB, int VAR>
 __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restrict__ blob,
                                                           const unsigned long long* __restrict__ offs,
                                                           const unsigned long long* __restrict__ lay_off, ChunkGeom g,
@@ -461,9 +473,12 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
                                                           int* error)
 {
     constexpr unsigned int CPW = 32 / NSUB;
+    constexpr bool kLdg = true, kBranchFree = true, kPair = true;
+    constexpr bool kLazy = (VAR & 1) != 0, kPack = (VAR & 2) != 0;
+    constexpr unsigned int TW = kPair ? 2 : 1;                            // words per table entry
     extern __shared__ __align__(16) uint32_t smem_dyn[];
     uint32_t* tab = smem_dyn;                                             // [symbol][column] = cum << 16 | count (+ sentinel row)
-    uint8_t* lut = reinterpret_cast<uint8_t*>(smem_dyn + 257 * CPW);      // [bucket][column]
+    uint8_t* lut = reinterpret_cast<uint8_t*>(smem_dyn + 257 * CPW * TW); // [bucket][column]
     const int layer = blockIdx.y;
     const unsigned int lane = threadIdx.x;
     const unsigned int col = lane / NSUB, sub = lane % NSUB;
@@ -478,7 +493,7 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
     d.X = d.p[1];                                 // lead byte skipped (rangecod.c:283-288)
     d.ip = 2;
     d.range = 1u << 7;
-    const uint32_t* tl = tab + col;
+    const uint32_t* tl = tab + col * TW;
     const uint8_t* ll = lut + col;
     unsigned long long n = 0;
     unsigned int nblocks = 0;
@@ -493,7 +508,8 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
         int nextb = 0;                            // first bucket not yet assigned
         for (int s = 0; s < 256; s++) {           // readcounts (rangecod.c:400-404) + prefix sums
             const uint32_t c = dec_short(d);
-            tab[s * CPW + col] = (acc << 16) | c;
+            tab[(s * CPW + col) * TW] = (acc << 16) | c;
+            if (kPair && s > 0) tab[((s - 1) * CPW + col) * TW + 1] = (acc << 16) | c;
             if (c) {
                 const int lastb = (int)((acc + c - 1) >> kLutShift);
                 if (lastb < kLutSize) for (; nextb <= lastb; nextb++) lut[nextb * CPW + col] = (uint8_t)s;
@@ -502,7 +518,8 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
             if (acc > kBlock) { bad = true; break; }
         }
         if (bad) break;
-        tab[256 * CPW + col] = 0xFFFF0000u;       // sentinel: never satisfies cum + count <= cf
+        tab[(256 * CPW + col) * TW] = 0xFFFF0000u;       // sentinel: never satisfies cum + count <= cf
+        if (kPair) { tab[(255 * CPW + col) * TW + 1] = 0xFFFF0000u; tab[(256 * CPW + col) * TW + 1] = 0xFFFF0000u; }
         const uint32_t bs = acc;
         if (n + bs > clen) { bad = true; break; }
         uint32_t s0 = 0, s1 = bs;
@@ -534,30 +551,50 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
         const uint32_t* __restrict__ wbase = reinterpret_cast<const uint32_t*>(pa & ~3ull);
         const uint32_t boff = (uint32_t)(pa & 3ull);
         uint32_t a = boff + d.ip;
-        uint32_t w0 = wbase[a >> 2], w1 = wbase[(a >> 2) + 1];
+        auto ldw = [&](uint32_t widx) -> uint32_t { return kLdg ? __ldg(wbase + widx) : wbase[widx]; };
+        uint32_t w0 = ldw(a >> 2), w1 = ldw((a >> 2) + 1);
         uint32_t sel = 0x0123u + 0x1111u * (a & 3u);
         uint32_t X = d.X, range = d.range;
+        // Symbols leave one byte at a time: stores are off the dependency chain, the symbol buffer may be flat
+        // (pitch == chunk_len, what the fused inverse transform reads) so a lane's run can start at any byte,
+        // and the bytes a lane writes complete whole 32-byte sectors in L2 long before they are evicted.
+        uint8_t* op = outb + n + s0;
+        uint8_t* const ostart = op;
+        uint8_t* const oend = outb + n + s1;
         uint32_t pack = 0;
-        uint32_t* wp = reinterpret_cast<uint32_t*>(outb + n + s0);   // 4-aligned: s0 % 16 == 0, n % 60000 == 0
-        uint32_t i = s0;
 #pragma unroll 1
-        for (; i < s1; i++) {
+        for (; op != oend; op++) {
             const uint32_t win = __byte_perm(w0, w1, sel);
             const bool k1 = range <= kBottom, k2 = range <= (kBottom >> 8);
-            X = k2 ? __funnelshift_l(win, X, 16) : (k1 ? __funnelshift_l(win, X, 8) : X);   // renormalise
-            range = k2 ? (range << 16) : (k1 ? (range << 8) : range);
-            const uint32_t an = a + (k1 ? 1u : 0u) + (k2 ? 1u : 0u);
+            uint32_t an;
+            if (kBranchFree) {
+                const uint32_t sh = k2 ? 16u : (k1 ? 8u : 0u);
+                X = __funnelshift_l(win, X, sh);                                                // renormalise
+                range <<= sh;
+                an = a + (sh >> 3);
+            } else {
+                X = k2 ? __funnelshift_l(win, X, 16) : (k1 ? __funnelshift_l(win, X, 8) : X);   // renormalise
+                range = k2 ? (range << 16) : (k1 ? (range << 8) : range);
+                an = a + (k1 ? 1u : 0u) + (k2 ? 1u : 0u);
+            }
             if ((an ^ a) & 0x80u) asm volatile("prefetch.global.L1 [%0];" :: "l"(wbase + (an >> 2) + 64));
+            if (kLazy) {
+                if ((an ^ a) & 4u) { w0 = w1; w1 = ldw((an >> 2) + 1); }      // at most 2 bytes per step: one word boundary
+            } else {
+                w0 = ldw(an >> 2);
+                w1 = ldw((an >> 2) + 1);
+            }
             a = an;
-            w0 = wbase[a >> 2];
-            w1 = wbase[(a >> 2) + 1];
             sel = 0x0123u + 0x1111u * (a & 3u);
             help = div_magic(range, mg);          // decode_culfreq(rc, bs)
             uint32_t cf = div_small_quot(X >> 1, help);
             cf = min(cf, bs - 1);
             uint32_t s = ll[(cf >> kLutShift) * CPW];
-            uint32_t e0, e1;                      // both probes issued together (volatile: keep them unconditional)
-            {
+            uint32_t e0, e1;                      // both probes issued together
+            if (kPair) {
+                const uint2 e = *reinterpret_cast<const uint2*>(tl + s * (CPW * 2));
+                e0 = e.x; e1 = e.y;
+            } else {
                 const uint32_t sa = (uint32_t)__cvta_generic_to_shared(tl + s * CPW);
                 asm volatile("ld.shared.u32 %0, [%2];\n\tld.shared.u32 %1, [%2+%3];"
                              : "=r"(e0), "=r"(e1) : "r"(sa), "n"(CPW * 4));
@@ -566,14 +603,27 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
             uint32_t ent = adv ? e1 : e0;
             s += adv ? 1u : 0u;
             uint32_t lt = ent >> 16, sy = ent & 0xFFFFu;
-            while (lt + sy <= cf && s < 255u) { s++; ent = tl[s * CPW]; lt = ent >> 16; sy = ent & 0xFFFFu; }
+            while (lt + sy <= cf && s < 255u) { s++; ent = tl[s * (CPW * TW)]; lt = ent >> 16; sy = ent & 0xFFFFu; }
             const uint32_t tmp = help * lt;       // decode_update (rangecod.c:339-351)
             X -= 2 * tmp;
             range = (lt + sy < bs) ? help * sy : range - tmp;
-            pack |= s << ((i & 3u) * 8);
-            if ((i & 3u) == 3u) { *wp++ = pack; pack = 0; }
+            if (kPack) {
+                const uint32_t ph = (uint32_t)(unsigned long long)op & 3u;
+                pack |= s << (8 * ph);
+                if (ph == 3u) {
+                    if (op - 3 >= ostart) *reinterpret_cast<uint32_t*>(op - 3) = pack;
+                    else for (uint8_t* q = ostart; q <= op; q++) *q = (uint8_t)(pack >> (8 * ((uint32_t)(unsigned long long)q & 3u)));   // ragged head
+                    pack = 0;
+                }
+            } else {
+                *op = (uint8_t)s;
+            }
         }
-        if (i & 3u) *wp = pack;                   // partial word: only at the end of a chunk (pitch slack)
+        if (kPack) {                              // ragged tail (and head, when the run ends inside its first word)
+            uint8_t* q = reinterpret_cast<uint8_t*>((unsigned long long)oend & ~3ull);
+            if (q < ostart) q = ostart;
+            for (; q < oend; q++) *q = (uint8_t)(pack >> (8 * ((uint32_t)(unsigned long long)q & 3u)));
+        }
         d.X = X; d.range = range; d.ip = a - boff;
         n += bs;
         if (NSUB > 1) {
@@ -594,18 +644,31 @@ void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, co
     const unsigned int nsub = g.nseek + 1;        // make_geom grants 0, 1, 3 or 7 seek points
     const unsigned int cpw = 32 / nsub;
     dim3 grid((g.nchunks + cpw - 1) / cpw, nlay, 1);
-    const int smem = (257 * 4 + kLutSize) * (int)cpw;
-    static bool configured = false;
-    if (!configured) {                            // 62.9 KB for one lane per chunk: above the 48 KB default
-        cudaFuncSetAttribute(range_decode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (257 * 4 + kLutSize) * 32);
-        configured = true;
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("WRB_DEC_VARIANT"); variant = (e && *e) ? (atoi(e) & 3) : kDecVariantDefault; }
+    const int smem = (257 * 4 * 2 + kLutSize) * (int)cpw;
+#define WRB_DEC_LAUNCH(NS, V)                                                                                          \
+    do {                                                                                                               \
+        static bool configured = false;                                                                                \
+        if (!configured) {      /* one lane per chunk needs more than the 48 KB default */                             \
+            cudaFuncSetAttribute(range_decode_kernel<NS, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
+            configured = true;                                                                                         \
+        }                                                                                                              \
+        range_decode_kernel<NS, V><<<grid, 32, smem, s>>>(blob, offs, lay_off, g, sym, sym_layer_stride, error);       \
+    } while (0)
+#define WRB_DEC_VARIANTS(NS)                                                                   \
+    switch (variant) {                                                                         \
+    case 0: WRB_DEC_LAUNCH(NS, 0); break; case 1: WRB_DEC_LAUNCH(NS, 1); break;                \
+    case 2: WRB_DEC_LAUNCH(NS, 2); break; default: WRB_DEC_LAUNCH(NS, 3); break;               \
     }
     switch (nsub) {
-    case 1: range_decode_kernel<1><<<grid, 32, smem, s>>>(blob, offs, lay_off, g, sym, sym_layer_stride, error); break;
-    case 2: range_decode_kernel<2><<<grid, 32, smem, s>>>(blob, offs, lay_off, g, sym, sym_layer_stride, error); break;
-    case 4: range_decode_kernel<4><<<grid, 32, smem, s>>>(blob, offs, lay_off, g, sym, sym_layer_stride, error); break;
-    default: range_decode_kernel<8><<<grid, 32, smem, s>>>(blob, offs, lay_off, g, sym, sym_layer_stride, error); break;
+    case 1: WRB_DEC_VARIANTS(1); break;
+    case 2: WRB_DEC_VARIANTS(2); break;
+    case 4: WRB_DEC_VARIANTS(4); break;
+    default: WRB_DEC_VARIANTS(8); break;
     }
+#undef WRB_DEC_VARIANTS
+#undef WRB_DEC_LAUNCH
     note_launch(1);
 }
 

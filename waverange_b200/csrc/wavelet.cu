@@ -12,6 +12,7 @@
 // Data flow per level (see codec.cu): x-pass src->A, y-pass A->B, z-pass B->{coefficients,lll};
 // the z-pass routes the low-low-low octant to a compact scratch (input of the next level) and
 // every final coefficient to the coefficient array, reducing their min/max on the way.
+#include <cstdlib>
 #include "wr_common.cuh"
 #include "wr_kernels.h"
 #include "wavelet_pairs.cuh"
@@ -406,6 +407,25 @@ void wavelet_inverse(double* coef, double* tmp, double* lllA, double* lllB, void
         if (out_is_f32) narrow_copy_kernel<float><<<blocks, 256, 0, s>>>(coef, (float*)out, n);
         else narrow_copy_kernel<double><<<blocks, 256, 0, s>>>(coef, (double*)out, n);
         note_launch(1);
+        return;
+    }
+    // one fused kernel per level when every level's box is even and >= 8 (and the symbols, if given, are flat)
+    bool fused = getenv("WRB_NO_FUSED_INVERSE") == nullptr && (long long)nx * ny < (1ll << 31) &&
+                 (sym == nullptr || pitch == chunk_len);
+    for (int k = 0; k < levels && fused; k++)
+        fused = fused_inverse_supported(ceil_shift(nx, k), ceil_shift(ny, k), ceil_shift(nz, k));
+    if (fused) {
+        const double* prev = nullptr;
+        for (int k = levels - 1; k >= 0; k--) {
+            const int n0 = ceil_shift(nx, k), n1 = ceil_shift(ny, k), n2 = ceil_shift(nz, k);
+            if (k == 0) {
+                fused_inverse_level(coef, ay, az, sym, layer_stride, nlay, deps, minval, prev, out, out_is_f32, ay, az, n0, n1, n2, s);
+            } else {
+                double* nxt = (k & 1) ? lllA : lllB;
+                fused_inverse_level(coef, ay, az, sym, layer_stride, nlay, deps, minval, prev, nxt, 0, n0, (long long)n0 * n1, n0, n1, n2, s);
+                prev = nxt;
+            }
+        }
         return;
     }
     const double* lll = nullptr; long long lsy = 0, lsz = 0;

@@ -46,6 +46,13 @@ void fused_forward_level(const void* src, int src_is_f32, long long ssy, long lo
                          unsigned long long* in_max, unsigned long long* out_min, unsigned long long* out_max,
                          cudaStream_t s, int zoff = 0, int pair_lo = 0, int nl = -1);
 
+// ---- wavelet_inv_fused.cu -----------------------------------------------------------------
+bool fused_inverse_supported(int n0, int n1, int n2);
+// sym != null: coefficients are rebuilt from the FLAT symbol planes (layer l at sym + l*lstride); else read from coef
+void fused_inverse_level(const double* coef, long long ay, long long az, const uint8_t* sym, unsigned long long lstride,
+                         int nlay, const double* deps, const double* minval, const double* lll, void* dst,
+                         int dst_is_f32, long long dsy, long long dsz, int n0, int n1, int n2, cudaStream_t s);
+
 // ---- quant.cu -----------------------------------------------------------------------------
 // Geometry of the chunked symbol container of one layer.
 //   chunk c covers symbols [c*chunk_len, min(ntot,(c+1)*chunk_len)); each chunk is cut into coder
