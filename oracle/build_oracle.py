@@ -13,6 +13,8 @@
                                  has; keeps gcc's default FMA contraction, which is
                                  the property of the stock build that matters
                                  (SURVEY.md section 8c).  Used as the CPU timing baseline.
+     wrenc_ref, wrdec_ref        the reference's generic front-ends (strict flags), used by the
+                                 .wrh/.wrb file-format parity tests
    The reference's own Makefiles are not run: three C/C++ files are compiled
    directly (src/core/Makefile:6-23 lists the same three objects).
 """
@@ -77,6 +79,23 @@ def build_ref(force=False):
         run(["g++", "-shared", "-o", out] + objs)
         for o in objs:
             os.remove(o)
+    # the reference's generic front-ends (strict flags), for the file-format parity tests:
+    # src/generic/gen_enc.cpp | gen_dec.cpp + gen_aux.cpp + the three library sources (Makefile:22-25)
+    gen = os.path.join(src, "generic")
+    strict = ["-O2", "-ffp-contract=off", "-w"]
+    for exe, main in (("wrenc_ref", "gen_enc.cpp"), ("wrdec_ref", "gen_dec.cpp")):
+        out = os.path.join(outdir, exe)
+        srcs = [os.path.join(gen, main), os.path.join(gen, "gen_aux.cpp"), wrap]
+        if force or newer(out, srcs + [wav, rc, __file__]):
+            cobjs = []
+            for s in (wav, rc):
+                o = os.path.join(outdir, "%s_cli.o" % os.path.basename(s)[:-2])
+                run(["gcc", "-c"] + strict + ["-o", o, s])
+                cobjs.append(o)
+            run(["g++"] + strict + ["-D__STDC_LIMIT_MACROS", "-o", out] + srcs + cobjs)
+            for o in cobjs:
+                os.remove(o)
+        outs[exe] = out
     return outs
 
 

@@ -37,6 +37,17 @@ class Header(C.Structure):
                     minval_vec=list(self.minval_vec)[:n], len_enc_vec=list(self.len_enc_vec)[:n])
 
 
+class FieldDesc(C.Structure):
+    """wrb_field_desc (include/waverange_files.h): per-field parameters of the generic front-end."""
+    _fields_ = [("nbytes", C.c_int), ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("nh", C.c_int),
+                ("idinv", C.c_int), ("icomp", C.c_int), ("tol_base", C.c_double)]
+
+
+class FieldRecord(C.Structure):
+    """wrb_field_record: one field record of a .wrh header file."""
+    _fields_ = [("desc", FieldDesc), ("recl", C.c_ubyte * 8), ("hdr", Header)]
+
+
 class WaveRangeError(RuntimeError):
     pass
 
@@ -54,6 +65,7 @@ EXPORTS = ["wrb_create", "wrb_destroy", "wrb_last_error", "wrb_set_stream", "wrb
            "wrb_encode_host", "wrb_decode_host", "wrb_set_slab", "wrb_encode_slab_device", "wrb_decode_slab_device", "wrb_quantise_slab_device", "wrb_wavelet3d_device", "wrb_quantise_device",
            "wrb_range_encode_device", "wrb_range_decode_device", "wrb_ind_p2w_3d", "wrb_set_timing",
            "wrb_last_stage_ms",
+           "wrb_wrh_begin", "wrb_wrh_append", "wrb_wrh_read", "wrb_file_encode", "wrb_file_decode", "wrb_file_last_error",
            "encoding_wrap", "decoding_wrap", "setup_wr", "encoding_wrap_f", "decoding_wrap_f", "setup_wr_f"]
 
 
@@ -96,6 +108,14 @@ def lib():
     L.wrb_ind_p2w_3d.restype = None
     L.wrb_set_timing.argtypes = [vp, i]
     L.wrb_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    cp = C.c_char_p
+    L.wrb_wrh_begin.argtypes = [cp, cp, i, i, i]
+    L.wrb_wrh_append.argtypes = [cp, i, C.POINTER(FieldRecord)]
+    L.wrb_wrh_read.argtypes = [cp, C.POINTER(i), C.POINTER(FieldRecord), i]
+    L.wrb_file_encode.argtypes = [vp, cp, cp, cp, i, i, i, C.POINTER(FieldDesc), C.POINTER(d)]
+    L.wrb_file_decode.argtypes = [vp, cp, cp, cp, i, i]
+    L.wrb_file_last_error.argtypes = []
+    L.wrb_file_last_error.restype = cp
     f64p, u8p, ulp = C.POINTER(d), C.POINTER(C.c_ubyte), C.POINTER(ul)
     L.encoding_wrap.argtypes = [i, i, i, f64p, i, i, i, i, f64p, f64p, f64p, f64p, u8p, u8p, ulp, f64p, f64p, ulp, u8p]
     L.encoding_wrap.restype = None
@@ -116,6 +136,28 @@ def setup_wr(nx, ny, nz):
 
 def _np_ptr(a, t):
     return a.ctypes.data_as(C.POINTER(t))
+
+
+# ---- generic .wrh / .wrb files (include/waverange_files.h) -------------------------------------
+def _fck(rc):
+    if rc != 0:
+        raise WaveRangeError("%s (code %d)" % (lib().wrb_file_last_error().decode(), rc))
+
+
+def wrh_read(path):
+    """all field records of a .wrh header file (reference gen_aux.cpp:554-644)"""
+    n = C.c_int()
+    _fck(lib().wrb_wrh_read(path.encode(), C.byref(n), None, 0))
+    recs = (FieldRecord * max(1, n.value))()
+    _fck(lib().wrb_wrh_read(path.encode(), C.byref(n), recs, n.value))
+    return list(recs)[:n.value]
+
+
+def wrh_write(path, encoded_name, filetype, endianflip, records):
+    """preamble + one record per field (reference gen_enc.cpp:508-519, gen_aux.cpp:505-551)"""
+    _fck(lib().wrb_wrh_begin(path.encode(), encoded_name.encode(), filetype, endianflip, len(records)))
+    for k, r in enumerate(records):
+        _fck(lib().wrb_wrh_append(path.encode(), k, C.byref(r)))
 
 
 def encoding_wrap(fld, tol, wtflag=1):
@@ -215,6 +257,19 @@ class Codec:
     def _ck(self, rc):
         if rc != 0:
             raise WaveRangeError("%s (code %d)" % (self.L.wrb_last_error(self.h).decode(), rc))
+
+    def file_encode(self, in_name, encoded_name, header_name, filetype, endianflip, fields, cutoff_all=None):
+        """wrenc (reference gen_enc.cpp): fields = list of FieldDesc; cutoff_all: one tolerance for every field
+        (the reference front-end's behaviour, see include/waverange_files.h)"""
+        arr = (FieldDesc * max(1, len(fields)))(*fields)
+        cut = C.byref(C.c_double(cutoff_all)) if cutoff_all is not None else None
+        _fck(self.L.wrb_file_encode(self.h, in_name.encode(), encoded_name.encode(), header_name.encode(), filetype,
+                                    endianflip, len(fields), arr, cut))
+
+    def file_decode(self, encoded_name, header_name, out_name, filetype, endianflip):
+        """wrdec (reference gen_dec.cpp)"""
+        _fck(self.L.wrb_file_decode(self.h, encoded_name.encode(), header_name.encode(), out_name.encode(), filetype,
+                                    endianflip))
 
     def set_stream(self, stream_handle):
         self._ck(self.L.wrb_set_stream(self.h, C.c_void_p(stream_handle)))

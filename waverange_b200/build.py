@@ -13,8 +13,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwaverange_b200.so")
-SOURCES = ["codec.cu", "wavelet.cu", "wavelet_fused.cu", "wavelet_inv_fused.cu", "wavelet_slab.cu", "quant.cu", "rangecoder.cu", "compat.cpp"]
-HEADERS = ["wr_common.cuh", "wr_kernels.h", "wavelet_pairs.cuh", "../../include/waverange_b200.h", "../../include/waverange.h"]
+SOURCES = ["codec.cu", "wavelet.cu", "wavelet_fused.cu", "wavelet_inv_fused.cu", "wavelet_slab.cu", "quant.cu", "rangecoder.cu", "compat.cpp", "wrfile.cpp"]
+HEADERS = ["wr_common.cuh", "wr_kernels.h", "wavelet_pairs.cuh", "../../include/waverange_b200.h", "../../include/waverange.h",
+           "../../include/waverange_files.h", "cli/wrenc.cpp", "cli/wrdec.cpp"]
+BIN = os.path.join(HERE, "bin")
+CLI = ["wrenc", "wrdec"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -64,6 +67,11 @@ def build(force=False, verbose=False):
     subprocess.check_call(cmd)
     for o in objs:
         os.remove(o)
+    # the generic front-ends (reference bin/generic/wrenc, wrdec): thin mains over wrb_file_encode / wrb_file_decode
+    os.makedirs(BIN, exist_ok=True)
+    for name in CLI:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", os.path.join(BIN, name), os.path.join(CSRC, "cli", name + ".cpp"),
+                               "-L" + HERE, "-lwaverange_b200", "-Wl,-rpath,$ORIGIN/.."])
     return LIB
 
 
