@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from tests.util import bits_equal  # noqa: E402
+from util import bits_equal  # noqa: E402
 
 L1 = 59999
 F64, F32 = 0, 1
