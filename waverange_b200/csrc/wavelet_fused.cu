@@ -222,6 +222,9 @@ void fused_forward_level(const void* src, int src_is_f32, long long ssy, long lo
     // z-segments: enough CTAs to fill the machine (148 SMs x 2 resident), but segments of >= 16 pairs
     int zp = m2;
     while (zp > 16 && (long long)gx * gy * ((m2 + zp - 1) / zp) < 148 * 4) zp = (zp + 1) / 2;
+    // coarse levels have too few tiles to occupy the machine: there the serial depth per CTA is what counts, so cut
+    // further (the restart overhead of 4 pairs per segment is irrelevant at that size)
+    while (zp > 4 && (long long)gx * gy * ((m2 + zp - 1) / zp) < 148) zp = (zp + 1) / 2;
     a.zpairs = zp;
     dim3 grid(gx, gy, (m2 + zp - 1) / zp);
     const bool track = in_min != nullptr;

@@ -249,6 +249,9 @@ void fused_inverse_level(const double* coef, long long ay, long long az, const u
     const int gx = (q0 + IPX - 1) / IPX, gy = (q1 + IPY - 1) / IPY;
     int zp = q2;                               // z-segments: a few CTAs per SM (one resident at a time), segments of >= 16 pairs
     while (zp > 16 && (long long)gx * gy * ((q2 + zp - 1) / zp) < 148 * 3) zp = (zp + 1) / 2;
+    // coarse levels have too few tiles to occupy the machine: there the serial depth per CTA is what counts, so cut
+    // further (the restart overhead of 4 pairs per segment is irrelevant at that size)
+    while (zp > 4 && (long long)gx * gy * ((q2 + zp - 1) / zp) < 148) zp = (zp + 1) / 2;
     a.zpairs = zp;
     dim3 grid(gx, gy, (q2 + zp - 1) / zp);
 #define WRB_INV_LAUNCH(NL)                                                                          \
