@@ -254,3 +254,16 @@ def test_corrupt_container_is_rejected(codec, torch_cuda, oracle):
     rec = torch_cuda.zeros(f.size, dtype=torch_cuda.float64, device="cuda")
     with pytest.raises(api.WaveRangeError):
         codec.decode_device(rec.data_ptr(), F64, 32, 32, 32, h, out.data_ptr())
+
+
+def test_layer_count_guess_falls_back_to_all_layers(codec, torch_cuda, oracle, monkeypatch):
+    """the encoder launches only as many layers as the tolerance can need (codec.cu layer_guess); when the guess is
+    too small the `done` flag of the device state is clear and the call repeats with all eight: same bytes"""
+    f = oracle.probe_field((48, 40, 56), seed=11, nm=12)
+    tol = 1e-9
+    h0, out0 = encode_dev(codec, torch_cuda, f, tol)
+    assert h0.nlay >= 4
+    monkeypatch.setenv("WRB_LAYER_GUESS", "2")
+    h1, out1 = encode_dev(codec, torch_cuda, f, tol)
+    assert h1.nlay == h0.nlay and h1.ntot_enc == h0.ntot_enc
+    assert torch_cuda.equal(out0[:h0.ntot_enc], out1[:h1.ntot_enc])

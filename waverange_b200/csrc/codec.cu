@@ -282,8 +282,25 @@ static int reduce_extrema(wrb_codec* c, unsigned long long* kmin, unsigned long 
     return 0;
 }
 
+// How many layers to launch.  The layer loop ends on the device (layer l is the last one when its natural step
+// deps_l falls below tolabs, wrappers.cpp:326-333) and the host does not wait for that, so it used to launch all 8
+// layers, 3 to 5 of them no-ops costing ~11 us each at 512^3.  The count is bounded, though: the residual of a
+// layer lies within half a step, so deps_{l+1} <= deps_l / 255, and deps_0 = (coefficient span) / 255 with the
+// span at most G times the field's; tolabs >= tol * span / 3.5.  Layer l therefore ends the loop as soon as
+// 255^(l+1) > 3.5 G / tol.  G = 1024 is generous for four levels of the 9/7 transform but NOT proven: the caller
+// checks the `done` flag that comes back with the header and repeats the call with all 8 layers if it is clear.
+static int layer_guess(double tolrel)
+{
+    if (!(tolrel > 0)) return kNLayMax;
+    const double need = 3.5 * 1024.0 / tolrel;
+    double p = 255.0;
+    int n = 1;
+    while (p <= need && n < kNLayMax) { p *= 255.0; n++; }
+    return n;
+}
+
 static int run_transform_and_quantise(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag,
-                                      double tolrel, const ChunkGeom& g, const SlabGeom* sg = nullptr)
+                                      double tolrel, const ChunkGeom& g, const SlabGeom* sg = nullptr, int nlayers = kNLayMax)
 {
     DevState* st = (DevState*)c->state.p;
     cudaStream_t s = c->stream;
@@ -304,7 +321,7 @@ static int run_transform_and_quantise(wrb_codec* c, const void* d_field, int dty
     const unsigned long long lstride = (unsigned long long)g.nchunks * g.pitch;
     const unsigned long long hstride = (unsigned long long)g.nblocks * 256;
     CK(cudaMemsetAsync(c->hist.p, 0, (size_t)kNLayMax * hstride * 4, s));     // the quantiser adds partial histograms
-    for (int l = 0; l < kNLayMax; l++) {
+    for (int l = 0; l < nlayers; l++) {
         // global extrema of the coefficients (l == 0) / of the residual left by layer l-1 (wrappers.cpp:308-314)
         if (dist && reduce_extrema(c, &st->rmin_key[l], &st->rmax_key[l])) return fail(c, WRB_E_CUDA, "reduce callback failed");
         layer_params(st, l, s);
@@ -321,8 +338,13 @@ extern "C" {
 }  // extern "C"
 
 static int encode_impl(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag, double tolrel,
-                       wrb_header* hdr, unsigned char* d_data_enc, unsigned long cap, const SlabGeom* sg)
+                       wrb_header* hdr, unsigned char* d_data_enc, unsigned long cap, const SlabGeom* sg, int nlayers = 0)
 {
+    if (nlayers <= 0) {
+        const char* e = getenv("WRB_LAYER_GUESS");            // tests: force a (wrong) guess to exercise the repeat below
+        nlayers = (e && *e) ? atoi(e) : layer_guess(tolrel);
+        if (nlayers < 1 || nlayers > kNLayMax) nlayers = kNLayMax;
+    }
     if (!c || !d_field || !hdr || !d_data_enc || nx < 1 || ny < 1 || nz < 1 || (dtype != WRB_F64 && dtype != WRB_F32))
         return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
     CK(cudaSetDevice(c->device));
@@ -334,11 +356,11 @@ static int encode_impl(wrb_codec* c, const void* d_field, int dtype, int nx, int
     if ((rc = ensure_coder_buffers(c, g, kNLayMax, true))) return rc;
     DevState* st = (DevState*)c->state.p;
     cudaStream_t s = c->stream;
-    if ((rc = run_transform_and_quantise(c, d_field, dtype, nx, ny, nz, wtflag, tolrel, g, sg))) return rc;
+    if ((rc = run_transform_and_quantise(c, d_field, dtype, nx, ny, nz, wtflag, tolrel, g, sg, nlayers))) return rc;
     const unsigned long long lstride = (unsigned long long)g.nchunks * g.pitch;
     const unsigned long long hstride = (unsigned long long)g.nblocks * 256;
     const unsigned long long sp = chunk_slot_pitch(g);
-    range_encode_chunks((const uint8_t*)c->sym.p, lstride, (const uint32_t*)c->hist.p, hstride, g, kNLayMax, st->active,
+    range_encode_chunks((const uint8_t*)c->sym.p, lstride, (const uint32_t*)c->hist.p, hstride, g, nlayers, st->active,
                         (uint8_t*)c->slots.p, sp, (unsigned long long*)c->lens.p, (uint32_t*)c->seek.p, s);
     if (c->timing) cudaEventRecord(c->ev[3], s);
     assemble_container((const uint8_t*)c->slots.p, sp, (const unsigned long long*)c->lens.p, (const uint32_t*)c->seek.p, g,
@@ -348,6 +370,8 @@ static int encode_impl(wrb_codec* c, const void* d_field, int dtype, int nx, int
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     if (c->timing) for (int i = 0; i < 4; i++) cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]);
+    if (!c->h_state->trivial && !c->h_state->done && nlayers < kNLayMax)       // the layer bound did not hold: all 8
+        return encode_impl(c, d_field, dtype, nx, ny, nz, wtflag, tolrel, hdr, d_data_enc, cap, sg, kNLayMax);
     header_from_state(*c->h_state, wtflag, hdr);
     if (c->h_state->error) return fail(c, WRB_E_OVERFLOW, "encoded data does not fit in data_enc");
     return 0;
