@@ -209,8 +209,9 @@ __global__ void __launch_bounds__(ITHREADS, 1) inv_level_fused_kernel(FusedInvAr
                 if (a.vec_ok && xp + IR <= q0) {
                     if (sizeof(TOUT) == 4) {
                         float4* o4 = reinterpret_cast<float4*>(o);
-                        o4[0] = make_float4((float)ev[0], (float)od[0], (float)ev[1], (float)od[1]);
-                        o4[1] = make_float4((float)ev[2], (float)od[2], (float)ev[3], (float)od[3]);
+#pragma unroll
+                        for (int j = 0; j < IR / 2; j++)
+                            o4[j] = make_float4((float)ev[2 * j], (float)od[2 * j], (float)ev[2 * j + 1], (float)od[2 * j + 1]);
                     } else {
                         double2* o2 = reinterpret_cast<double2*>(o);
 #pragma unroll
@@ -248,7 +249,7 @@ void fused_inverse_level(const double* coef, long long ay, long long az, const u
     const int q0 = n0 / 2, q1 = n1 / 2, q2 = n2 / 2;
     const int gx = (q0 + IPX - 1) / IPX, gy = (q1 + IPY - 1) / IPY;
     int zp = q2;                               // z-segments: a few CTAs per SM (one resident at a time), segments of >= 16 pairs
-    while (zp > 16 && (long long)gx * gy * ((q2 + zp - 1) / zp) < 148 * 3) zp = (zp + 1) / 2;
+    while (zp > 16 && (long long)gx * gy * ((q2 + zp - 1) / zp) < 148 * 4) zp = (zp + 1) / 2;
     // coarse levels have too few tiles to occupy the machine: there the serial depth per CTA is what counts, so cut
     // further (the restart overhead of 4 pairs per segment is irrelevant at that size)
     while (zp > 4 && (long long)gx * gy * ((q2 + zp - 1) / zp) < 148) zp = (zp + 1) / 2;
