@@ -219,11 +219,11 @@ void fused_forward_level(const void* src, int src_is_f32, long long ssy, long lo
     a.in_min = in_min; a.in_max = in_max; a.out_min = out_min; a.out_max = out_max;
     const int m0 = n0 / 2, m1 = n1 / 2, m2 = a.nl;
     const int gx = (m0 + FPX - 1) / FPX, gy = (m1 + FPY - 1) / FPY;
-    // z-segments: enough CTAs to fill the machine (148 SMs x 2 resident), but segments of >= 16 pairs
+    // z-segments: enough CTAs to fill the machine (148 SMs x 2 resident), but segments of >= 16 pairs (two CTAs share
+    // an SM, so the restart overhead of short segments costs throughput: the wave model of pick_zpairs measured worse)
     int zp = m2;
     while (zp > 16 && (long long)gx * gy * ((m2 + zp - 1) / zp) < 148 * 4) zp = (zp + 1) / 2;
-    // coarse levels have too few tiles to occupy the machine: there the serial depth per CTA is what counts, so cut
-    // further (the restart overhead of 4 pairs per segment is irrelevant at that size)
+    // coarse levels have too few tiles to occupy the machine: there the serial depth per CTA is what counts
     while (zp > 4 && (long long)gx * gy * ((m2 + zp - 1) / zp) < 148) zp = (zp + 1) / 2;
     a.zpairs = zp;
     dim3 grid(gx, gy, (m2 + zp - 1) / zp);

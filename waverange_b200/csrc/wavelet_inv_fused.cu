@@ -248,11 +248,8 @@ void fused_inverse_level(const double* coef, long long ay, long long az, const u
     a.vec_ok = ((reinterpret_cast<size_t>(dst) % 16) == 0 && (dsy * esz) % 16 == 0 && (dsz * esz) % 16 == 0) ? 1 : 0;
     const int q0 = n0 / 2, q1 = n1 / 2, q2 = n2 / 2;
     const int gx = (q0 + IPX - 1) / IPX, gy = (q1 + IPY - 1) / IPY;
-    int zp = q2;                               // z-segments: a few CTAs per SM (one resident at a time), segments of >= 16 pairs
-    while (zp > 16 && (long long)gx * gy * ((q2 + zp - 1) / zp) < 148 * 4) zp = (zp + 1) / 2;
-    // coarse levels have too few tiles to occupy the machine: there the serial depth per CTA is what counts, so cut
-    // further (the restart overhead of 4 pairs per segment is irrelevant at that size)
-    while (zp > 4 && (long long)gx * gy * ((q2 + zp - 1) / zp) < 148) zp = (zp + 1) / 2;
+    // z-segments: shortest critical path for one resident CTA per SM (512^3 level 1: 4 segments, 7 waves)
+    const int zp = pick_zpairs((long long)gx * gy, q2, 148, 4, 4);
     a.zpairs = zp;
     dim3 grid(gx, gy, (q2 + zp - 1) / zp);
 #define WRB_INV_LAUNCH(NL)                                                                          \

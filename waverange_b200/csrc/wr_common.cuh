@@ -111,4 +111,22 @@ __device__ inline void block_minmax_commit(unsigned long long kmin, unsigned lon
 
 struct Strides { long long y, z; };   // x stride is always 1
 
+// z-segment length (in output pairs) of the one-pass-per-level kernels.  A CTA restarts its z pipeline `lead`
+// pairs before its segment, and CTAs run in waves of `slots` (resident CTAs on the machine): pick the segment
+// count that minimises  waves * (segment + lead),  i.e. the length of the critical path in plane pairs.
+inline int pick_zpairs(long long tiles, int m2, int slots, int lead, int min_zp)
+{
+    int best = m2;
+    long long best_cost = -1;
+    for (int nseg = 1; nseg <= m2; nseg++) {
+        const int zp = (m2 + nseg - 1) / nseg;
+        if (zp < min_zp && nseg > 1) break;
+        const long long ctas = tiles * ((m2 + zp - 1) / zp);
+        const long long waves = (ctas + slots - 1) / slots;
+        const long long cost = waves * (zp + lead);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = zp; }
+    }
+    return best;
+}
+
 }  // namespace wrb
