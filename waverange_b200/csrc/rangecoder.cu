@@ -24,6 +24,7 @@
 //    X = W - 2*low (mod 2^32), X being the decoder's (low << 1 | last bit read), so several lanes
 //    decode one chunk concurrently.  The chunk stream itself is unchanged.
 #include <cstdlib>
+#include <type_traits>
 #include "wr_common.cuh"
 #include "wr_kernels.h"
 
@@ -416,6 +417,19 @@ __device__ __forceinline__ uint32_t div_small_quot(uint32_t a, uint32_t b)
     uint32_t q = __float2uint_rz(__fmul_rz(__uint2float_rz(a), rb));              // q_true - 1 <= q <= q_true
     return q + ((a - q * b >= b) ? 1u : 0u);
 }
+// The same for b < 2^24 and a / b < 2^23 (the symbol loop: b = range / tot <= 2^31 / 256 for blocks of >= 256
+// symbols, quotient < tot < 2^16): b converts exactly, so the round-up conversion (a slow-pipe instruction) is not
+// needed, and floor() of the estimate is taken with the 2^23 trick (add with round-towards-zero leaves the integer
+// part in the mantissa) instead of a float-to-int conversion -- two slow-pipe instructions fewer on the chain.
+__device__ __forceinline__ uint32_t div_small_quot_fast(uint32_t a, uint32_t b)
+{
+    float rb;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(__uint2float_rz(b)));      // exact operand, result <= 1 ulp off
+    rb = __int_as_float(__float_as_int(rb) - 2);                                  // now <= 1 / b
+    const float est = __fmul_rz(__uint2float_rz(a), rb);                          // <= a / b
+    const uint32_t q = __float_as_uint(__fadd_rz(est, 8388608.0f)) & 0x7FFFFFu;   // floor(est); q_true - 1 <= q <= q_true
+    return q + ((a - q * b >= b) ? 1u : 0u);
+}
 
 // Decoder state in "X form": X = (low << 1) | (lowest bit of the last byte read), i.e. the last four
 // stream bytes read minus twice the coder's cumulative low; a renormalisation step (rangecod.c:293-300)
@@ -562,6 +576,10 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
         uint8_t* const ostart = op;
         uint8_t* const oend = outb + n + s1;
         uint32_t pack = 0;
+        // two copies of the loop (a generic lambda instantiated for both values): the fast division needs
+        // help < 2^24 in every lane, decided once per block
+        auto symbol_loop = [&](auto fast_tag) {
+        constexpr bool kFastDiv = decltype(fast_tag)::value;
 #pragma unroll 1
         for (; op != oend; op++) {
             const uint32_t win = __byte_perm(w0, w1, sel);
@@ -587,7 +605,7 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
             a = an;
             sel = 0x0123u + 0x1111u * (a & 3u);
             help = div_magic(range, mg);          // decode_culfreq(rc, bs)
-            uint32_t cf = div_small_quot(X >> 1, help);
+            uint32_t cf = kFastDiv ? div_small_quot_fast(X >> 1, help) : div_small_quot(X >> 1, help);
             cf = min(cf, bs - 1);
             uint32_t s = ll[(cf >> kLutShift) * CPW];
             uint32_t e0, e1;                      // both probes issued together
@@ -619,6 +637,8 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
                 *op = (uint8_t)s;
             }
         }
+        };
+        if (__all_sync(__activemask(), bs >= 256u)) symbol_loop(std::true_type{}); else symbol_loop(std::false_type{});
         if (kPack) {                              // ragged tail (and head, when the run ends inside its first word)
             uint8_t* q = reinterpret_cast<uint8_t*>((unsigned long long)oend & ~3ull);
             if (q < ostart) q = ostart;
