@@ -71,6 +71,13 @@ int wrb_set_chunk_blocks(wrb_codec* c, int blocks);
  * n interior symbol positions of every single-block chunk, 12 bytes each, in the container's
  * seek table; the decoder then runs n+1 lanes per chunk.  Chunk streams are unaffected. */
 int wrb_set_seek_points(wrb_codec* c, int n);
+/* Local (spatially varying) cutoff: the mx*my*mz > 1 branch of encoding_wrap() (reference wrappers.cpp:343-379,
+ * lcl_prec :55-64).  cutoffvec holds mx*my*mz relative tolerances, x fastest.  While set, wrb_encode_* ignore their
+ * tolrel argument: tolabs comes from the minimum of cutoffvec (:292-299) and every layer codes symbol 0 where its
+ * residual span is below the point's precision -- exactly what the reference does, including the fact that its
+ * ind_p2w_3d() reports the full level for every point, so the per-point precision only takes effect with
+ * wtflag == 0.  mx*my*mz <= 1 or cutoffvec == NULL switches it off.  Not available in z-slab mode. */
+int wrb_set_local_cutoff(wrb_codec* c, int mx, int my, int mz, const double* cutoffvec);
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 unsigned long long wrb_launch_count(const wrb_codec* c);
 /* Release cached device scratch (it is otherwise kept and grown on demand). */

@@ -67,6 +67,9 @@ class Restatement:
         L.wro_range_decode.restype = C.c_size_t
         L.wro_range_decode.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t]
         L.wro_encode.restype = C.c_int
+        L.wro_encode_cutoff.restype = C.c_int
+        L.wro_encode_cutoff.argtypes = [C.c_int, C.c_int, C.c_int, f64p, C.c_int, C.c_int, C.c_int, C.c_int, f64p,
+                                        C.c_uint64, C.POINTER(Header), u8p, C.c_uint64, u8p, u32p]
         L.wro_encode.argtypes = [C.c_int, C.c_int, C.c_int, f64p, C.c_int, C.c_double, C.c_uint64,
                                  C.POINTER(Header), u8p, C.c_uint64, u8p, u32p]
         L.wro_decode.restype = C.c_int
@@ -99,8 +102,9 @@ class Restatement:
         return sym[:min(n, cap)].copy(), n
 
     # -- whole path ------------------------------------------------------
-    def encode(self, fld, tol, wtflag=1, chunk_len=0, want_symbols=False):
-        """fld: float64 (nz,ny,nx).  Returns dict(header, data, symbols, chunk_lens, residual)."""
+    def encode(self, fld, tol, wtflag=1, chunk_len=0, want_symbols=False, cutoff=None):
+        """fld: float64 (nz,ny,nx).  Returns dict(header, data, symbols, chunk_lens, residual).
+        cutoff = (mx, my, mz, values): the local-precision grid of encoding_wrap (tol is then ignored)."""
         a = np.ascontiguousarray(fld, dtype=np.float64).copy()
         nz, ny, nx = a.shape
         ntot = a.size
@@ -110,8 +114,16 @@ class Restatement:
         sym = np.empty(NLAYMAX * ntot, dtype=np.uint8) if want_symbols else None
         nch = (ntot + chunk_len - 1) // chunk_len if chunk_len else 1
         cl = np.zeros(NLAYMAX * nch, dtype=np.uint32)
-        rc = self.lib.wro_encode(nx, ny, nz, _p(a, f64p), wtflag, tol, chunk_len, C.byref(hdr),
-                                 _p(data, u8p), cap, _p(sym, u8p) if want_symbols else None, _p(cl, u32p))
+        if cutoff is None:
+            rc = self.lib.wro_encode(nx, ny, nz, _p(a, f64p), wtflag, tol, chunk_len, C.byref(hdr),
+                                     _p(data, u8p), cap, _p(sym, u8p) if want_symbols else None, _p(cl, u32p))
+        else:
+            cmx, cmy, cmz, vals = cutoff
+            cv = np.ascontiguousarray(vals, dtype=np.float64)
+            assert cv.size == cmx * cmy * cmz
+            rc = self.lib.wro_encode_cutoff(nx, ny, nz, _p(a, f64p), wtflag, cmx, cmy, cmz, _p(cv, f64p), chunk_len,
+                                            C.byref(hdr), _p(data, u8p), cap, _p(sym, u8p) if want_symbols else None,
+                                            _p(cl, u32p))
         if rc != 0:
             raise RuntimeError("oracle encode overflow")
         nlay = hdr.nlay
@@ -194,7 +206,7 @@ class Reference:
         self.lib.ref_range_decode(_p(buf, u8p), len(stream) + 8, _p(sym, u8p), nsym)
         return sym[:nsym].copy()
 
-    def encode(self, fld, tol, wtflag=1):
+    def encode(self, fld, tol, wtflag=1, cutoff=None):
         a = np.ascontiguousarray(fld, dtype=np.float64).copy()
         nz, ny, nx = a.shape
         ntot = a.size
@@ -203,6 +215,10 @@ class Reference:
         self.lib.setup_wr(nx, ny, nz, C.byref(nlaymax), C.byref(cap))
         data = np.zeros(cap.value + 16, dtype=np.uint8)
         cut = np.array([tol], dtype=np.float64)
+        cmx = cmy = cmz = 1
+        if cutoff is not None:
+            cmx, cmy, cmz, vals = cutoff
+            cut = np.ascontiguousarray(vals, dtype=np.float64)
         tolabs, mid, half = C.c_double(), C.c_double(), C.c_double()
         wlev, nlay = C.c_uint8(), C.c_uint8()
         ntot_enc = C.c_ulong()
@@ -210,7 +226,7 @@ class Reference:
         minv = np.zeros(NLAYMAX)
         lens = (C.c_ulong * NLAYMAX)()
         with quiet_stdout():
-            self.lib.encoding_wrap(nx, ny, nz, _p(a, f64p), wtflag, 1, 1, 1, _p(cut, f64p),
+            self.lib.encoding_wrap(nx, ny, nz, _p(a, f64p), wtflag, cmx, cmy, cmz, _p(cut, f64p),
                                    C.cast(C.byref(tolabs), f64p), C.cast(C.byref(mid), f64p),
                                    C.cast(C.byref(half), f64p), C.cast(C.byref(wlev), u8p),
                                    C.cast(C.byref(nlay), u8p), C.byref(ntot_enc), _p(deps, f64p), _p(minv, f64p),

@@ -1,6 +1,8 @@
 """GPU parity tests: every stage of the CUDA path, called through the C ABI, against the oracle
 (oracle/wr_oracle.c, pinned to the reference) and the golden vectors.  Bit-exact everywhere:
 wavelet coefficients (0 ULP), header doubles, symbols, chunk bytes, reconstructed field."""
+import os
+
 import numpy as np
 import pytest
 
@@ -267,3 +269,37 @@ def test_layer_count_guess_falls_back_to_all_layers(codec, torch_cuda, oracle, m
     h1, out1 = encode_dev(codec, torch_cuda, f, tol)
     assert h1.nlay == h0.nlay and h1.ntot_enc == h0.ntot_enc
     assert torch_cuda.equal(out0[:h0.ntot_enc], out1[:h1.ntot_enc])
+
+
+@pytest.mark.parametrize("wt", [0, 1])
+@pytest.mark.parametrize("shape,grid", [((12, 10, 14), (2, 2, 2)), ((40, 33, 50), (3, 2, 4)), ((70, 64, 64), (1, 1, 5))])
+def test_local_cutoff_branch(product_lib, codec, torch_cuda, oracle, wt, shape, grid):
+    """encoding_wrap(mx*my*mz > 1): the drop-in entry point, stock layout, against the oracle's bytes; and the chunked
+    layout through the codec handle, decoded on the GPU, against the oracle's reconstruction"""
+    from waverange_b200 import api
+    rng = np.random.default_rng(shape[0] + grid[2] + wt)
+    f = oracle.probe_field(shape, seed=31 + wt, nm=14)
+    vals = 10.0 ** rng.uniform(-6, -2, size=grid[0] * grid[1] * grid[2])
+    want = oracle.encode(f, 0.0, wtflag=wt, cutoff=(*grid, vals))
+    hw = want["header"]
+    nz, ny, nx = shape
+    d_f = torch_cuda.from_numpy(f).cuda()
+    _, cap = api.setup_wr(nx, ny, nz)
+    blob = torch_cuda.zeros(cap + 64, dtype=torch_cuda.uint8, device="cuda")
+    c0 = api.Codec(device=0, chunk_blocks=0)                      # stock layout: the reference's bytes
+    c0.set_local_cutoff(*grid, vals)
+    h0 = c0.encode_device(d_f.data_ptr(), F64, nx, ny, nz, 0.0, blob.data_ptr(), cap, wt)
+    c0.close()
+    assert (h0.nlay, h0.ntot_enc, list(h0.len_enc_vec)[:h0.nlay]) == (hw.nlay, hw.ntot_enc, list(hw.len)[:hw.nlay])
+    assert blob[:h0.ntot_enc].cpu().numpy().tobytes() == want["data"].tobytes()
+    h, data = api.encoding_wrap(f, 0.0, wtflag=wt, cutoff=(*grid, vals))          # the drop-in entry point
+    assert (h.nlay, h.tolabs, list(h.deps_vec)[:h.nlay], list(h.minval_vec)[:h.nlay]) == \
+           (hw.nlay, hw.tolabs, list(hw.deps)[:hw.nlay], list(hw.minval)[:hw.nlay])
+    assert bits_equal(api.decoding_wrap(shape, h, data), oracle.decode(shape, hw, want["data"]))
+    codec.set_local_cutoff(*grid, vals)
+    h2 = codec.encode_device(d_f.data_ptr(), F64, nx, ny, nz, 123.0, blob.data_ptr(), cap, wt)     # tolrel is ignored
+    codec.set_local_cutoff()
+    assert (h2.nlay, h2.tolabs, list(h2.deps_vec)[:h2.nlay]) == (hw.nlay, hw.tolabs, list(hw.deps)[:hw.nlay])
+    rec = torch_cuda.zeros(f.size, dtype=torch_cuda.float64, device="cuda")
+    codec.decode_device(rec.data_ptr(), F64, nx, ny, nz, h2, blob.data_ptr())
+    assert bits_equal(rec.cpu().numpy().reshape(shape), oracle.decode(shape, hw, want["data"]))

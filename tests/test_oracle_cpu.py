@@ -120,3 +120,24 @@ def test_restatement_vs_reference_random(oracle, ref):
         assert np.array_equal(a["data"], b["data"])
         assert bytes(a["header"]) == bytes(b["header"])
         assert bits_equal(oracle.decode(f.shape, a["header"], a["data"]), ref.decode(f.shape, b["header"], b["data"]))
+
+
+@pytest.mark.parametrize("wt", [0, 1])
+@pytest.mark.parametrize("grid", [(2, 2, 2), (3, 1, 2), (1, 1, 4)])
+def test_local_cutoff_restatement_vs_reference(oracle, ref, wt, grid):
+    """encoding_wrap with mx*my*mz > 1 (wrappers.cpp:343-379): the restatement against the compiled reference.
+    With the transform on, ind_p2w_3d() reports level 4 for every point, so the result is that of the uniform
+    minimum cutoff; with the transform off every point is coded to its block's precision."""
+    rng = np.random.default_rng(grid[0] * 7 + grid[2] + wt)
+    f = oracle.probe_field((12, 10, 14), seed=5 + wt, nm=10)
+    vals = 10.0 ** rng.uniform(-6, -1, size=grid[0] * grid[1] * grid[2])
+    a = oracle.encode(f, 0.0, wtflag=wt, cutoff=(*grid, vals))
+    b = ref.encode(f, 0.0, wtflag=wt, cutoff=(*grid, vals))
+    ha, hb = a["header"], b["header"]
+    assert (ha.nlay, ha.ntot_enc, ha.tolabs, list(ha.deps), list(ha.minval)) == (hb.nlay, hb.ntot_enc, hb.tolabs, list(hb.deps), list(hb.minval))
+    assert a["data"].tobytes() == b["data"].tobytes()
+    u = oracle.encode(f, float(vals.min()), wtflag=wt)
+    if wt:
+        assert u["data"].tobytes() == a["data"].tobytes()
+    else:
+        assert a["header"].ntot_enc < u["header"].ntot_enc

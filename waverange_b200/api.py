@@ -61,7 +61,7 @@ _lib = None
 
 # every symbol include/waverange_b200.h and include/waverange.h declare
 EXPORTS = ["wrb_create", "wrb_destroy", "wrb_last_error", "wrb_set_stream", "wrb_set_chunk_blocks", "wrb_set_seek_points",
-           "wrb_launch_count", "wrb_trim", "wrb_setup", "wrb_encode_device", "wrb_decode_device",
+           "wrb_set_local_cutoff", "wrb_launch_count", "wrb_trim", "wrb_setup", "wrb_encode_device", "wrb_decode_device",
            "wrb_encode_host", "wrb_decode_host", "wrb_set_slab", "wrb_encode_slab_device", "wrb_decode_slab_device", "wrb_quantise_slab_device", "wrb_wavelet3d_device", "wrb_quantise_device",
            "wrb_range_encode_device", "wrb_range_decode_device", "wrb_ind_p2w_3d", "wrb_set_timing",
            "wrb_last_stage_ms",
@@ -87,6 +87,7 @@ def lib():
     L.wrb_set_stream.argtypes = [vp, vp]
     L.wrb_set_chunk_blocks.argtypes = [vp, i]
     L.wrb_set_seek_points.argtypes = [vp, i]
+    L.wrb_set_local_cutoff.argtypes = [vp, i, i, i, C.POINTER(d)]
     L.wrb_launch_count.argtypes = [vp]
     L.wrb_launch_count.restype = C.c_ulonglong
     L.wrb_trim.argtypes = [vp]
@@ -160,8 +161,9 @@ def wrh_write(path, encoded_name, filetype, endianflip, records):
         _fck(lib().wrb_wrh_append(path.encode(), k, C.byref(r)))
 
 
-def encoding_wrap(fld, tol, wtflag=1):
+def encoding_wrap(fld, tol, wtflag=1, cutoff=None):
     """The reference's encoding_wrap on a host float64 array shaped (nz, ny, nx).
+    cutoff = (mx, my, mz, values): the local-precision grid (tol is then ignored).
     Returns (Header, data_enc[:ntot_enc])."""
     L = lib()
     a = np.ascontiguousarray(fld, dtype=np.float64)
@@ -169,12 +171,17 @@ def encoding_wrap(fld, tol, wtflag=1):
     _, cap = setup_wr(nx, ny, nz)
     data = np.zeros(cap, dtype=np.uint8)
     cut = np.array([tol], dtype=np.float64)
+    cmx = cmy = cmz = 1
+    if cutoff is not None:
+        cmx, cmy, cmz, vals = cutoff
+        cut = np.ascontiguousarray(vals, dtype=np.float64)
+        assert cut.size == cmx * cmy * cmz
     h = Header()
     tolabs, mid, half = C.c_double(), C.c_double(), C.c_double()
     wlev, nlay, ntot_enc = C.c_ubyte(), C.c_ubyte(), C.c_ulong()
     deps, minv = np.zeros(NLAYMAX), np.zeros(NLAYMAX)
     lens = (C.c_ulong * NLAYMAX)()
-    L.encoding_wrap(nx, ny, nz, _np_ptr(a, C.c_double), wtflag, 1, 1, 1, _np_ptr(cut, C.c_double),
+    L.encoding_wrap(nx, ny, nz, _np_ptr(a, C.c_double), wtflag, cmx, cmy, cmz, _np_ptr(cut, C.c_double),
                     C.byref(tolabs), C.byref(mid), C.byref(half), C.byref(wlev), C.byref(nlay), C.byref(ntot_enc),
                     _np_ptr(deps, C.c_double), _np_ptr(minv, C.c_double), lens, _np_ptr(data, C.c_ubyte))
     h.tolabs, h.midval, h.halfspanval = tolabs.value, mid.value, half.value
@@ -276,6 +283,15 @@ class Codec:
 
     def set_chunk_blocks(self, k):
         self._ck(self.L.wrb_set_chunk_blocks(self.h, k))
+
+    def set_local_cutoff(self, mx=0, my=0, mz=0, cutoffvec=None):
+        """encoding_wrap()'s mx*my*mz > 1 branch (wrappers.cpp:343-379); no arguments: off"""
+        if cutoffvec is None:
+            self._ck(self.L.wrb_set_local_cutoff(self.h, 0, 0, 0, None))
+        else:
+            v = np.ascontiguousarray(cutoffvec, dtype=np.float64)
+            assert v.size == mx * my * mz
+            self._ck(self.L.wrb_set_local_cutoff(self.h, mx, my, mz, _np_ptr(v, C.c_double)))
 
     def set_seek_points(self, n):
         self._ck(self.L.wrb_set_seek_points(self.h, n))

@@ -45,7 +45,9 @@ struct wrb_codec {
     int chunk_blocks = 1;
     int seek_points = 3;             // decoder entry points inside a chunk (4 lanes decode one chunk)
     std::string err;
-    DevBuf coef, tmp, lllA, lllB, sym, hist, slots, lens, dstoff, seek, state, blob, field, offs, layoff, misc, ext;
+    DevBuf coef, tmp, lllA, lllB, sym, hist, slots, lens, dstoff, seek, state, blob, field, offs, layoff, misc, ext, lcut;
+    int lc_mx = 0, lc_my = 0, lc_mz = 0;      // local cutoff grid (0: off), wrb_set_local_cutoff
+    double lc_min = 0;
     SlabHooks hooks;                  // z-slab partition collectives (nranks == 1: none)
     DevState* h_state = nullptr;      // pinned
     unsigned long long* h_u64 = nullptr;   // pinned scratch (64 KiB)
@@ -122,6 +124,20 @@ void wrb_destroy(wrb_codec* c)
 const char* wrb_last_error(const wrb_codec* c) { return c ? c->err.c_str() : "null codec"; }
 int wrb_set_stream(wrb_codec* c, void* s) { if (!c) return WRB_E_ARG; c->stream = (cudaStream_t)s; return 0; }
 int wrb_set_chunk_blocks(wrb_codec* c, int b) { if (!c || b < 0) return WRB_E_ARG; c->chunk_blocks = b; return 0; }
+int wrb_set_local_cutoff(wrb_codec* c, int mx, int my, int mz, const double* cutoffvec)
+{
+    if (!c) return WRB_E_ARG;
+    if (!cutoffvec || mx < 1 || my < 1 || mz < 1 || (long long)mx * my * mz <= 1) { c->lc_mx = c->lc_my = c->lc_mz = 0; return 0; }
+    const size_t m = (size_t)mx * my * mz;
+    CK(cudaSetDevice(c->device));
+    CK(c->lcut.ensure(m * 8));
+    CK(cudaMemcpyAsync(c->lcut.p, cutoffvec, m * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    double mn = cutoffvec[0];
+    for (size_t k = 1; k < m; k++) if (cutoffvec[k] < mn) mn = cutoffvec[k];     // wrappers.cpp:292-293
+    c->lc_mx = mx; c->lc_my = my; c->lc_mz = mz; c->lc_min = mn;
+    return 0;
+}
 int wrb_set_seek_points(wrb_codec* c, int n) { if (!c || n < 0 || n > 15) return WRB_E_ARG; c->seek_points = n; return 0; }
 unsigned long long wrb_launch_count(const wrb_codec*) { return g_launches.load(); }
 int wrb_set_timing(wrb_codec* c, int on) { if (!c) return WRB_E_ARG; c->timing = on; return 0; }
@@ -307,6 +323,12 @@ static int run_transform_and_quantise(wrb_codec* c, const void* d_field, int dty
     state_init(st, s);
     if (c->timing) cudaEventRecord(c->ev[0], s);
     const bool dist = sg != nullptr && c->hooks.nranks > 1;
+    const bool local = c->lc_mx > 0;
+    if (local) {
+        if (sg != nullptr) return fail(c, WRB_E_ARG, "local cutoff is not available in z-slab mode");
+        tolrel = c->lc_min;
+    }
+    const LocalCutoff lc{wtflag ? 0 : 1, nx, ny, nz, c->lc_mx, c->lc_my, c->lc_mz, (const double*)c->lcut.p, c->lc_min};
     if (sg != nullptr && wtflag) {
         int rc = wavelet_forward_slab(d_field, dtype == WRB_F32, (double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p,
                                       (double*)c->lllB.p, nx, ny, sg->nz_global, sg->z0, nz, kWavLvl, st, c->hooks, s);
@@ -325,8 +347,12 @@ static int run_transform_and_quantise(wrb_codec* c, const void* d_field, int dty
         // global extrema of the coefficients (l == 0) / of the residual left by layer l-1 (wrappers.cpp:308-314)
         if (dist && reduce_extrema(c, &st->rmin_key[l], &st->rmax_key[l])) return fail(c, WRB_E_CUDA, "reduce callback failed");
         layer_params(st, l, s);
-        quantise_layer((const double*)c->coef.p, g, l, st, (uint8_t*)c->sym.p + l * lstride,
-                       (uint32_t*)c->hist.p + l * hstride, s);
+        if (local)
+            quantise_layer_masked((const double*)c->coef.p, g, l, st, (uint8_t*)c->sym.p + l * lstride,
+                                  (uint32_t*)c->hist.p + l * hstride, lc, s);
+        else
+            quantise_layer((const double*)c->coef.p, g, l, st, (uint8_t*)c->sym.p + l * lstride,
+                           (uint32_t*)c->hist.p + l * hstride, s);
     }
     if (c->timing) cudaEventRecord(c->ev[2], s);
     CK(cudaGetLastError());
@@ -340,6 +366,7 @@ extern "C" {
 static int encode_impl(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag, double tolrel,
                        wrb_header* hdr, unsigned char* d_data_enc, unsigned long cap, const SlabGeom* sg, int nlayers = 0)
 {
+    if (c && c->lc_mx > 0) tolrel = c->lc_min;                    // local cutoff: the minimum sets tolabs (wrappers.cpp:292-296)
     if (nlayers <= 0) {
         const char* e = getenv("WRB_LAYER_GUESS");            // tests: force a (wrong) guess to exercise the repeat below
         nlayers = (e && *e) ? atoi(e) : layer_guess(tolrel);

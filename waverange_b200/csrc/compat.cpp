@@ -43,13 +43,16 @@ extern "C" void encoding_wrap(int nx, int ny, int nz, double* fld_1d, int wtflag
 {
     std::lock_guard<std::mutex> lk(g_mu);
     wrb_codec* c = codec();
-    // minimum cutoff (wrappers.cpp:292-293).  The spatially varying branch (:343-379) is compiled
-    // out of every reference front-end (UNIFORM_CUTOFF 1, defs.h:40); with mtot > 1 the global
-    // minimum is applied everywhere, which is at least as accurate at every point.
+    // minimum cutoff (wrappers.cpp:292-293); mx*my*mz > 1 selects the spatially varying branch (:343-379)
     unsigned int mtot = (unsigned int)(mx * my * mz);
     double tolrel = cutoffvec[0];
     for (unsigned int k = 1; k < mtot; k++) if (cutoffvec[k] < tolrel) tolrel = cutoffvec[k];
-    if (mtot > 1) fprintf(stderr, "waverange_b200: local cutoff (mx*my*mz > 1) not supported, using the minimum cutoff everywhere\n");
+    struct LocalGuard {                      // the handle is process-global: never leave the local cutoff set
+        wrb_codec* c; bool on;
+        ~LocalGuard() { if (on) wrb_set_local_cutoff(c, 0, 0, 0, nullptr); }
+    } guard{c, mtot > 1};
+    if (mtot > 1 && wrb_set_local_cutoff(c, mx, my, mz, cutoffvec) != 0)
+        throw std::runtime_error(std::string("waverange_b200: ") + wrb_last_error(c));
     if (verbose()) std::cout << "Wavelet decomposition..." << std::endl << "Range encoding..." << std::endl;
     unsigned char nlaymax; unsigned long cap;
     wrb_setup(nx, ny, nz, &nlaymax, &cap);

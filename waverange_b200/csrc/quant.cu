@@ -44,6 +44,7 @@ __global__ void state_init_kernel(DevState* st)
     for (int l = 0; l <= kNLayMax; l++) { st->rmin_key[l] = kKeyMinInit; st->rmax_key[l] = kKeyMaxInit; }
     for (int l = 0; l < kNLayMax; l++) {
         st->active[l] = 0; st->deps[l] = 0; st->minval[l] = 0; st->aopt[l] = 0; st->bopt[l] = 0; st->len_enc[l] = 0;
+        st->span[l] = 0;
     }
     st->tolabs = 0; st->midval = 0; st->halfspan = 0;
     st->nlay = 0; st->done = 0; st->trivial = 0; st->error = 0; st->ntot_enc = 0;
@@ -70,6 +71,7 @@ __global__ void layer_params_kernel(DevState* st, int l)
     if (st->trivial || st->done) { st->active[l] = 0; return; }
     double mn = dunkey(st->rmin_key[l]), mx = dunkey(st->rmax_key[l]);
     st->minval[l] = mn;
+    st->span[l] = mx - mn;
     double deps = (mx - mn) / 255.0;
     int last = 0;
     if (deps < st->tolabs) { deps = st->tolabs; last = 1; }
@@ -258,6 +260,78 @@ void quantise_layer(const double* coef, const ChunkGeom& g, int layer, DevState*
     case 6: launch_quantise<6>(coef, g, layer, st, sym, hist, s); break;
     default: launch_quantise<7>(coef, g, layer, st, sym, hist, s); break;
     }
+    note_launch(1);
+}
+
+// ------------------------------------------------------------------------------------------
+// Local (spatially varying) cutoff: the mx*my*mz > 1 branch of encoding_wrap() (wrappers.cpp:343-379).
+// For every point the reference takes the wavelet-space index and level from ind_p2w_3d(), a precision
+//   precmask = (level <= LOC_CUTOFF_LVL) ? tolabs / tolrel * cutoffvec[block of the PHYSICAL point] : tolabs,
+// and, in every layer, codes symbol 0 and leaves residual 0 (fld = minval; fld -= 0*deps + minval) where the
+// layer's residual span max - min is below precmask.  ind_p2w_3d() reports level == lvlin for every point (its
+// `chlvl` flag is never cleared, waveletcdf97_3d.c:487,535), so with the transform on (lvlin = 4 > 1) precmask
+// is tolabs everywhere, and with the transform off (lvlin = 0) the wavelet index IS the physical index and every
+// point gets its block's cutoff.  Both cases are reproduced as they are.  Rarely used: a plain kernel, one CTA per
+// coder block, shared-memory atomics for the histogram.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) quantise_masked_kernel(const double* __restrict__ coef, ChunkGeom g, int layer,
+                                                              DevState* st, uint8_t* __restrict__ sym,
+                                                              uint32_t* __restrict__ hist, LocalCutoff lc)
+{
+    if (!st->active[layer]) return;
+    __shared__ uint32_t s_hist[256];
+    const int tid = threadIdx.x;
+    s_hist[tid] = 0;
+    __syncthreads();
+    const unsigned int b = blockIdx.x;
+    const unsigned int c = b / g.blocks_per_chunk, kb = b % g.blocks_per_chunk;
+    const unsigned long long cstart = (unsigned long long)c * g.chunk_len;
+    const unsigned long long clen = (g.ntot - cstart < g.chunk_len) ? g.ntot - cstart : g.chunk_len;
+    const unsigned long long boff = (unsigned long long)kb * kBlock;
+    const unsigned int bs = (clen - boff < kBlock) ? (unsigned int)(clen - boff) : kBlock;
+    const double tolabs = st->tolabs;
+    const double scale = tolabs / lc.tolrel;                         // tolabs/tolrel * lcl_prec(...), left to right
+    const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+    double rmin = kInf, rmax = -kInf;
+    for (unsigned int i = tid; i < bs; i += blockDim.x) {
+        const unsigned long long jw = cstart + boff + i;
+        double pm = tolabs;
+        if (lc.per_point) {                                          // level 0: physical index == array index
+            const int jx = (int)(jw % (unsigned long long)lc.nx);
+            const int jy = (int)((jw / (unsigned long long)lc.nx) % (unsigned long long)lc.ny);
+            const int jz = (int)(jw / ((unsigned long long)lc.nx * lc.ny));
+            const int kx = (int)((double)jx / (double)lc.nx * (double)lc.mx);     // lcl_prec, wrappers.cpp:55-64
+            const int ky = (int)((double)jy / (double)lc.ny * (double)lc.my);
+            const int kz = (int)((double)jz / (double)lc.nz * (double)lc.mz);
+            pm = scale * lc.cut[kx + lc.mx * ky + lc.mx * lc.my * kz];
+        }
+        double r = coef[jw];
+        unsigned int q = 0;
+        for (int m = 0; m <= layer; m++) {
+            if (st->span[m] < pm) {                                  // :365-371
+                q = 0;
+                r = 0.0;                                             // minval - (0*deps + minval)
+            } else {
+                const double fq = st->aopt[m] * r + st->bopt[m];
+                q = (unsigned int)(unsigned char)__double2int_rz(fq);
+                r = r - ((double)q * st->deps[m] + st->minval[m]);
+            }
+        }
+        sym[(unsigned long long)c * g.pitch + boff + i] = (uint8_t)q;
+        atomicAdd(&s_hist[q], 1u);
+        rmin = dmin2(rmin, r);
+        rmax = dmax2(rmax, r);
+    }
+    __syncthreads();
+    if (s_hist[tid]) atomicAdd(&hist[(unsigned long long)b * 256 + tid], s_hist[tid]);
+    block_minmax_commit(rmin <= rmax ? dkey(rmin) : kKeyMinInit, rmin <= rmax ? dkey(rmax) : kKeyMaxInit, &st->rmin_key[layer + 1],
+                        &st->rmax_key[layer + 1]);
+}
+
+void quantise_layer_masked(const double* coef, const ChunkGeom& g, int layer, DevState* st, uint8_t* sym, uint32_t* hist,
+                           const LocalCutoff& lc, cudaStream_t s)
+{
+    quantise_masked_kernel<<<g.nblocks, 256, 0, s>>>(coef, g, layer, st, sym, hist, lc);
     note_launch(1);
 }
 

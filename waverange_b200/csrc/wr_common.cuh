@@ -36,6 +36,7 @@ struct DevState {
     unsigned long long rmin_key[kNLayMax + 1], rmax_key[kNLayMax + 1];  // residual extrema before layer l
     double tolabs, midval, halfspan;
     double deps[kNLayMax], minval[kNLayMax], aopt[kNLayMax], bopt[kNLayMax];
+    double span[kNLayMax];     // max - min of the residual before layer l (the local-cutoff test, wrappers.cpp:365)
     int    active[kNLayMax];   // layer l is part of the stream
     int    nlay;
     int    done;               // brflag seen (wrappers.cpp:326-333)

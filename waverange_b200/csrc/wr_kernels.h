@@ -77,6 +77,15 @@ void state_prepare(DevState* st, double tolrel, cudaStream_t s);          // aft
 void layer_params(DevState* st, int layer, cudaStream_t s);                // before quantising `layer`
 void quantise_layer(const double* coef, const ChunkGeom& g, int layer, DevState* st, uint8_t* sym,
                     uint32_t* hist, cudaStream_t s);
+// local cutoff of encoding_wrap()'s mx*my*mz > 1 branch (see quant.cu)
+struct LocalCutoff {
+    int per_point;            // 1: transform off, every point gets its block's cutoff; 0: precmask = tolabs everywhere
+    int nx, ny, nz, mx, my, mz;
+    const double* cut;        // device, mx*my*mz
+    double tolrel;            // min(cut)
+};
+void quantise_layer_masked(const double* coef, const ChunkGeom& g, int layer, DevState* st, uint8_t* sym, uint32_t* hist,
+                           const LocalCutoff& lc, cudaStream_t s);
 void dequantise(const uint8_t* sym, unsigned long long layer_stride, const ChunkGeom& g, int nlay,
                 const double* deps, const double* minval, double* coef, cudaStream_t s);
 
