@@ -35,9 +35,10 @@ N_FIELD = 512
 TOL = 1e-4
 SAMPLE = 256            # edge of the CPU-baseline sample cube
 METRIC = "raw-field compress+decompress throughput (device-timed)"
-# DRAM bytes of the forward-wavelet + quantise kernels of one compress of the default workload, from ncu:
-# fused level 1: 0.555 + 1.028 GB, levels 2-4: 0.156 + 0.099 + ~0.04 GB, quantise 3 x (1.07 + 0.13) GB
-NCU_TRAFFIC_512 = int((0.555 + 1.028 + 0.156 + 0.099 + 0.04 + 3 * (1.07 + 0.13)) * 1e9)
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the forward-wavelet + quantise kernels of one compress of
+# the default workload, from the ncu --set full capture profiles/r1j_ncu_raw_512.csv:
+# forward levels 1-4: 1.578 + 0.249 + 0.017 + 0.002 GB, quantise 3 x (1.076 + 0.131) GB
+NCU_TRAFFIC_512 = int((1.578 + 0.249 + 0.017 + 0.002 + 3 * (1.076 + 0.131)) * 1e9)
 UNIT = "GB/s"
 
 
@@ -351,7 +352,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "scope": "forward wavelet + quantise kernels of one compress (stage events)",
                      "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                      # dram__bytes_read+write of those kernels from the ncu --set full captures of this workload
-                     # (profiles/r1d_fused_forward_ncu_raw_512.csv + r1b_wavelet_quantise_ncu_raw_512.csv), per compress
+                     # (profiles/r1j_ncu_raw_512.csv), per compress
                      "traffic": (NCU_TRAFFIC_512 if (n == N_FIELD and nlay == 3 and not slab_mode) else None),
                      "algorithmic_bytes": a_c, "peak_source": peak_src},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": world * (nbytes + int(h.ntot_enc)),
