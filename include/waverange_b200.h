@@ -122,6 +122,16 @@ int wrb_decode_slab_device(wrb_codec* c, void* d_field_slab_out, int dtype, int 
 int wrb_quantise_slab_device(wrb_codec* c, const void* d_field_slab, int dtype, int nx, int ny, int nz, int z0, int nzl,
                              int wtflag, double tolrel, wrb_header* hdr, double* d_coef, unsigned char* d_sym);
 
+/* Dequantise + inverse transform from given symbols instead of coded data: d_sym holds hdr->nlay planes of ntot
+ * (slab: nx*ny*nzl) bytes in array order, what wrb_quantise_device / wrb_quantise_slab_device return.  Together with
+ * wrb_range_encode_device / wrb_range_decode_device these let a caller put its own exchange between the quantiser and
+ * the coder -- waverange_b200/slab.py uses them to code a z-slab partitioned field in the GLOBAL symbol order, so that
+ * the chunk streams are those of the single-GPU run. */
+int wrb_decode_symbols_device(wrb_codec* c, void* d_field_out, int dtype, int nx, int ny, int nz, const wrb_header* hdr,
+                              const unsigned char* d_sym);
+int wrb_decode_slab_symbols_device(wrb_codec* c, void* d_field_slab_out, int dtype, int nx, int ny, int nz, int z0, int nzl,
+                                   const wrb_header* hdr, const unsigned char* d_sym);
+
 /* ---- host-buffer path (copies inside) ------------------------------------------------------- */
 int wrb_encode_host(wrb_codec* c, const void* field, int dtype, int nx, int ny, int nz, int wtflag, double tolrel,
                     wrb_header* hdr, unsigned char* data_enc, unsigned long cap);

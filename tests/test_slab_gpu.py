@@ -102,3 +102,63 @@ def test_slab_rejects_bad_partition(codec, torch_cuda):
     out = torch_cuda.zeros(1 << 20, dtype=torch_cuda.uint8, device="cuda")
     with pytest.raises(api.WaveRangeError):
         codec.encode_slab_device(x.data_ptr(), F64, 8, 8, 96, 0, 48, 1e-3, out.data_ptr(), 1 << 20)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+@pytest.mark.parametrize("shape,tol", [((128, 64, 96), 1e-5), ((128, 48, 40), 1e-9)])
+def test_slab_global_symbol_order(torch_cuda, oracle, world, shape, tol):
+    """with the symbol exchange (slab.encode_global) the ranks code whole chunks of the GLOBAL
+    sequence: every chunk stream equals the oracle's range_encode of that chunk (= the single-GPU run's), the joined
+    pieces are an ordinary container that the single-GPU decoder reads, and decode_global gives the reference's
+    reconstruction"""
+    torch = torch_cuda
+    from waverange_b200 import api, slab
+    nz, ny, nx = shape
+    f = oracle.probe_field(shape, seed=77 + world, nm=16)
+    want = oracle.encode(f, tol, chunk_len=slab.CHUNK)
+    hw = want["header"]
+    parts = slab.partition(nz, world)
+    grp = slab.LocalGroup(torch, world)
+
+    def rank_fn(r, halo_cb, reduce_cb):
+        z0, nzl = parts[r]
+        c = api.Codec(device=0)
+        c.set_slab(r, world, halo_cb, reduce_cb)
+        hooks = grp.rank_hooks(r)
+        go = slab.GlobalOrder(torch, nx, ny, nz, r, world, torch.device("cuda", 0))
+        d_f = torch.from_numpy(np.ascontiguousarray(f[z0:z0 + nzl])).cuda()
+        h, pieces = slab.encode_global(torch, c, hooks, go, d_f.data_ptr(), F64, tol)
+        rec = torch.zeros(nzl * ny * nx, dtype=torch.float64, device="cuda")
+        slab.decode_global(torch, c, hooks, go, h, pieces, rec.data_ptr(), F64)
+        out = dict(h=h, pieces=[(list(l), s.cpu().numpy().tobytes()) for l, s in pieces], rec=rec.cpu().numpy().reshape(nzl, ny, nx))
+        c.close()
+        return out
+
+    res = grp.run(rank_fn)
+    h = res[0]["h"]
+    assert h.nlay == hw.nlay and list(h.deps_vec)[:h.nlay] == list(hw.deps)[:h.nlay]
+    # the chunk streams of all ranks, in rank order, are the oracle's chunk streams
+    blob = b""
+    woff = 0
+    for l in range(h.nlay):
+        lens = [n for r in res for n in r["pieces"][l][0]]
+        streams = b"".join(r["pieces"][l][1] for r in res)
+        assert lens == [int(x) for x in want["chunk_lens"][l]]
+        n = sum(lens)
+        assert streams == want["data"][woff:woff + n].tobytes(), "layer %d" % l
+        woff += n
+        layer = slab.wrck_container(slab.CHUNK if f.size > slab.CHUNK else f.size, f.size, lens, streams)
+        h.len_enc_vec[l] = len(layer)
+        blob += layer
+    h.ntot_enc = len(blob)
+    # ... and the joined pieces are a container the plain single-GPU decoder reads
+    c = api.Codec(device=0)
+    d_blob = torch.zeros(len(blob) + 64, dtype=torch.uint8, device="cuda")
+    d_blob[:len(blob)] = torch.from_numpy(np.frombuffer(blob, dtype=np.uint8).copy()).cuda()
+    rec1 = torch.zeros(f.size, dtype=torch.float64, device="cuda")
+    c.decode_device(rec1.data_ptr(), F64, nx, ny, nz, h, d_blob.data_ptr())
+    c.close()
+    whole = oracle.encode(f, tol)
+    want_rec = oracle.decode(shape, whole["header"], whole["data"])
+    assert bits_equal(rec1.cpu().numpy().reshape(shape), want_rec)
+    assert bits_equal(np.concatenate([r["rec"] for r in res], axis=0), want_rec)

@@ -62,7 +62,7 @@ _lib = None
 # every symbol include/waverange_b200.h and include/waverange.h declare
 EXPORTS = ["wrb_create", "wrb_destroy", "wrb_last_error", "wrb_set_stream", "wrb_set_chunk_blocks", "wrb_set_seek_points",
            "wrb_set_local_cutoff", "wrb_launch_count", "wrb_trim", "wrb_setup", "wrb_encode_device", "wrb_decode_device",
-           "wrb_encode_host", "wrb_decode_host", "wrb_set_slab", "wrb_encode_slab_device", "wrb_decode_slab_device", "wrb_quantise_slab_device", "wrb_wavelet3d_device", "wrb_quantise_device",
+           "wrb_encode_host", "wrb_decode_host", "wrb_decode_symbols_device", "wrb_decode_slab_symbols_device", "wrb_set_slab", "wrb_encode_slab_device", "wrb_decode_slab_device", "wrb_quantise_slab_device", "wrb_wavelet3d_device", "wrb_quantise_device",
            "wrb_range_encode_device", "wrb_range_decode_device", "wrb_ind_p2w_3d", "wrb_set_timing",
            "wrb_last_stage_ms",
            "wrb_wrh_begin", "wrb_wrh_append", "wrb_wrh_read", "wrb_file_encode", "wrb_file_decode", "wrb_file_last_error",
@@ -100,6 +100,8 @@ def lib():
     L.wrb_set_slab.argtypes = [vp, i, i, HALO_FN, REDUCE_FN, vp]
     L.wrb_encode_slab_device.argtypes = [vp, vp, i, i, i, i, i, i, i, d, H, vp, ul]
     L.wrb_decode_slab_device.argtypes = [vp, vp, i, i, i, i, i, i, H, vp]
+    L.wrb_decode_symbols_device.argtypes = [vp, vp, i, i, i, i, H, vp]
+    L.wrb_decode_slab_symbols_device.argtypes = [vp, vp, i, i, i, i, i, i, H, vp]
     L.wrb_quantise_slab_device.argtypes = [vp, vp, i, i, i, i, i, i, i, d, H, vp, vp]
     L.wrb_wavelet3d_device.argtypes = [vp, vp, i, i, i, i]
     L.wrb_quantise_device.argtypes = [vp, vp, i, i, i, i, i, d, H, vp, vp]
@@ -336,6 +338,12 @@ class Codec:
 
     def decode_slab_device(self, d_out, dtype, nx, ny, nz, z0, nzl, h, d_data):
         self._ck(self.L.wrb_decode_slab_device(self.h, d_out, dtype, nx, ny, nz, z0, nzl, C.byref(h), d_data))
+
+    def decode_symbols_device(self, d_out, dtype, nx, ny, nz, h, d_sym):
+        self._ck(self.L.wrb_decode_symbols_device(self.h, d_out, dtype, nx, ny, nz, C.byref(h), d_sym))
+
+    def decode_slab_symbols_device(self, d_out, dtype, nx, ny, nz, z0, nzl, h, d_sym):
+        self._ck(self.L.wrb_decode_slab_symbols_device(self.h, d_out, dtype, nx, ny, nz, z0, nzl, C.byref(h), d_sym))
 
     # ---- host path -------------------------------------------------------------------------
     def encode_host(self, fld, tol, wtflag=1, out=None):

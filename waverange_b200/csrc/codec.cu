@@ -489,23 +489,51 @@ int wrb_quantise_slab_device(wrb_codec* c, const void* d_field_slab, int dtype, 
 
 }  // extern "C"
 
+// d_sym_flat != null: the layers' symbols are given (nlay planes of ntot bytes, array order) instead of coded data --
+// the parse and range-decoder stages are skipped (wrb_decode_symbols_device, wrb_decode_slab_symbols_device)
 static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int nz, const wrb_header* hdr,
-                       const unsigned char* d_data_enc, const SlabGeom* sg)
+                       const unsigned char* d_data_enc, const SlabGeom* sg, const unsigned char* d_sym_flat = nullptr)
 {
     if (!c || !d_out || !hdr || nx < 1 || ny < 1 || nz < 1 || (dtype != WRB_F64 && dtype != WRB_F32))
         return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
     CK(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     const unsigned long long ntot = (unsigned long long)nx * ny * nz;
-    if (hdr->ntot_enc == 0) {                                 // wrappers.cpp:462-469
+    if (hdr->ntot_enc == 0 && (d_sym_flat == nullptr || hdr->nlay == 0)) {      // wrappers.cpp:462-469
         if (dtype == WRB_F32) fill_kernel<float><<<grid_for(ntot), 256, 0, s>>>((float*)d_out, ntot, hdr->midval);
         else fill_kernel<double><<<grid_for(ntot), 256, 0, s>>>((double*)d_out, ntot, hdr->midval);
         note_launch(1);
         CK(cudaStreamSynchronize(s));
         return 0;
     }
-    if (!d_data_enc || hdr->nlay < 1 || hdr->nlay > kNLayMax || hdr->wlev > 16) return fail(c, WRB_E_ARG, "bad header");
+    if ((!d_data_enc && !d_sym_flat) || hdr->nlay < 1 || hdr->nlay > kNLayMax || hdr->wlev > 16) return fail(c, WRB_E_ARG, "bad header");
     const int nlay = hdr->nlay;
+    if (d_sym_flat != nullptr) {
+        ChunkGeom g = make_geom(ntot, 0, 0);
+        g.pitch = g.chunk_len;
+        int rc;
+        if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr))) return rc;
+        const unsigned long long lstride = ntot;
+        if (c->timing) for (int i = 0; i < 4; i++) cudaEventRecord(c->ev[i], s);
+        const bool fuse = sg == nullptr && hdr->wlev > 0 && nz >= (1 << hdr->wlev);
+        if (!fuse) dequantise(d_sym_flat, lstride, g, nlay, hdr->deps_vec, hdr->minval_vec, (double*)c->coef.p, s);
+        if (sg != nullptr && hdr->wlev > 0) {
+            if (wavelet_inverse_slab((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, (double*)c->ext.p,
+                                     d_out, dtype == WRB_F32, nx, ny, sg->nz_global, sg->z0, nz, (int)hdr->wlev, c->hooks, s))
+                return fail(c, WRB_E_CUDA, "halo exchange callback failed");
+        } else if (fuse) {
+            wavelet_inverse((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, d_out, dtype == WRB_F32,
+                            nx, ny, nz, (int)hdr->wlev, s, d_sym_flat, lstride, g.chunk_len, g.pitch, nlay, hdr->deps_vec, hdr->minval_vec);
+        } else {
+            wavelet_inverse((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, d_out, dtype == WRB_F32,
+                            nx, ny, nz, (int)hdr->wlev, s);
+        }
+        if (c->timing) cudaEventRecord(c->ev[4], s);
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        if (c->timing) for (int i = 0; i < 4; i++) cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]);
+        return 0;
+    }
     unsigned long long* lay = c->h_u64;                       // layer offsets [nlay+1]
     lay[0] = 0;
     for (int l = 0; l < nlay; l++) lay[l + 1] = lay[l] + hdr->len_enc_vec[l];
@@ -587,6 +615,23 @@ int wrb_decode_slab_device(wrb_codec* c, void* d_out_slab, int dtype, int nx, in
     if (rc) return rc;
     SlabGeom sg{nz, z0};
     return decode_impl(c, d_out_slab, dtype, nx, ny, nzl, hdr, d_data_enc, &sg);
+}
+
+int wrb_decode_symbols_device(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int nz, const wrb_header* hdr,
+                              const unsigned char* d_sym)
+{
+    if (!d_sym) return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
+    return decode_impl(c, d_out, dtype, nx, ny, nz, hdr, nullptr, nullptr, d_sym);
+}
+
+int wrb_decode_slab_symbols_device(wrb_codec* c, void* d_out_slab, int dtype, int nx, int ny, int nz, int z0, int nzl,
+                                   const wrb_header* hdr, const unsigned char* d_sym)
+{
+    if (!c || !hdr || !d_sym) return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
+    int rc = slab_check(c, nx, ny, nz, z0, nzl, (int)hdr->wlev);
+    if (rc) return rc;
+    SlabGeom sg{nz, z0};
+    return decode_impl(c, d_out_slab, dtype, nx, ny, nzl, hdr, nullptr, &sg, d_sym);
 }
 
 int wrb_encode_host(wrb_codec* c, const void* field, int dtype, int nx, int ny, int nz, int wtflag, double tolrel,
