@@ -107,10 +107,12 @@ constexpr int kQLoads = 8;                               // coefficients per thr
 constexpr int kQTile = kQThreads * kQLoads;              // 2048
 constexpr int kQAhead = 3;                               // L2 prefetch distance in tiles
 constexpr int kQHistBytes = 256 * kQThreads;             // private byte counters: 64 KiB
-// A coder block is split over kQSub CTAs (partial histograms are added with global atomics): 2237 blocks at
-// 512^3 on 444 CTA slots would otherwise run 6 waves for 5.04 waves of work
-constexpr unsigned int kQSubLen = 8 * kQTile;            // 16384 coefficients
-constexpr unsigned int kQSub = (kBlock + kQSubLen - 1) / kQSubLen;   // 4
+// CTAs per coder block.  The per-CTA costs (clearing 64 KiB of counters, adding them up, the first exposed load, the
+// extrema commit) outweigh the tail of the last wave: measured at 512^3 (2237 blocks, 444 CTA slots) the three layers
+// take 0.71 ms with one CTA per block, 0.73 with two, 0.77 with three, 0.81 with four.  Partial histograms are added
+// with global atomics, so any split works.
+constexpr unsigned int kQSubLen = 30 * kQTile;           // >= 60000: one CTA per block
+constexpr unsigned int kQSub = (kBlock + kQSubLen - 1) / kQSubLen;
 
 __device__ __forceinline__ double floor_magic(double fq)
 {
@@ -219,16 +221,16 @@ __global__ void __launch_bounds__(kQThreads, (LAYER <= 2) ? 3 : 2) quantise_kern
     __syncthreads();
     {   // thread = bin: add up the 256 private counters of the bin (64 words, rotated start -> no bank conflicts)
         const uint4* row = reinterpret_cast<const uint4*>(s_cnt + tid * 64);
-        int tot = 0;
+        unsigned int tot = 0;
 #pragma unroll
         for (int w = 0; w < 16; w++) {
             const uint4 x = row[(w + tid) & 15];
-            tot = __dp4a((int)x.x, 0x01010101, tot);      // sum of the four byte counters of a word
-            tot = __dp4a((int)x.y, 0x01010101, tot);
-            tot = __dp4a((int)x.z, 0x01010101, tot);
-            tot = __dp4a((int)x.w, 0x01010101, tot);
+            tot = __dp4a(x.x, 0x01010101u, tot);          // sum of the four byte counters of a word (UNSIGNED bytes:
+            tot = __dp4a(x.y, 0x01010101u, tot);          // a counter can exceed 127)
+            tot = __dp4a(x.z, 0x01010101u, tot);
+            tot = __dp4a(x.w, 0x01010101u, tot);
         }
-        if (tot) atomicAdd(&hist[(unsigned long long)b * 256 + tid], (uint32_t)tot);      // hist is zeroed per encode
+        if (tot) atomicAdd(&hist[(unsigned long long)b * 256 + tid], tot);      // hist is zeroed per encode
     }
     const bool any = (unsigned int)tid < n;
     block_minmax_commit(any ? dkey(rmin) : kKeyMinInit, any ? dkey(rmax) : kKeyMaxInit, &st->rmin_key[layer + 1],
