@@ -303,3 +303,66 @@ def test_local_cutoff_branch(product_lib, codec, torch_cuda, oracle, wt, shape, 
     rec = torch_cuda.zeros(f.size, dtype=torch_cuda.float64, device="cuda")
     codec.decode_device(rec.data_ptr(), F64, nx, ny, nz, h2, blob.data_ptr())
     assert bits_equal(rec.cpu().numpy().reshape(shape), oracle.decode(shape, hw, want["data"]))
+
+
+def _random_cases(n, seed):
+    """shapes that hit every dispatch of the transform: all levels fused (multiples of 16, >= 64 / 128), some levels
+    fused and the coarser ones general (even but not multiples of 16), odd and tiny extents, 2-D and 1-D fields"""
+    rng = np.random.default_rng(seed)
+    pools = [[64, 80, 96, 128], [24, 40, 56, 72, 88, 100, 36], [9, 17, 31, 33, 50, 63, 7, 5], [1, 2, 3]]
+    out = []
+    for k in range(n):
+        kind = k % 5
+        if kind == 0:
+            shape = tuple(int(rng.choice(pools[0])) for _ in range(3))
+        elif kind == 1:
+            shape = tuple(int(rng.choice(pools[1])) for _ in range(3))
+        elif kind == 2:
+            shape = tuple(int(rng.choice(pools[2])) for _ in range(3))
+        elif kind == 3:
+            shape = (int(rng.choice(pools[3])), int(rng.choice(pools[0] + pools[1])), int(rng.choice(pools[1] + pools[2])))
+        else:
+            shape = tuple(int(rng.choice(pools[int(rng.integers(0, 3))])) for _ in range(3))
+        tol = float(10.0 ** rng.uniform(-12, -2))
+        out.append((shape, tol, int(rng.integers(0, 2)), int(rng.integers(0, 5) > 0)))
+    return out
+
+
+@pytest.mark.parametrize("shape,tol,f32,wt", _random_cases(40, 2026))
+def test_randomised_differential(codec, torch_cuda, oracle, shape, tol, f32, wt):
+    """whole pipeline against the oracle on random shapes / tolerances / precisions: header doubles, every chunk
+    stream, the stock-layout bytes and both decoders' reconstructions, bit for bit"""
+    from waverange_b200 import api
+    f = oracle.probe_field(shape, seed=sum(shape) + int(-np.log10(tol)), nm=12, round_f32=bool(f32))
+    nz, ny, nx = shape
+    dt = F32 if f32 else F64
+    want = oracle.encode(f, tol, wtflag=wt, chunk_len=L1)
+    whole = oracle.encode(f, tol, wtflag=wt)
+    hw = want["header"]
+    fin = f.astype(np.float32) if f32 else f
+    h, out = encode_dev(codec, torch_cuda, fin, tol, wt, dtype=dt)
+    assert (h.nlay, h.wlev) == (hw.nlay, hw.wlev)
+    assert bits_equal(np.array([h.tolabs, h.midval, h.halfspanval]), np.array([hw.tolabs, hw.midval, hw.halfspan]))
+    assert list(h.deps_vec)[:h.nlay] == list(hw.deps)[:h.nlay] and list(h.minval_vec)[:h.nlay] == list(hw.minval)[:h.nlay]
+    blob = out[:h.ntot_enc].cpu().numpy()
+    off, woff = 0, 0
+    for l in range(h.nlay):
+        _, streams = api.parse_container(blob[off:off + h.len_enc_vec[l]])
+        n = int(want["chunk_lens"][l].sum())
+        assert b"".join(streams) == want["data"][woff:woff + n].tobytes(), "layer %d" % l
+        woff += n
+        off += h.len_enc_vec[l]
+    rec = torch_cuda.zeros(f.size, dtype=torch_cuda.float32 if f32 else torch_cuda.float64, device="cuda")
+    codec.decode_device(rec.data_ptr(), dt, nx, ny, nz, h, out.data_ptr())
+    want_rec = oracle.decode(shape, whole["header"], whole["data"])
+    if f32:
+        want_rec = want_rec.astype(np.float32)
+    assert bits_equal(rec.cpu().numpy().reshape(shape), want_rec)
+    # stock layout: the reference's own bytes, and its streams decode on the GPU
+    c0 = api.Codec(device=0, chunk_blocks=0)
+    h0, out0 = encode_dev(c0, torch_cuda, fin, tol, wt, dtype=dt)
+    assert h0.ntot_enc == whole["header"].ntot_enc and out0[:h0.ntot_enc].cpu().numpy().tobytes() == whole["data"].tobytes()
+    rec.zero_()
+    c0.decode_device(rec.data_ptr(), dt, nx, ny, nz, h0, out0.data_ptr())
+    c0.close()
+    assert bits_equal(rec.cpu().numpy().reshape(shape), want_rec)
