@@ -515,11 +515,13 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
         if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr))) return rc;
         const unsigned long long lstride = ntot;
         if (c->timing) for (int i = 0; i < 4; i++) cudaEventRecord(c->ev[i], s);
-        const bool fuse = sg == nullptr && hdr->wlev > 0 && nz >= (1 << hdr->wlev);
+        const bool slab_fused = sg != nullptr && hdr->wlev > 0 && wavelet_inverse_slab_fused_ok(nx, ny, sg->nz_global, nz, (int)hdr->wlev);
+        const bool fuse = slab_fused || (sg == nullptr && hdr->wlev > 0 && nz >= (1 << hdr->wlev));
         if (!fuse) dequantise(d_sym_flat, lstride, g, nlay, hdr->deps_vec, hdr->minval_vec, (double*)c->coef.p, s);
         if (sg != nullptr && hdr->wlev > 0) {
             if (wavelet_inverse_slab((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, (double*)c->ext.p,
-                                     d_out, dtype == WRB_F32, nx, ny, sg->nz_global, sg->z0, nz, (int)hdr->wlev, c->hooks, s))
+                                     d_out, dtype == WRB_F32, nx, ny, sg->nz_global, sg->z0, nz, (int)hdr->wlev, c->hooks, s,
+                                     slab_fused ? d_sym_flat : nullptr, lstride, nlay, hdr->deps_vec, hdr->minval_vec))
                 return fail(c, WRB_E_CUDA, "halo exchange callback failed");
         } else if (fuse) {
             wavelet_inverse((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, d_out, dtype == WRB_F32,
@@ -573,12 +575,14 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
     if (c->timing) cudaEventRecord(c->ev[2], s);
     // The inverse z pass rebuilds the coefficients from the symbols itself; a separate dequantise pass is only
     // needed without a transform, for extent-1 z, and in slab mode (its band buffers are built from coef).
-    const bool fuse_deq = sg == nullptr && hdr->wlev > 0 && nz >= (1 << hdr->wlev) && getenv("WRB_NO_FUSED_DEQUANT") == nullptr;
+    const bool slab_fused = sg != nullptr && hdr->wlev > 0 && wavelet_inverse_slab_fused_ok(nx, ny, sg->nz_global, nz, (int)hdr->wlev);
+    const bool fuse_deq = slab_fused || (sg == nullptr && hdr->wlev > 0 && nz >= (1 << hdr->wlev) && getenv("WRB_NO_FUSED_DEQUANT") == nullptr);
     if (!fuse_deq) dequantise((const uint8_t*)c->sym.p, lstride, g, nlay, hdr->deps_vec, hdr->minval_vec, (double*)c->coef.p, s);
     if (c->timing) cudaEventRecord(c->ev[3], s);
     if (sg != nullptr && hdr->wlev > 0) {
         if (wavelet_inverse_slab((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, (double*)c->ext.p,
-                                 d_out, dtype == WRB_F32, nx, ny, sg->nz_global, sg->z0, nz, (int)hdr->wlev, c->hooks, s))
+                                 d_out, dtype == WRB_F32, nx, ny, sg->nz_global, sg->z0, nz, (int)hdr->wlev, c->hooks, s,
+                                 slab_fused ? (const uint8_t*)c->sym.p : nullptr, lstride, nlay, hdr->deps_vec, hdr->minval_vec))
             return fail(c, WRB_E_CUDA, "halo exchange callback failed");
     } else {
         if (fuse_deq)

@@ -48,6 +48,11 @@ struct FusedInvArgs {
     int n0, n1, n2;                           // box extents (even)
     int zpairs;                               // output pairs per z-segment
     int vec_ok;                               // output rows are 16-byte aligned: vector stores allowed
+    // z-slab mode (NLAY == 0 only): the coefficients come from two band buffers that hold this rank's pairs
+    // [pair_lo, pair_lo + nown) of the GLOBAL line plus `halo` planes of the neighbours on either side (own pair p at
+    // plane p - pair_lo + halo); n2 is then the global extent and the output planes are rank-local.
+    const double* lowb; const double* highb; long long bsz;
+    int pair_lo, nown, halo;
 };
 
 // mirrored index of a low (s-type) / high (d-type) coefficient of a line with Q pairs, clamped
@@ -99,8 +104,10 @@ __global__ void __launch_bounds__(ITHREADS, 1) inv_level_fused_kernel(FusedInvAr
     const int tid = threadIdx.x;
     const int q0 = a.n0 >> 1, q1 = a.n1 >> 1, q2 = a.n2 >> 1;
     const int px0 = blockIdx.x * IPX, py0 = blockIdx.y * IPY;
-    const int e0 = blockIdx.z * a.zpairs;
-    const int e1 = (e0 + a.zpairs < q2) ? e0 + a.zpairs : q2;
+    const bool band = (NLAY == 0) && a.lowb != nullptr;
+    const int pair_lo = band ? a.pair_lo : 0, pair_hi = band ? a.pair_lo + a.nown : q2;
+    const int e0 = pair_lo + blockIdx.z * a.zpairs;
+    const int e1 = (e0 + a.zpairs < pair_hi) ? e0 + a.zpairs : pair_hi;
     // ---- coefficient positions of this thread: flat index tid + k*ITHREADS over ICY x ICX ----
     int coff[ISLOTS], loff[ISLOTS], soff[ISLOTS];
     bool inl[ISLOTS];                          // the z-low coefficient comes from the previous level's output
@@ -138,6 +145,9 @@ __global__ void __launch_bounds__(ITHREADS, 1) inv_level_fused_kernel(FusedInvAr
                     if (!inl[k]) qlo[k][l] = a.sym[(unsigned long long)l * a.lstride + jl];
                 }
                 if (inl[k]) clo[k] = a.lll[loff[k] + pl * a.lsz];
+            } else if (band) {
+                chi[k] = a.highb[coff[k] + (ph - q2 - pair_lo + a.halo) * a.bsz];
+                clo[k] = a.lowb[coff[k] + (pl - pair_lo + a.halo) * a.bsz];
             } else {
                 chi[k] = a.coef[jh];
                 clo[k] = inl[k] ? a.lll[loff[k] + pl * a.lsz] : a.coef[jl];
@@ -203,7 +213,7 @@ __global__ void __launch_bounds__(ITHREADS, 1) inv_level_fused_kernel(FusedInvAr
             inv_window(ldl, ldh, ev, od);
             const int xp = px0 + g * IR;                                  // first output pair
             const int y = 2 * py0 + r;
-            const long long z = 2 * (long long)(m - 2) + pl;
+            const long long z = 2 * (long long)(m - 2 - pair_lo) + pl;
             if (y < a.n1 && xp < q0) {
                 TOUT* __restrict__ o = (TOUT*)a.dst + 2 * xp + (long long)y * a.dsy + z * a.dsz;
                 if (a.vec_ok && xp + IR <= q0) {
@@ -269,6 +279,28 @@ void fused_inverse_level(const double* coef, long long ay, long long az, const u
     default: WRB_INV_LAUNCH(8); break;
     }
 #undef WRB_INV_LAUNCH
+    note_launch(1);
+}
+
+// One level in z-slab mode: bands (coefficient layout in x, y; strides bsy, bsz; own pair p at plane p - pair_lo + halo)
+// -> this rank's 2*nown output planes.  n2g: GLOBAL z extent of the level's box.
+void fused_inverse_level_bands(const double* lowb, const double* highb, long long bsy, long long bsz, int halo, int pair_lo,
+                               int nown, void* dst, int dst_is_f32, long long dsy, long long dsz, int n0, int n1, int n2g,
+                               cudaStream_t s)
+{
+    FusedInvArgs a{};
+    a.coef = nullptr; a.ay = bsy; a.az = 0; a.sym = nullptr; a.nlay = 0; a.lll = nullptr;
+    a.dst = dst; a.dsy = dsy; a.dsz = dsz; a.n0 = n0; a.n1 = n1; a.n2 = n2g;
+    a.lowb = lowb; a.highb = highb; a.bsz = bsz; a.pair_lo = pair_lo; a.nown = nown; a.halo = halo;
+    const size_t esz = dst_is_f32 ? 4 : 8;
+    a.vec_ok = ((reinterpret_cast<size_t>(dst) % 16) == 0 && (dsy * esz) % 16 == 0 && (dsz * esz) % 16 == 0) ? 1 : 0;
+    const int q0 = n0 / 2, q1 = n1 / 2;
+    const int gx = (q0 + IPX - 1) / IPX, gy = (q1 + IPY - 1) / IPY;
+    const int zp = pick_zpairs((long long)gx * gy, nown, 148, 4, 4);
+    a.zpairs = zp;
+    dim3 grid(gx, gy, (nown + zp - 1) / zp);
+    if (dst_is_f32) inv_level_fused_kernel<float, 0><<<grid, ITHREADS, 0, s>>>(a);
+    else inv_level_fused_kernel<double, 0><<<grid, ITHREADS, 0, s>>>(a);
     note_launch(1);
 }
 

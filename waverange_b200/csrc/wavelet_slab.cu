@@ -11,6 +11,7 @@
 // run unchanged on it; the coefficient VALUES are those of the global transform, bit for bit,
 // because the kernels below evaluate the same register windows (fwd_pairs / inv_pairs) with global
 // line indices and only remap where a plane is stored.
+#include <cstdlib>
 #include "wr_common.cuh"
 #include "wr_kernels.h"
 #include "wavelet_pairs.cuh"
@@ -115,6 +116,35 @@ __global__ void __launch_bounds__(128) build_bands_kernel(const double* __restri
     band[x + (long long)y * bsy + (long long)(pp + kHaloInv) * bsz] = v;
 }
 
+// the same, with the coefficients rebuilt from the symbol planes (fld = (q0*deps0 + min0) + (q1*deps1 + min1) + ...,
+// wrappers.cpp:480,513-514): no dequantise pass and no coefficient array in slab decoding
+struct BandDequant { const uint8_t* sym; unsigned long long lstride; int nlay; double deps[kNLayMax], minval[kNLayMax]; };
+
+__global__ void __launch_bounds__(128) build_bands_sym_kernel(BandDequant dq, long long ay, long long az,
+                                                              const double* __restrict__ lll, long long lsy, long long lsz,
+                                                              int q0, int q1, int n0, int n1, int nl,
+                                                              double* __restrict__ lowx, double* __restrict__ highx,
+                                                              long long bsy, long long bsz)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, p = blockIdx.z;                   // p in [0, 2*nl)
+    if (x >= n0) return;
+    double v;
+    if (lll != nullptr && x < q0 && y < q1 && p < nl) {
+        v = lll[x + (long long)y * lsy + (long long)p * lsz];
+    } else {
+        const uint8_t* __restrict__ q = dq.sym + (x + (long long)y * ay + (long long)p * az);
+        v = 0.0;
+        for (int l = 0; l < dq.nlay; l++) {
+            const double t = (double)q[(unsigned long long)l * dq.lstride] * dq.deps[l] + dq.minval[l];
+            v = (l == 0) ? t : v + t;
+        }
+    }
+    double* band = (p < nl) ? lowx : highx;
+    const int pp = (p < nl) ? p : p - nl;
+    band[x + (long long)y * bsy + (long long)(pp + kHaloInv) * bsz] = v;
+}
+
 template <class T>
 __global__ void __launch_bounds__(256) copy_convert_kernel(const double* __restrict__ src, T* __restrict__ dst, unsigned long long n)
 {
@@ -195,11 +225,53 @@ int wavelet_forward_slab(const void* src, int src_is_f32, double* coef, double* 
 }
 
 // Inverse, slab mode.  ext must hold 2 * (nzl/2 + 4) * nx * ny doubles.
+int wavelet_inverse_slab_fused_ok(int nx, int ny, int nz, int nzl, int levels)
+{
+    if (levels < 1 || getenv("WRB_NO_FUSED_INVERSE") != nullptr || (long long)nx * ny >= (1ll << 31)) return 0;
+    for (int k = 0; k < levels; k++) {
+        const int n0 = (nx + (1 << k) - 1) >> k, n1 = (ny + (1 << k) - 1) >> k;
+        if (!fused_inverse_supported(n0, n1, nz >> k) || ((nzl >> k) / 2) < 1) return 0;
+    }
+    return 1;
+}
+
 int wavelet_inverse_slab(double* coef, double* tmp, double* lllA, double* lllB, double* ext, void* out, int out_is_f32,
-                         int nx, int ny, int nz, int z0, int nzl, int levels, const SlabHooks& hk, cudaStream_t s)
+                         int nx, int ny, int nz, int z0, int nzl, int levels, const SlabHooks& hk, cudaStream_t s,
+                         const uint8_t* sym, unsigned long long lstride, int nlay, const double* deps, const double* minval)
 {
     const long long ay = nx, az = (long long)nx * ny;
     const double* lll = nullptr; long long lsy = 0, lsz = 0;
+    if (wavelet_inverse_slab_fused_ok(nx, ny, nz, nzl, levels)) {
+        // per level: band buffers (own pairs + halo room) from the symbols or the coefficient array, two halo
+        // exchanges, then ONE kernel for the z, y and x inverse lifting (wavelet_inv_fused.cu, band mode)
+        BandDequant dq{};
+        dq.sym = sym; dq.lstride = lstride; dq.nlay = nlay;
+        for (int l = 0; l < nlay && l < kNLayMax && sym != nullptr; l++) { dq.deps[l] = deps[l]; dq.minval[l] = minval[l]; }
+        for (int k = levels - 1; k >= 0; k--) {
+            const int n0 = (nx + (1 << k) - 1) >> k, n1 = (ny + (1 << k) - 1) >> k;
+            const int n2l = nzl >> k, n2g = nz >> k, zg = z0 >> k;
+            const int q0 = n0 / 2, q1 = n1 / 2, nl = n2l / 2;
+            const long long bsy = n0, bsz = (long long)n0 * n1;
+            double* lowx = ext;
+            double* highx = ext + (long long)(nl + 2 * kHaloInv) * bsz;
+            dim3 block(128, 1, 1), grid((n0 + 127) / 128, n1, 2 * nl);
+            if (sym != nullptr) build_bands_sym_kernel<<<grid, block, 0, s>>>(dq, ay, az, lll, lsy, lsz, q0, q1, n0, n1, nl, lowx, highx, bsy, bsz);
+            else build_bands_kernel<<<grid, block, 0, s>>>(coef, ay, az, lll, lsy, lsz, q0, q1, n0, n1, nl, lowx, highx, bsy, bsz);
+            note_launch(1);
+            if (hk.nranks > 1) {
+                int rc = hk.halo(hk.user, lowx, 8, bsz, nl, kHaloInv, kHaloInv);
+                if (rc) return rc;
+                rc = hk.halo(hk.user, highx, 8, bsz, nl, kHaloInv, kHaloInv);
+                if (rc) return rc;
+            }
+            double* nxt = (k & 1) ? lllA : lllB;
+            fused_inverse_level_bands(lowx, highx, bsy, bsz, kHaloInv, zg / 2, nl, (k == 0) ? out : (void*)nxt,
+                                      (k == 0) ? out_is_f32 : 0, (k == 0) ? ay : (long long)n0,
+                                      (k == 0) ? az : (long long)n0 * n1, n0, n1, n2g, s);
+            lll = nxt; lsy = n0; lsz = (long long)n0 * n1;
+        }
+        return 0;
+    }
     for (int k = levels - 1; k >= 0; k--) {
         const int n0 = (nx + (1 << k) - 1) >> k, n1 = (ny + (1 << k) - 1) >> k;
         const int n2l = nzl >> k, n2g = nz >> k, zg = z0 >> k;

@@ -36,8 +36,13 @@ struct SlabHooks { int rank = 0, nranks = 1; HaloFn halo = nullptr; ReduceFn red
 int wavelet_slab_supported(int nx, int ny, int nz, int z0, int nzl, int levels);
 int wavelet_forward_slab(const void* src, int src_is_f32, double* coef, double* tmp, double* lllA, double* lllB, int nx,
                          int ny, int nz, int z0, int nzl, int levels, DevState* st, const SlabHooks& hk, cudaStream_t s);
+// sym != null (flat symbol planes of the rank-local array, layer l at sym + l*lstride): the band buffers are built
+// straight from the symbols -- no dequantise pass, coef untouched; needs wavelet_inverse_slab_fused_ok()
 int wavelet_inverse_slab(double* coef, double* tmp, double* lllA, double* lllB, double* ext, void* out, int out_is_f32,
-                         int nx, int ny, int nz, int z0, int nzl, int levels, const SlabHooks& hk, cudaStream_t s);
+                         int nx, int ny, int nz, int z0, int nzl, int levels, const SlabHooks& hk, cudaStream_t s,
+                         const uint8_t* sym = nullptr, unsigned long long lstride = 0, int nlay = 0,
+                         const double* deps = nullptr, const double* minval = nullptr);
+int wavelet_inverse_slab_fused_ok(int nx, int ny, int nz, int nzl, int levels);
 
 // ---- wavelet_fused.cu ---------------------------------------------------------------------
 bool fused_forward_supported(int n0, int n1, int n2);
@@ -52,6 +57,10 @@ bool fused_inverse_supported(int n0, int n1, int n2);
 void fused_inverse_level(const double* coef, long long ay, long long az, const uint8_t* sym, unsigned long long lstride,
                          int nlay, const double* deps, const double* minval, const double* lll, void* dst,
                          int dst_is_f32, long long dsy, long long dsz, int n0, int n1, int n2, cudaStream_t s);
+
+void fused_inverse_level_bands(const double* lowb, const double* highb, long long bsy, long long bsz, int halo, int pair_lo,
+                               int nown, void* dst, int dst_is_f32, long long dsy, long long dsz, int n0, int n1, int n2g,
+                               cudaStream_t s);
 
 // ---- quant.cu -----------------------------------------------------------------------------
 // Geometry of the chunked symbol container of one layer.
