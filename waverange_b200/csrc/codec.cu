@@ -237,13 +237,30 @@ static int grid_for(unsigned long long n)
 // ------------------------------------------------------------------------------------------
 struct SlabGeom { int nz_global, z0; };   // slab mode: the nz passed around is the LOCAL plane count
 
-static int ensure_transform_buffers(wrb_codec* c, int nx, int ny, int nz, bool slab = false)
+// Does the transform of an (nx, ny, nz) field go through the one-pass-per-level kernels at every level?  Then neither
+// direction needs the full-size scratch `tmp`, and decoding from symbols does not need the coefficient array either
+// (same predicates as wavelet_forward / wavelet_inverse in wavelet.cu).
+static bool all_levels_fused(int nx, int ny, int nz, int levels)
+{
+    if (levels <= 0 || (long long)nx * ny >= (1ll << 31) || getenv("WRB_NO_FUSED_INVERSE") != nullptr) return false;
+    int n0 = nx, n1 = ny, n2 = nz;
+    for (int k = 0; k < levels; k++) {
+        if (!fused_forward_supported(n0, n1, n2) || !fused_inverse_supported(n0, n1, n2)) return false;
+        n0 = half_up(n0); n1 = half_up(n1); n2 = half_up(n2);
+    }
+    return true;
+}
+
+// scratch of the transform.  need_coef / need_tmp: see all_levels_fused(); the z-slab mode always takes both
+// (its level-1 input is copied into `tmp` with halo room, its inverse may fall back to the line passes)
+static int ensure_transform_buffers(wrb_codec* c, int nx, int ny, int nz, bool slab = false, bool need_coef = true,
+                                    bool need_tmp = true)
 {
     const size_t ntot = (size_t)nx * ny * nz;
     const size_t m1 = (size_t)half_up(nx) * half_up(ny) * half_up(nz);
     const size_t m2 = (size_t)half_up(half_up(nx)) * half_up(half_up(ny)) * half_up(half_up(nz));
-    CK(c->coef.ensure(ntot * 8));
-    CK(c->tmp.ensure((ntot + (slab ? 7ull * nx * ny : 0ull)) * 8));
+    if (need_coef || slab) CK(c->coef.ensure(ntot * 8));
+    if (need_tmp || slab) CK(c->tmp.ensure((ntot + (slab ? 7ull * nx * ny : 0ull)) * 8));
     if (slab) CK(c->ext.ensure(((size_t)nz + 8) * nx * ny * 8));
     const size_t h1 = slab ? 7ull * half_up(nx) * half_up(ny) : 0, h2 = slab ? 7ull * half_up(half_up(nx)) * half_up(half_up(ny)) : 0;
     CK(c->lllA.ensure((m1 + h1) * 8 + 64));      // slab mode: room for 4 + 3 halo planes
@@ -342,7 +359,7 @@ static int run_transform_and_quantise(wrb_codec* c, const void* d_field, int dty
     if (c->timing) cudaEventRecord(c->ev[1], s);
     const unsigned long long lstride = (unsigned long long)g.nchunks * g.pitch;
     const unsigned long long hstride = (unsigned long long)g.nblocks * 256;
-    CK(cudaMemsetAsync(c->hist.p, 0, (size_t)kNLayMax * hstride * 4, s));     // the quantiser adds partial histograms
+    CK(cudaMemsetAsync(c->hist.p, 0, (size_t)nlayers * hstride * 4, s));      // the quantiser adds partial histograms
     for (int l = 0; l < nlayers; l++) {
         // global extrema of the coefficients (l == 0) / of the residual left by layer l-1 (wrappers.cpp:308-314)
         if (dist && reduce_extrema(c, &st->rmin_key[l], &st->rmax_key[l])) return fail(c, WRB_E_CUDA, "reduce callback failed");
@@ -379,8 +396,9 @@ static int encode_impl(wrb_codec* c, const void* d_field, int dtype, int nx, int
     const ChunkGeom g = make_geom(ntot, chunk_len_of(c), (unsigned)c->seek_points);
     const int chunked = c->chunk_blocks > 0;
     int rc;
-    if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr))) return rc;
-    if ((rc = ensure_coder_buffers(c, g, kNLayMax, true))) return rc;
+    const bool fused_all = sg == nullptr && all_levels_fused(nx, ny, nz, wtflag ? kWavLvl : 0);
+    if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr, true, !fused_all))) return rc;
+    if ((rc = ensure_coder_buffers(c, g, nlayers, true))) return rc;      // symbols, histograms and coder scratch of the layers launched
     DevState* st = (DevState*)c->state.p;
     cudaStream_t s = c->stream;
     if ((rc = run_transform_and_quantise(c, d_field, dtype, nx, ny, nz, wtflag, tolrel, g, sg, nlayers))) return rc;
@@ -562,7 +580,9 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
     if (g.nseek != nseek) return fail(c, WRB_E_FORMAT, "seek table does not match the chunk geometry");
     if (getenv("WRB_DEC_PADDED") == nullptr) g.pitch = g.chunk_len;        // decoded symbols are kept flat (array order): the inverse transform indexes them directly
     int rc;
-    if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr))) return rc;
+    const bool fused_all = sg == nullptr && all_levels_fused(nx, ny, nz, (int)hdr->wlev) && nz >= (1 << hdr->wlev) &&
+                           getenv("WRB_NO_FUSED_DEQUANT") == nullptr;
+    if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr, !fused_all, !fused_all))) return rc;
     if ((rc = ensure_coder_buffers(c, g, nlay, false))) return rc;
     int* d_err = (int*)c->misc.p;
     CK(cudaMemsetAsync(d_err, 0, sizeof(int), s));
