@@ -15,6 +15,8 @@
                                  (SURVEY.md section 8c).  Used as the CPU timing baseline.
      wrenc_ref, wrdec_ref        the reference's generic front-ends (strict flags), used by the
                                  .wrh/.wrb file-format parity tests
+     wrmssgenc_ref, wrmssgdec_ref  the reference's MSSG front-ends (strict flags), used by the MSSG
+                                 file-layout parity tests
    The reference's own Makefiles are not run: three C/C++ files are compiled
    directly (src/core/Makefile:6-23 lists the same three objects).
 """
@@ -86,6 +88,21 @@ def build_ref(force=False):
     for exe, main in (("wrenc_ref", "gen_enc.cpp"), ("wrdec_ref", "gen_dec.cpp")):
         out = os.path.join(outdir, exe)
         srcs = [os.path.join(gen, main), os.path.join(gen, "gen_aux.cpp"), wrap]
+        if force or newer(out, srcs + [wav, rc, __file__]):
+            cobjs = []
+            for s in (wav, rc):
+                o = os.path.join(outdir, "%s_cli.o" % os.path.basename(s)[:-2])
+                run(["gcc", "-c"] + strict + ["-o", o, s])
+                cobjs.append(o)
+            run(["g++"] + strict + ["-D__STDC_LIMIT_MACROS", "-o", out] + srcs + cobjs)
+            for o in cobjs:
+                os.remove(o)
+        outs[exe] = out
+    # the reference's MSSG front-ends: src/mssg/mssg_enc.cpp | mssg_dec.cpp + ctrl_aux.cpp + the library (Makefile:24-28)
+    mssg = os.path.join(src, "mssg")
+    for exe, main in (("wrmssgenc_ref", "mssg_enc.cpp"), ("wrmssgdec_ref", "mssg_dec.cpp")):
+        out = os.path.join(outdir, exe)
+        srcs = [os.path.join(mssg, main), os.path.join(mssg, "ctrl_aux.cpp"), wrap]
         if force or newer(out, srcs + [wav, rc, __file__]):
             cobjs = []
             for s in (wav, rc):

@@ -48,6 +48,17 @@ class FieldRecord(C.Structure):
     _fields_ = [("desc", FieldDesc), ("recl", C.c_ubyte * 8), ("hdr", Header)]
 
 
+class MssgCtl(C.Structure):
+    """wrb_mssg_ctl (include/waverange_mssg.h): what the MSSG front-end takes from a GrADS .ctl file."""
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("nt", C.c_int), ("undef", C.c_double), ("dset", C.c_char * 256)]
+
+
+class MssgNmlst(C.Structure):
+    """wrb_mssg_nmlst: grid, process grid and record table of an MSSG restart .nmlst file."""
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("nprocx", C.c_int), ("nprocy", C.c_int), ("ndset", C.c_int),
+                ("dset", (C.c_char * 256) * 50)]
+
+
 class WaveRangeError(RuntimeError):
     pass
 
@@ -66,6 +77,8 @@ EXPORTS = ["wrb_create", "wrb_destroy", "wrb_last_error", "wrb_set_stream", "wrb
            "wrb_range_encode_device", "wrb_range_decode_device", "wrb_ind_p2w_3d", "wrb_set_timing",
            "wrb_last_stage_ms",
            "wrb_wrh_begin", "wrb_wrh_append", "wrb_wrh_read", "wrb_file_encode", "wrb_file_decode", "wrb_file_last_error",
+           "wrb_mssg_read_ctl", "wrb_mssg_read_nmlst", "wrb_mssg_header_begin", "wrb_mssg_header_time", "wrb_mssg_header_append",
+           "wrb_mssg_header_read", "wrb_mssg_encode", "wrb_mssg_decode", "wrb_mssg_last_error",
            "encoding_wrap", "decoding_wrap", "setup_wr", "encoding_wrap_f", "decoding_wrap_f", "setup_wr_f"]
 
 
@@ -119,6 +132,16 @@ def lib():
     L.wrb_file_decode.argtypes = [vp, cp, cp, cp, i, i]
     L.wrb_file_last_error.argtypes = []
     L.wrb_file_last_error.restype = cp
+    L.wrb_mssg_read_ctl.argtypes = [cp, C.POINTER(MssgCtl)]
+    L.wrb_mssg_read_nmlst.argtypes = [cp, C.POINTER(MssgNmlst)]
+    L.wrb_mssg_header_begin.argtypes = [cp, cp, cp, i, i, i, d]
+    L.wrb_mssg_header_time.argtypes = [cp, cp, C.POINTER(d)]
+    L.wrb_mssg_header_append.argtypes = [cp, i, cp, H]
+    L.wrb_mssg_header_read.argtypes = [cp, i, C.POINTER(d), C.POINTER(i), C.POINTER(i), vp, H, i]
+    L.wrb_mssg_encode.argtypes = [vp, cp, cp, i, i, i, d, i]
+    L.wrb_mssg_decode.argtypes = [vp, cp, cp, cp, i, i, i, i]
+    L.wrb_mssg_last_error.argtypes = []
+    L.wrb_mssg_last_error.restype = cp
     f64p, u8p, ulp = C.POINTER(d), C.POINTER(C.c_ubyte), C.POINTER(ul)
     L.encoding_wrap.argtypes = [i, i, i, f64p, i, i, i, i, f64p, f64p, f64p, f64p, u8p, u8p, ulp, f64p, f64p, ulp, u8p]
     L.encoding_wrap.restype = None
@@ -154,6 +177,48 @@ def wrh_read(path):
     recs = (FieldRecord * max(1, n.value))()
     _fck(lib().wrb_wrh_read(path.encode(), C.byref(n), recs, n.value))
     return list(recs)[:n.value]
+
+
+# ---- MSSG files (include/waverange_mssg.h) --------------------------------------------------------
+def _mck(rc):
+    if rc != 0:
+        raise WaveRangeError("%s (code %d)" % (lib().wrb_mssg_last_error().decode(), rc))
+
+
+def mssg_read_ctl(path):
+    """GrADS control file of MSSG regular output (reference ctrl_aux.cpp:217-320) -> dict"""
+    g = MssgCtl()
+    _mck(lib().wrb_mssg_read_ctl(path.encode(), C.byref(g)))
+    return dict(nx=g.nx, ny=g.ny, nz=g.nz, nt=g.nt, undef=g.undef, dset=g.dset.decode())
+
+
+def mssg_read_nmlst(path):
+    """MSSG restart namelist (reference ctrl_aux.cpp:49-213) -> dict"""
+    m = MssgNmlst()
+    _mck(lib().wrb_mssg_read_nmlst(path.encode(), C.byref(m)))
+    return dict(nx=m.nx, ny=m.ny, nz=m.nz, nprocx=m.nprocx, nprocy=m.nprocy, ndset=m.ndset,
+                dset=[m.dset[k].value.decode() for k in range(m.ndset)])
+
+
+def mssg_header_read(path, filetype):
+    """all of an MSSG encoding header -> (time record or None, [(id, name, Header)])  (reference ctrl_aux.cpp:538-585)"""
+    n = C.c_int()
+    t = (C.c_double * 15)()
+    _mck(lib().wrb_mssg_header_read(path.encode(), filetype, t, C.byref(n), None, None, None, 0))
+    k = max(1, n.value)
+    ids, names, hdrs = (C.c_int * k)(), ((C.c_char * 256) * k)(), (Header * k)()
+    _mck(lib().wrb_mssg_header_read(path.encode(), filetype, t, C.byref(n), ids, C.cast(names, C.c_void_p), hdrs, n.value))
+    return (list(t) if filetype else None), [(ids[j], names[j].value.decode(), hdrs[j]) for j in range(n.value)]
+
+
+def mssg_header_write(path, prefix, ext, filetype, nbytes, endianflip, tol_base, time_name, time_rec, records):
+    """preamble, the time record (types 1/2) and one record per (0-based id, name, Header)
+    (reference mssg_enc.cpp:273-284, 459-486, ctrl_aux.cpp:498-535)"""
+    _mck(lib().wrb_mssg_header_begin(path.encode(), prefix.encode(), ext.encode(), filetype, nbytes, endianflip, tol_base))
+    if filetype:
+        _mck(lib().wrb_mssg_header_time(path.encode(), time_name.encode(), (C.c_double * 15)(*time_rec)))
+    for idset, name, h in records:
+        _mck(lib().wrb_mssg_header_append(path.encode(), idset, name.encode(), C.byref(h)))
 
 
 def wrh_write(path, encoded_name, filetype, endianflip, records):
@@ -279,6 +344,15 @@ class Codec:
         """wrdec (reference gen_dec.cpp)"""
         _fck(self.L.wrb_file_decode(self.h, encoded_name.encode(), header_name.encode(), out_name.encode(), filetype,
                                     endianflip))
+
+    def mssg_encode(self, prefix, ext, filetype, nbytes, endianflip, tol_base, procid=0):
+        """wrmssgenc (reference mssg_enc.cpp): file names derive from the prefix, relative to the working directory"""
+        _mck(self.L.wrb_mssg_encode(self.h, prefix.encode(), ext.encode(), filetype, nbytes, endianflip, tol_base, procid))
+
+    def mssg_decode(self, in_prefix, ext, out_prefix, filetype, nbytes, endianflip, procid=0):
+        """wrmssgdec (reference mssg_dec.cpp)"""
+        _mck(self.L.wrb_mssg_decode(self.h, in_prefix.encode(), ext.encode(), out_prefix.encode(), filetype, nbytes,
+                                    endianflip, procid))
 
     def set_stream(self, stream_handle):
         self._ck(self.L.wrb_set_stream(self.h, C.c_void_p(stream_handle)))

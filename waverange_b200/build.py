@@ -13,11 +13,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwaverange_b200.so")
-SOURCES = ["codec.cu", "wavelet.cu", "wavelet_fused.cu", "wavelet_inv_fused.cu", "wavelet_slab.cu", "quant.cu", "rangecoder.cu", "compat.cpp", "wrfile.cpp"]
+SOURCES = ["codec.cu", "wavelet.cu", "wavelet_fused.cu", "wavelet_inv_fused.cu", "wavelet_slab.cu", "quant.cu", "rangecoder.cu", "compat.cpp", "wrfile.cpp", "mssgfile.cpp"]
 HEADERS = ["wr_common.cuh", "wr_kernels.h", "wavelet_pairs.cuh", "../../include/waverange_b200.h", "../../include/waverange.h",
-           "../../include/waverange_files.h", "cli/wrenc.cpp", "cli/wrdec.cpp"]
+           "../../include/waverange_files.h", "../../include/waverange_mssg.h", "cli/wrenc.cpp", "cli/wrdec.cpp",
+           "cli/wrmssgenc.cpp", "cli/wrmssgdec.cpp"]
 BIN = os.path.join(HERE, "bin")
-CLI = ["wrenc", "wrdec"]
+CLI = ["wrenc", "wrdec", "wrmssgenc", "wrmssgdec"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -67,7 +68,8 @@ def build(force=False, verbose=False):
     subprocess.check_call(cmd)
     for o in objs:
         os.remove(o)
-    # the generic front-ends (reference bin/generic/wrenc, wrdec): thin mains over wrb_file_encode / wrb_file_decode
+    # the generic and MSSG front-ends (reference bin/generic/wrenc, wrdec, bin/mssg/wrmssgenc, wrmssgdec): thin mains over
+    # wrb_file_encode / wrb_file_decode / wrb_mssg_encode / wrb_mssg_decode
     os.makedirs(BIN, exist_ok=True)
     for name in CLI:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", os.path.join(BIN, name), os.path.join(CSRC, "cli", name + ".cpp"),
