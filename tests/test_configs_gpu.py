@@ -130,7 +130,7 @@ def test_c3_1024_f64_tol1e8_properties(codec, torch_cuda, oracle):
         assert hdr[:4] == b"WRCK"
         nseek = int.from_bytes(hdr[28:32], "little")
         lens = np.frombuffer(blob[off + 32:off + 32 + 4 * nch].cpu().numpy().tobytes(), dtype="<u4")
-        starts = off + 32 + 4 * nch + 12 * nseek * nch + np.concatenate([[0], np.cumsum(lens[:-1], dtype=np.int64)])
+        starts = off + 32 + 4 * nch + 10 * nseek * nch + np.concatenate([[0], np.cumsum(lens[:-1], dtype=np.int64)])
         for c in (0, 1, nch // 3, nch - 2, nch - 1):
             s0 = c * L1
             s1 = min(n ** 3, s0 + L1)

@@ -185,6 +185,51 @@ def test_encode_chunks_bit_exact_and_decode(codec, torch_cuda, oracle, shape, to
     assert np.abs(want_rec - f).max() <= tol * np.abs(f).max()
 
 
+@pytest.mark.parametrize("nseek", [-1, 0, 1, 3, 7])
+def test_seek_points_change_neither_streams_nor_reconstruction(product_lib, torch_cuda, oracle, nseek):
+    """Seek points (decoder entry points inside a chunk) only add table bytes: for every setting the chunk streams are the
+    oracle's and the decoder -- running nseek+1 lanes per chunk -- returns the reference's reconstruction.  The field has a
+    short last chunk (lanes without work, unused table entries).  -1 = the encoder's own choice, bounded to keep the
+    container within 1 % of the reference's streams."""
+    from waverange_b200 import api
+    shape, tol = (70, 64, 96), 1e-7                      # 430080 symbols: 7 full chunks + one of 10087
+    f = oracle.probe_field(shape, seed=11, nm=20)
+    c = api.Codec(device=0)
+    c.set_seek_points(nseek)
+    h, out = encode_dev(c, torch_cuda, f, tol)
+    want = oracle.encode(f, tol, chunk_len=L1)
+    whole = oracle.encode(f, tol)
+    blob = out[:h.ntot_enc].cpu().numpy()
+    off, woff, kept = 0, 0, set()
+    for l in range(h.nlay):
+        layer = blob[off:off + h.len_enc_vec[l]]
+        assert bytes(layer[:4]) == b"WRCK" and int.from_bytes(bytes(layer[4:8]), "little") == 3
+        kept.add(int.from_bytes(bytes(layer[28:32]), "little"))
+        _, streams = api.parse_container(layer)
+        for k, s in enumerate(streams):
+            n = int(want["chunk_lens"][l][k])
+            assert s == want["data"][woff:woff + n].tobytes(), "layer %d chunk %d" % (l, k)
+            woff += n
+        off += h.len_enc_vec[l]
+    assert len(kept) == 1                                 # one geometry for all layers
+    k = kept.pop()
+    nchunks = want["chunk_lens"].shape[1]
+    streams_total = int(want["chunk_lens"][:h.nlay].sum())
+    assert h.ntot_enc == streams_total + h.nlay * (32 + nchunks * (4 + 10 * k))
+    if nseek >= 0:
+        assert k == nseek
+    else:
+        assert k in (0, 1, 3, 7) and h.ntot_enc <= 1.01 * whole["header"].ntot_enc
+        assert h.nlay * nchunks * (4 + 10 * k) <= 0.0085 * streams_total
+        if k < 7:
+            assert h.nlay * nchunks * (4 + 10 * (2 * k + 1)) > 0.0085 * streams_total     # as many as the budget allows
+    nz, ny, nx = shape
+    rec = torch_cuda.zeros(f.size, dtype=torch_cuda.float64, device="cuda")
+    c.decode_device(rec.data_ptr(), F64, nx, ny, nz, h, out.data_ptr())
+    assert bits_equal(rec.cpu().numpy().reshape(shape), oracle.decode(shape, whole["header"], whole["data"]))
+    c.close()
+
+
 @pytest.mark.parametrize("key", ["e2e_a", "e2e_b", "e2e_c", "e2e_d"])
 def test_single_stream_mode_is_byte_identical_to_reference(codec, torch_cuda, golden, key):
     """chunk_blocks = 0: data_enc, lengths and header doubles equal encoding_wrap() of the reference."""

@@ -288,12 +288,12 @@ def parse_container(layer_bytes):
     b = bytes(layer_bytes)
     if b[:4] != b"WRCK":
         return 0, [b]
-    assert int.from_bytes(b[4:8], "little") == 2, "container version"
+    assert int.from_bytes(b[4:8], "little") in (2, 3), "container version"
     chunk_len = int.from_bytes(b[8:16], "little")
     nch = int.from_bytes(b[24:28], "little")
     nseek = int.from_bytes(b[28:32], "little")
     lens = np.frombuffer(b, dtype="<u4", count=nch, offset=32)
-    off = 32 + 4 * nch + 12 * nseek * nch
+    off = 32 + 4 * nch + 10 * nseek * nch          # version 3: 10-byte seek entries (version 2 is only read without them)
     out = []
     for n in lens:
         out.append(b[off:off + int(n)])

@@ -43,7 +43,7 @@ struct wrb_codec {
     int device = 0;
     cudaStream_t stream = nullptr;
     int chunk_blocks = 1;
-    int seek_points = 3;             // decoder entry points inside a chunk (4 lanes decode one chunk)
+    int seek_points = -1;            // decoder entry points inside a chunk; -1: the encoder decides (assemble_container)
     std::string err;
     DevBuf coef, tmp, lllA, lllB, sym, hist, slots, lens, dstoff, seek, state, blob, field, offs, layoff, misc, ext, lcut;
     int lc_mx = 0, lc_my = 0, lc_mz = 0;      // local cutoff grid (0: off), wrb_set_local_cutoff
@@ -138,7 +138,7 @@ int wrb_set_local_cutoff(wrb_codec* c, int mx, int my, int mz, const double* cut
     c->lc_mx = mx; c->lc_my = my; c->lc_mz = mz; c->lc_min = mn;
     return 0;
 }
-int wrb_set_seek_points(wrb_codec* c, int n) { if (!c || n < 0 || n > 15) return WRB_E_ARG; c->seek_points = n; return 0; }
+int wrb_set_seek_points(wrb_codec* c, int n) { if (!c || n < -1 || n > 15) return WRB_E_ARG; c->seek_points = n; return 0; }
 unsigned long long wrb_launch_count(const wrb_codec*) { return g_launches.load(); }
 int wrb_set_timing(wrb_codec* c, int on) { if (!c) return WRB_E_ARG; c->timing = on; return 0; }
 int wrb_last_stage_ms(const wrb_codec* c, float ms[4])
@@ -277,7 +277,7 @@ static int ensure_coder_buffers(wrb_codec* c, const ChunkGeom& g, int nlayers, b
         CK(c->slots.ensure((size_t)nlayers * g.nchunks * chunk_slot_pitch(g)));
         CK(c->lens.ensure((size_t)nlayers * g.nchunks * 8));
         CK(c->dstoff.ensure((size_t)nlayers * g.nchunks * 8));
-        CK(c->seek.ensure((size_t)nlayers * g.nchunks * (g.nseek ? g.nseek : 1) * 12 + 64));
+        CK(c->seek.ensure((size_t)nlayers * g.nchunks * (g.nseek ? g.nseek : 1) * 12 + 64));      // scratch: three words per recorded point
     }
     CK(c->offs.ensure((size_t)nlayers * g.nchunks * 8 + 64));
     CK(c->layoff.ensure(16 * 8));
@@ -393,7 +393,7 @@ static int encode_impl(wrb_codec* c, const void* d_field, int dtype, int nx, int
         return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
     CK(cudaSetDevice(c->device));
     const unsigned long long ntot = (unsigned long long)nx * ny * nz;
-    const ChunkGeom g = make_geom(ntot, chunk_len_of(c), (unsigned)c->seek_points);
+    const ChunkGeom g = make_geom(ntot, chunk_len_of(c), c->seek_points < 0 ? 7u : (unsigned)c->seek_points);
     const int chunked = c->chunk_blocks > 0;
     int rc;
     const bool fused_all = sg == nullptr && all_levels_fused(nx, ny, nz, wtflag ? kWavLvl : 0);
@@ -409,7 +409,7 @@ static int encode_impl(wrb_codec* c, const void* d_field, int dtype, int nx, int
                         (uint8_t*)c->slots.p, sp, (unsigned long long*)c->lens.p, (uint32_t*)c->seek.p, s);
     if (c->timing) cudaEventRecord(c->ev[3], s);
     assemble_container((const uint8_t*)c->slots.p, sp, (const unsigned long long*)c->lens.p, (const uint32_t*)c->seek.p, g,
-                       chunked, st, d_data_enc, cap, (unsigned long long*)c->dstoff.p, s);
+                       chunked, c->seek_points < 0, st, d_data_enc, cap, (unsigned long long*)c->dstoff.p, s);
     if (c->timing) cudaEventRecord(c->ev[4], s);
     CK(cudaMemcpyAsync(c->h_state, st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -464,7 +464,7 @@ static int quantise_impl(wrb_codec* c, const void* d_field, int dtype, int nx, i
         return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
     CK(cudaSetDevice(c->device));
     const unsigned long long ntot = (unsigned long long)nx * ny * nz;
-    const ChunkGeom g = make_geom(ntot, chunk_len_of(c), (unsigned)c->seek_points);
+    const ChunkGeom g = make_geom(ntot, chunk_len_of(c), c->seek_points < 0 ? 7u : (unsigned)c->seek_points);
     int rc;
     if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr))) return rc;
     if ((rc = ensure_coder_buffers(c, g, kNLayMax, false))) return rc;
@@ -571,7 +571,8 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
         unsigned long long nsym = 0, nch = 0, ver = 0;
         for (int k = 0; k < 8; k++) { chunk_len |= (unsigned long long)peek[8 + k] << (8 * k); nsym |= (unsigned long long)peek[16 + k] << (8 * k); }
         for (int k = 0; k < 4; k++) { ver |= (unsigned long long)peek[4 + k] << (8 * k); nch |= (unsigned long long)peek[24 + k] << (8 * k); nseek |= (unsigned long long)peek[28 + k] << (8 * k); }
-        if (ver != 2 || nsym != ntot || chunk_len == 0 || chunk_len > ntot || nch != (ntot + chunk_len - 1) / chunk_len || nseek > 15)
+        // version 3: 10-byte seek entries on nested grids; a version-2 container without seek points has the same layout
+        if (!(ver == 3 || (ver == 2 && nseek == 0)) || nsym != ntot || chunk_len == 0 || chunk_len > ntot || nch != (ntot + chunk_len - 1) / chunk_len || nseek > 15)
             return fail(c, WRB_E_FORMAT, "chunk container header does not match the field size");
     } else if (npeek >= 1 && peek[0] != 0x00) {
         return fail(c, WRB_E_FORMAT, "layer is neither a WRCK container nor a reference stream");
@@ -739,7 +740,7 @@ int wrb_range_encode_device(wrb_codec* c, const unsigned char* d_sym, unsigned l
     const unsigned long long sp = chunk_slot_pitch(g);
     range_encode_chunks((const uint8_t*)c->sym.p, 0, (const uint32_t*)c->hist.p, 0, g, 1, nullptr, (uint8_t*)c->slots.p, sp,
                         (unsigned long long*)c->lens.p, (uint32_t*)c->seek.p, s);
-    assemble_container((const uint8_t*)c->slots.p, sp, (const unsigned long long*)c->lens.p, (const uint32_t*)c->seek.p, g, 0,
+    assemble_container((const uint8_t*)c->slots.p, sp, (const unsigned long long*)c->lens.p, (const uint32_t*)c->seek.p, g, 0, 0,
                        st, d_out, cap, (unsigned long long*)c->dstoff.p, s);
     CK(cudaMemcpyAsync(c->h_state, st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
     if (lens) {

@@ -29,11 +29,15 @@ ChunkGeom make_geom(unsigned long long ntot, unsigned long long chunk_len, unsig
     g.nseek = 0;
     g.sub_len = 0;
     if (nseek_req >= 7) nseek_req = 7; else if (nseek_req >= 3) nseek_req = 3; else if (nseek_req >= 1) nseek_req = 1;   // 2, 4 or 8 lanes per chunk
-    if (nseek_req > 0 && g.blocks_per_chunk == 1 && g.chunk_len >= 64ull * (nseek_req + 1)) {
-        g.nseek = nseek_req;
-        unsigned long long sub = (g.chunk_len + nseek_req) / (nseek_req + 1);      // ceil(chunk_len / nsub)
-        g.sub_len = (unsigned int)((sub + 15ull) & ~15ull);
-        if ((unsigned long long)g.nseek * g.sub_len >= g.chunk_len) { g.nseek = 0; g.sub_len = 0; }   // no empty tails
+    // Seek grids are nested: the finest one (7 points) has spacing base = ceil16(ceil(chunk_len / 8)), the grids of 3 and
+    // of 1 point are every 2nd / 4th point of it.  An encoder can so record the finest grid and decide afterwards how
+    // many points the container keeps.  The largest grid <= the request whose last sub-range is not empty is granted.
+    if (nseek_req > 0 && g.blocks_per_chunk == 1 && g.chunk_len >= 512) {
+        const unsigned long long base = (((g.chunk_len + 7ull) / 8ull) + 15ull) & ~15ull;
+        for (unsigned int n = nseek_req; n >= 1; n = (n - 1) / 2) {
+            const unsigned long long sub = base * (8u / (n + 1));
+            if ((unsigned long long)n * sub < g.chunk_len) { g.nseek = n; g.sub_len = (unsigned int)sub; break; }
+        }
     }
     return g;
 }
@@ -47,7 +51,7 @@ __global__ void state_init_kernel(DevState* st)
         st->span[l] = 0;
     }
     st->tolabs = 0; st->midval = 0; st->halfspan = 0;
-    st->nlay = 0; st->done = 0; st->trivial = 0; st->error = 0; st->ntot_enc = 0;
+    st->nlay = 0; st->done = 0; st->trivial = 0; st->error = 0; st->ntot_enc = 0; st->nseek_keep = 0;
 }
 void state_init(DevState* st, cudaStream_t s) { state_init_kernel<<<1, 1, 0, s>>>(st); note_launch(1); }
 

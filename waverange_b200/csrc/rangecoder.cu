@@ -254,24 +254,53 @@ __device__ __forceinline__ void put_le(uint8_t* p, unsigned long long v, int nby
     for (int k = 0; k < nbytes; k++) p[k] = (uint8_t)(v >> (8 * k));
 }
 
-__host__ __device__ inline unsigned long long container_header_bytes(const ChunkGeom& g, int chunked)
+constexpr unsigned int kSeekBytes = 10;       // u32 low, u32 range, u16 stream position relative to the previous point
+constexpr unsigned int kContainerVersion = 3;
+
+__host__ __device__ inline unsigned long long container_header_bytes(const ChunkGeom& g, int chunked, unsigned int nseek)
 {
-    return chunked ? 32ull + 4ull * g.nchunks + 12ull * g.nseek * g.nchunks : 0ull;
+    return chunked ? 32ull + 4ull * g.nchunks + (unsigned long long)kSeekBytes * nseek * g.nchunks : 0ull;
 }
 
+// Seek points cost bytes (10 per point and chunk) and buy decoder lanes.  With seek_auto the container keeps the
+// fewest points of the recorded grid that give the decoder kSeekLaneTarget lanes over all layers (about three warps
+// per scheduler of a B200: more does not decode faster), and never more than kSeekBudget of the coded bytes for the
+// chunk tables (length + seek entries) -- the container stays within 1 % of the reference's layer streams.
+constexpr unsigned long long kSeekLaneTarget = 50000ull;
+constexpr double kSeekBudget = 0.0085;
+
 __global__ void __launch_bounds__(1024) assemble_scan_kernel(const unsigned long long* __restrict__ lens, ChunkGeom g,
-                                                             int chunked, DevState* st, uint8_t* __restrict__ blob,
-                                                             unsigned long long cap,
+                                                             int chunked, int seek_auto, DevState* st,
+                                                             uint8_t* __restrict__ blob, unsigned long long cap,
                                                              unsigned long long* __restrict__ dst_off)
 {
     __shared__ unsigned long long s_part[1024];
     __shared__ unsigned long long s_base;
+    __shared__ unsigned int s_keep;
     const int t = threadIdx.x;
     const unsigned int per = (g.nchunks + 1023) / 1024;
     const unsigned int c0 = t * per, c1 = (c0 + per < g.nchunks) ? c0 + per : g.nchunks;
-    if (t == 0) s_base = 0;
-    __syncthreads();
     const int nlay = st->nlay;
+    if (t == 0) { s_base = 0; s_keep = chunked ? g.nseek : 0; }
+    if (chunked && seek_auto && g.nseek > 0) {            // how many of the recorded seek points to keep (one answer for all layers)
+        unsigned long long sum = 0;
+        for (int l = 0; l < nlay; l++)
+            for (unsigned int c = c0; c < c1; c++) sum += lens[(unsigned long long)l * g.nchunks + c];
+        s_part[t] = sum;
+        __syncthreads();
+        for (int o = 512; o > 0; o >>= 1) { if (t < o) s_part[t] += s_part[t + o]; __syncthreads(); }
+        if (t == 0) {
+            const unsigned long long chunks = (unsigned long long)g.nchunks * (unsigned long long)(nlay > 0 ? nlay : 1);
+            const double budget = kSeekBudget * (double)s_part[0];
+            unsigned int keep = g.nseek;
+            while (keep > 0 && chunks * ((keep - 1) / 2 + 1) >= kSeekLaneTarget) keep = (keep - 1) / 2;       // enough lanes with fewer
+            while (keep > 0 && (double)(chunks * (4ull + (unsigned long long)kSeekBytes * keep)) > budget) keep = (keep - 1) / 2;
+            s_keep = keep;
+        }
+    }
+    __syncthreads();
+    const unsigned int keep = s_keep;
+    if (t == 0) st->nseek_keep = (int)keep;
     for (int l = 0; l < nlay; l++) {
         const unsigned long long* ll = lens + (unsigned long long)l * g.nchunks;
         unsigned long long sum = 0;
@@ -287,17 +316,17 @@ __global__ void __launch_bounds__(1024) assemble_scan_kernel(const unsigned long
         const unsigned long long total = s_part[1023];
         unsigned long long off = s_part[t] - sum;
         const unsigned long long base = s_base;
-        const unsigned long long hdr = container_header_bytes(g, chunked);
+        const unsigned long long hdr = container_header_bytes(g, chunked, keep);
         const bool fits = base + hdr + total <= cap;
         if (fits) {
             if (chunked && t == 0) {
                 uint8_t* h = blob + base;
                 h[0] = 'W'; h[1] = 'R'; h[2] = 'C'; h[3] = 'K';
-                put_le(h + 4, 2, 4);
+                put_le(h + 4, kContainerVersion, 4);
                 put_le(h + 8, g.chunk_len, 8);
                 put_le(h + 16, g.ntot, 8);
                 put_le(h + 24, g.nchunks, 4);
-                put_le(h + 28, g.nseek, 4);
+                put_le(h + 28, keep, 4);
             }
             for (unsigned int c = c0; c < c1; c++) {
                 dst_off[(unsigned long long)l * g.nchunks + c] = base + hdr + off;
@@ -344,18 +373,28 @@ __global__ void __launch_bounds__(256) assemble_copy_kernel(const uint8_t* __res
         }
         dst[j] = (uint8_t)((v & 0x7FFFu) + cin);
     }
-    if (chunked && g.nseek) {
-        uint8_t* sdst = blob + st->lay_off[l] + 32 + 4ull * g.nchunks + 12ull * g.nseek * blockIdx.x;
+    const uint32_t keep = (uint32_t)st->nseek_keep;
+    if (chunked && keep) {
+        // every stride-th recorded point, 10 bytes each: low, range, stream position as the distance from the previous
+        // kept point (< 2^16: a sub-range of <= 30016 symbols codes into < 16 bits per symbol plus the 513-byte table)
+        const uint32_t stride = (g.nseek + 1) / (keep + 1);
+        uint8_t* sdst = blob + st->lay_off[l] + 32 + 4ull * g.nchunks + (unsigned long long)kSeekBytes * keep * blockIdx.x;
         const uint32_t* ssrc = seek + id * g.nseek * 3;
-        for (uint32_t t = threadIdx.x; t < g.nseek * 3; t += blockDim.x) put_le(sdst + 4ull * t, ssrc[t], 4);
+        for (uint32_t t = threadIdx.x; t < keep; t += blockDim.x) {
+            const uint32_t* e = ssrc + ((t + 1) * stride - 1) * 3;
+            const uint32_t prev = t ? ssrc[(t * stride - 1) * 3 + 2] : 0u;
+            put_le(sdst + kSeekBytes * t, e[0], 4);
+            put_le(sdst + kSeekBytes * t + 4, e[1], 4);
+            put_le(sdst + kSeekBytes * t + 8, e[2] >= prev ? e[2] - prev : 0u, 2);     // unused points (short last chunk) are zero
+        }
     }
 }
 
 void assemble_container(const uint8_t* slots, unsigned long long slot_pitch, const unsigned long long* lens,
-                        const uint32_t* seek, const ChunkGeom& g, int chunked, DevState* st, uint8_t* blob,
+                        const uint32_t* seek, const ChunkGeom& g, int chunked, int seek_auto, DevState* st, uint8_t* blob,
                         unsigned long long cap, unsigned long long* dst_off, cudaStream_t s)
 {
-    assemble_scan_kernel<<<1, 1024, 0, s>>>(lens, g, chunked, st, blob, cap, dst_off);
+    assemble_scan_kernel<<<1, 1024, 0, s>>>(lens, g, chunked, seek_auto, st, blob, cap, dst_off);
     dim3 grid(g.nchunks, kNLayMax, 1);
     assemble_copy_kernel<<<grid, 256, 0, s>>>(slots, slot_pitch, lens, dst_off, seek, g, chunked, st, blob);
     note_launch(2);
@@ -378,7 +417,7 @@ __global__ void __launch_bounds__(1024) parse_container_kernel(const uint8_t* __
         const unsigned long long base = lay_off[l];
         if (!chunked) { if (t == 0) offs[l] = base; continue; }
         const uint8_t* tabp = blob + base + 32;
-        const unsigned long long hdr = container_header_bytes(g, 1);
+        const unsigned long long hdr = container_header_bytes(g, 1, g.nseek);
         unsigned long long sum = 0;
         for (unsigned int c = c0; c < c1; c++) {
             const uint8_t* q = tabp + 4ull * c;
@@ -543,10 +582,14 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
             s1 = (s0 + g.sub_len < bs) ? s0 + g.sub_len : bs;
             if (sub > 0) {                        // restart from the seek point: X = W - 2*low
                 const uint8_t* sp = blob + lay_off[layer] + 32 + 4ull * g.nchunks +
-                                    12ull * ((unsigned long long)chunk * g.nseek + (sub - 1));
+                                    (unsigned long long)kSeekBytes * ((unsigned long long)chunk * g.nseek + (sub - 1));
                 const uint32_t slow = sp[0] | (sp[1] << 8) | (sp[2] << 16) | ((uint32_t)sp[3] << 24);
                 const uint32_t srng = sp[4] | (sp[5] << 8) | (sp[6] << 16) | ((uint32_t)sp[7] << 24);
-                const uint32_t spos = sp[8] | (sp[9] << 8) | (sp[10] << 16) | ((uint32_t)sp[11] << 24);
+                uint32_t spos = 0;                // positions are stored as distances from the previous point
+                for (unsigned int j = 0; j < sub; j++) {
+                    const uint8_t* q = sp - (unsigned long long)kSeekBytes * j;
+                    spos += q[8] | (q[9] << 8);
+                }
                 const uint8_t* q = d.p + spos;
                 const uint32_t W = ((uint32_t)q[0] << 24) | (q[1] << 16) | (q[2] << 8) | q[3];
                 d.X = W - 2 * slow;
@@ -664,8 +707,10 @@ void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, co
     const unsigned int nsub = g.nseek + 1;        // make_geom grants 0, 1, 3 or 7 seek points
     const unsigned int cpw = 32 / nsub;
     dim3 grid((g.nchunks + cpw - 1) / cpw, nlay, 1);
-    static int variant = -1;
-    if (variant < 0) { const char* e = getenv("WRB_DEC_VARIANT"); variant = (e && *e) ? (atoi(e) & 3) : kDecVariantDefault; }
+    int variant = -1;
+    // eager stream loads win while one or two warps share a scheduler; with 8 lanes per chunk (~3 warps) the
+    // L1 wavefronts of two 32-sector loads per symbol cost more than the occasional dependent load (3.42 -> 3.23 ms)
+    if (variant < 0) { const char* e = getenv("WRB_DEC_VARIANT"); variant = (e && *e) ? (atoi(e) & 3) : (nsub >= 8 ? 3 : kDecVariantDefault); }
     const int smem = (257 * 4 * 2 + kLutSize) * (int)cpw;
 #define WRB_DEC_LAUNCH(NS, V)                                                                                          \
     do {                                                                                                               \

@@ -45,6 +45,7 @@ struct DevState {
     unsigned long long ntot_enc;
     unsigned long long len_enc[kNLayMax];
     unsigned long long lay_off[kNLayMax + 1];   // byte offset of every layer inside the blob
+    int    nseek_keep;         // seek points per chunk that went into the container (<= those recorded)
 };
 
 __host__ __device__ inline unsigned long long dkey(double x)

@@ -78,7 +78,7 @@ struct ChunkGeom {
     unsigned int nseek;             // seek points per chunk (decoder entry points inside a chunk); 0 = none
     unsigned int sub_len;           // symbols between seek points (multiple of 16); 0 when nseek == 0
 };
-// nseek_req seek points are granted only to single-block chunks (chunk_len < 60000)
+// nseek_req seek points are granted only to single-block chunks (chunk_len < 60000); grids of 7 / 3 / 1 points are nested
 ChunkGeom make_geom(unsigned long long ntot, unsigned long long chunk_len, unsigned int nseek_req);
 
 void state_init(DevState* st, cudaStream_t s);
@@ -105,8 +105,10 @@ void range_encode_chunks(const uint8_t* sym, unsigned long long sym_layer_stride
                          unsigned long long hist_layer_stride, const ChunkGeom& g, int nlayers, const int* active,
                          uint8_t* slots, unsigned long long slot_pitch, unsigned long long* lens, uint32_t* seek,
                          cudaStream_t s);
+// seek_auto: the container keeps as few of the g.nseek recorded seek points as the decoder needs and the size budget
+// allows (rangecoder.cu: kSeekLaneTarget, kSeekBudget); the count goes into st->nseek_keep and the layer headers
 void assemble_container(const uint8_t* slots, unsigned long long slot_pitch, const unsigned long long* lens,
-                        const uint32_t* seek, const ChunkGeom& g, int chunked, DevState* st, uint8_t* blob,
+                        const uint32_t* seek, const ChunkGeom& g, int chunked, int seek_auto, DevState* st, uint8_t* blob,
                         unsigned long long cap, unsigned long long* dst_off, cudaStream_t s);
 void parse_container(const uint8_t* blob, const ChunkGeom& g, int chunked, int nlay, const unsigned long long* lay_off,
                      unsigned long long* offs, int* error, cudaStream_t s);

@@ -344,8 +344,8 @@ class GlobalOrder:
 
 
 def wrck_container(chunk_len, nsym, lens, streams):
-    """a WRCK v2 layer container without seek points from chunk byte lengths and the concatenated streams"""
-    hdr = b"WRCK" + (2).to_bytes(4, "little") + int(chunk_len).to_bytes(8, "little") + int(nsym).to_bytes(8, "little") \
+    """a WRCK v3 layer container without seek points from chunk byte lengths and the concatenated streams"""
+    hdr = b"WRCK" + (3).to_bytes(4, "little") + int(chunk_len).to_bytes(8, "little") + int(nsym).to_bytes(8, "little") \
         + len(lens).to_bytes(4, "little") + (0).to_bytes(4, "little")
     return hdr + np.asarray(lens, dtype="<u4").tobytes() + streams
 
