@@ -70,9 +70,9 @@ int wrb_set_chunk_blocks(wrb_codec* c, int blocks);
 /* Seek points per chunk: the encoder stores (low, range, stream position) at n interior symbol positions of
  * every single-block chunk, 10 bytes each, in the container's seek table; the decoder then runs n+1 lanes per
  * chunk.  Chunk streams are unaffected.  n = 0, 1, 3 or 7 (other values round down); n = -1 (default): the
- * encoder keeps the fewest points that give the decoder enough lanes to fill the GPU (none for large fields),
- * and never more than 0.85 % of the coded bytes for the chunk tables, so that the container stays within 1 %
- * of the reference's layer streams.  WRB_SEEK_POINTS in the environment sets the handle's initial value. */
+ * encoder keeps as many points (7, 3, 1 or 0) as fit into 0.85 % of the coded bytes for the chunk tables, so
+ * that the container stays within 1 % of the reference's layer streams whatever the data.
+ * WRB_SEEK_POINTS in the environment sets the handle's initial value. */
 int wrb_set_seek_points(wrb_codec* c, int n);
 /* Local (spatially varying) cutoff: the mx*my*mz > 1 branch of encoding_wrap() (reference wrappers.cpp:343-379,
  * lcl_prec :55-64).  cutoffvec holds mx*my*mz relative tolerances, x fastest.  While set, wrb_encode_* ignore their

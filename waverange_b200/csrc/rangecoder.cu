@@ -262,11 +262,11 @@ __host__ __device__ inline unsigned long long container_header_bytes(const Chunk
     return chunked ? 32ull + 4ull * g.nchunks + (unsigned long long)kSeekBytes * nseek * g.nchunks : 0ull;
 }
 
-// Seek points cost bytes (10 per point and chunk) and buy decoder lanes.  With seek_auto the container keeps the
-// fewest points of the recorded grid that give the decoder kSeekLaneTarget lanes over all layers (about three warps
-// per scheduler of a B200: more does not decode faster), and never more than kSeekBudget of the coded bytes for the
-// chunk tables (length + seek entries) -- the container stays within 1 % of the reference's layer streams.
-constexpr unsigned long long kSeekLaneTarget = 50000ull;
+// Seek points cost bytes (10 per point and chunk) and buy decoder lanes: the decoder keeps a chunk's tables in shared
+// memory, so lanes per chunk are also what fills an SM (measured at 1024^3 f32, 53.7 k chunks: 0 / 1 / 3 / 7 points
+// decode in 75.9 / 39.6 / 21.8 / 13.5 ms).  With seek_auto the container keeps as many points of the recorded grid as
+// fit into kSeekBudget of the coded bytes for the chunk tables (length + seek entries), so that it stays within 1 % of
+// the reference's layer streams whatever the data.
 constexpr double kSeekBudget = 0.0085;
 
 __global__ void __launch_bounds__(1024) assemble_scan_kernel(const unsigned long long* __restrict__ lens, ChunkGeom g,
@@ -293,7 +293,6 @@ __global__ void __launch_bounds__(1024) assemble_scan_kernel(const unsigned long
             const unsigned long long chunks = (unsigned long long)g.nchunks * (unsigned long long)(nlay > 0 ? nlay : 1);
             const double budget = kSeekBudget * (double)s_part[0];
             unsigned int keep = g.nseek;
-            while (keep > 0 && chunks * ((keep - 1) / 2 + 1) >= kSeekLaneTarget) keep = (keep - 1) / 2;       // enough lanes with fewer
             while (keep > 0 && (double)(chunks * (4ull + (unsigned long long)kSeekBytes * keep)) > budget) keep = (keep - 1) / 2;
             s_keep = keep;
         }
@@ -498,8 +497,12 @@ __device__ __forceinline__ uint32_t dec_short(Dec& d)
 }
 
 constexpr int kDecVariantDefault = 2;     // packed stores, eager stream loads (fastest measured at 512^3: 5.38 ms)     // see range_decode_kernel
-constexpr int kLutShift = 6;
-constexpr int kLutSize = (kBlock >> kLutShift) + 1;           // 938 buckets
+// Table footprint per chunk decides how many chunks an SM can hold (227 KB of shared memory), and with one or two lanes
+// per chunk that is what bounds the decoder: those variants take the compact form (single table entries, 128-wide LUT
+// buckets: 1.5 KB per chunk), four and eight lanes per chunk the fast form (entry pairs, 64-wide buckets: 3 KB).
+__host__ __device__ constexpr int dec_lut_shift(int nsub) { return nsub >= 4 ? 6 : 7; }
+__host__ __device__ constexpr int dec_lut_size(int nsub) { return (kBlock >> dec_lut_shift(nsub)) + 1; }   // 938 / 469 buckets
+__host__ __device__ constexpr bool dec_pair_table(int nsub) { return nsub >= 4; }
 
 // grid (ceil(nchunks/CPW), layers), block 32: lane == (chunk column, sub-chunk); NSUB lanes decode one
 // chunk, CPW = 32/NSUB chunks per warp.   wrappers.cpp:153-224
@@ -526,7 +529,8 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
                                                           int* error)
 {
     constexpr unsigned int CPW = 32 / NSUB;
-    constexpr bool kLdg = true, kBranchFree = true, kPair = true;
+    constexpr bool kLdg = true, kBranchFree = true, kPair = dec_pair_table(NSUB);
+    constexpr int kLutShift = dec_lut_shift(NSUB), kLutSize = dec_lut_size(NSUB);
     constexpr bool kLazy = (VAR & 1) != 0, kPack = (VAR & 2) != 0;
     constexpr unsigned int TW = kPair ? 2 : 1;                            // words per table entry
     extern __shared__ __align__(16) uint32_t smem_dyn[];
@@ -711,7 +715,7 @@ void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, co
     // eager stream loads win while one or two warps share a scheduler; with 8 lanes per chunk (~3 warps) the
     // L1 wavefronts of two 32-sector loads per symbol cost more than the occasional dependent load (3.42 -> 3.23 ms)
     if (variant < 0) { const char* e = getenv("WRB_DEC_VARIANT"); variant = (e && *e) ? (atoi(e) & 3) : (nsub >= 8 ? 3 : kDecVariantDefault); }
-    const int smem = (257 * 4 * 2 + kLutSize) * (int)cpw;
+    const int smem = (257 * 4 * (dec_pair_table((int)nsub) ? 2 : 1) + ((dec_lut_size((int)nsub) + 3) & ~3)) * (int)cpw;
 #define WRB_DEC_LAUNCH(NS, V)                                                                                          \
     do {                                                                                                               \
         static bool configured = false;                                                                                \
