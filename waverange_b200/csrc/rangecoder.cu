@@ -197,6 +197,9 @@ __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restr
                 until_seek--;
             }
             const uint4 wn = p[i + 1];                                     // next 16 symbols (pitch slack covers it)
+            // every lane streams its own chunk: 32 sectors per load, DRAM latency well above one group's ~1400 cycles
+            // when the symbols have left L2 -- pull the line eight groups ahead into L2 (prefetches never fault)
+            if ((i & 7u) == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(p + i + 16));
             const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
             uint32_t cs[16], ent[16];
 #pragma unroll
@@ -561,7 +564,7 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
         if ((d.X >> 1) < help) break;             // marker 0: no further block
         d.X -= 2 * help; d.range -= help;         // decode_update(rc,1,1,2)
         if (++nblocks > g.blocks_per_chunk) { bad = true; break; }
-        uint32_t acc = 0;
+        uint32_t acc = 0, lastsym = 0;            // lastsym: last symbol with a non-zero count
         int nextb = 0;                            // first bucket not yet assigned
         for (int s = 0; s < 256; s++) {           // readcounts (rangecod.c:400-404) + prefix sums
             const uint32_t c = dec_short(d);
@@ -570,6 +573,7 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
             if (c) {
                 const int lastb = (int)((acc + c - 1) >> kLutShift);
                 if (lastb < kLutSize) for (; nextb <= lastb; nextb++) lut[nextb * CPW + col] = (uint8_t)s;
+                lastsym = (uint32_t)s;
             }
             acc += c;
             if (acc > kBlock) { bad = true; break; }
@@ -616,46 +620,52 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
         uint32_t w0 = ldw(a >> 2), w1 = ldw((a >> 2) + 1);
         uint32_t sel = 0x0123u + 0x1111u * (a & 3u);
         uint32_t X = d.X, range = d.range;
-        // Symbols leave one byte at a time: stores are off the dependency chain, the symbol buffer may be flat
-        // (pitch == chunk_len, what the fused inverse transform reads) so a lane's run can start at any byte,
-        // and the bytes a lane writes complete whole 32-byte sectors in L2 long before they are evicted.
-        uint8_t* op = outb + n + s0;
-        uint8_t* const ostart = op;
-        uint8_t* const oend = outb + n + s1;
-        uint32_t pack = 0;
+        // Symbols leave through 32-bit stores: a lane's run may start at any byte of the (flat) symbol buffer, so up to
+        // three head symbols go out as bytes, then groups of four as one word, then the tail as bytes.  Stores are off
+        // the dependency chain and the bytes a lane writes complete whole 32-byte sectors in L2 long before eviction.
+        uint8_t* const op = outb + n + s0;
+        const uint32_t cnt = s1 - s0;
         // two copies of the loop (a generic lambda instantiated for both values): the fast division needs
         // help < 2^24 in every lane, decided once per block
         auto symbol_loop = [&](auto fast_tag) {
         constexpr bool kFastDiv = decltype(fast_tag)::value;
-#pragma unroll 1
-        for (; op != oend; op++) {
+        // One symbol (rangecod.c:309-319 decode_culfreq, wrappers.cpp:203-205 look-up, rangecod.c:339-351 decode_update).
+        // The float quotient q is floor(V / help) or one less; it only picks the LUT bucket.  The symbol itself is found
+        // with exact integer thresholds: s is the symbol iff help * cum[s] <= V < help * cum[s+1], which is cum[s] <= cf <
+        // cum[s+1] for cf = floor(V / help) without ever forming cf (no fix-up on the chain).  The reference's clamp
+        // cf <= tot - 1 (rangecod.c:318) only matters above the last symbol with a non-zero count: the search stops there.
+        auto step = [&]() -> uint32_t {
             const uint32_t win = __byte_perm(w0, w1, sel);
             const bool k1 = range <= kBottom, k2 = range <= (kBottom >> 8);
-            uint32_t an;
-            if (kBranchFree) {
-                const uint32_t sh = k2 ? 16u : (k1 ? 8u : 0u);
-                X = __funnelshift_l(win, X, sh);                                                // renormalise
-                range <<= sh;
-                an = a + (sh >> 3);
-            } else {
-                X = k2 ? __funnelshift_l(win, X, 16) : (k1 ? __funnelshift_l(win, X, 8) : X);   // renormalise
-                range = k2 ? (range << 16) : (k1 ? (range << 8) : range);
-                an = a + (k1 ? 1u : 0u) + (k2 ? 1u : 0u);
-            }
-            if ((an ^ a) & 0x80u) asm volatile("prefetch.global.L1 [%0];" :: "l"(wbase + (an >> 2) + 64));
+            const uint32_t sh = k2 ? 16u : (k1 ? 8u : 0u);
+            X = __funnelshift_l(win, X, sh);                                                    // renormalise
+            range <<= sh;
+            const uint32_t an = a + (sh >> 3);
             if (kLazy) {
                 if ((an ^ a) & 4u) { w0 = w1; w1 = ldw((an >> 2) + 1); }      // at most 2 bytes per step: one word boundary
             } else {
+                if ((an ^ a) & 0x80u) asm volatile("prefetch.global.L1 [%0];" :: "l"(wbase + (an >> 2) + 64));
                 w0 = ldw(an >> 2);
                 w1 = ldw((an >> 2) + 1);
             }
             a = an;
             sel = 0x0123u + 0x1111u * (a & 3u);
-            help = div_magic(range, mg);          // decode_culfreq(rc, bs)
-            uint32_t cf = kFastDiv ? div_small_quot_fast(X >> 1, help) : div_small_quot(X >> 1, help);
-            cf = min(cf, bs - 1);
-            uint32_t s = ll[(cf >> kLutShift) * CPW];
-            uint32_t e0, e1;                      // both probes issued together
+            const uint32_t V = X >> 1;
+            uint32_t q;
+            if (kFastDiv) {
+                help = __umulhi(range, mg.mul) >> mg.sh;                 // decode_culfreq(rc, bs): bs >= 256 here
+                float rb;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(__uint2float_rz(help)));      // help < 2^24 converts exactly
+                rb = __int_as_float(__float_as_int(rb) - 2);                                    // now <= 1 / help
+                const float est = __fmul_rz(__uint2float_rz(V), rb);                            // <= V / help
+                q = __float_as_uint(__fadd_rz(est, 8388608.0f)) & 0x7FFFFFu;                    // floor(est): cf - 1 <= q <= cf
+            } else {
+                help = div_magic(range, mg);
+                q = div_small_quot(V, help);
+            }
+            q = min(q, bs - 1);                   // V / help can exceed tot (the remainder range / tot leaves): last bucket
+            uint32_t s = ll[(q >> kLutShift) * CPW];
+            uint32_t e0, e1;                      // entries s and s + 1, both loads issued together
             if (kPair) {
                 const uint2 e = *reinterpret_cast<const uint2*>(tl + s * (CPW * 2));
                 e0 = e.x; e1 = e.y;
@@ -664,33 +674,37 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
                 asm volatile("ld.shared.u32 %0, [%2];\n\tld.shared.u32 %1, [%2+%3];"
                              : "=r"(e0), "=r"(e1) : "r"(sa), "n"(CPW * 4));
             }
-            const bool adv = (e0 >> 16) + (e0 & 0xFFFFu) <= cf;
+            const bool adv = s < lastsym && help * (e1 >> 16) <= V;
             uint32_t ent = adv ? e1 : e0;
             s += adv ? 1u : 0u;
-            uint32_t lt = ent >> 16, sy = ent & 0xFFFFu;
-            while (lt + sy <= cf && s < 255u) { s++; ent = tl[s * (CPW * TW)]; lt = ent >> 16; sy = ent & 0xFFFFu; }
-            const uint32_t tmp = help * lt;       // decode_update (rangecod.c:339-351)
-            X -= 2 * tmp;
-            range = (lt + sy < bs) ? help * sy : range - tmp;
-            if (kPack) {
-                const uint32_t ph = (uint32_t)(unsigned long long)op & 3u;
-                pack |= s << (8 * ph);
-                if (ph == 3u) {
-                    if (op - 3 >= ostart) *reinterpret_cast<uint32_t*>(op - 3) = pack;
-                    else for (uint8_t* q = ostart; q <= op; q++) *q = (uint8_t)(pack >> (8 * ((uint32_t)(unsigned long long)q & 3u)));   // ragged head
-                    pack = 0;
-                }
-            } else {
-                *op = (uint8_t)s;
+            if (adv) {                            // rare: more than one step from the bucket's first symbol
+                uint32_t nx = tl[(s + 1) * (CPW * TW)];
+                while (s < lastsym && help * (nx >> 16) <= V) { s++; ent = nx; nx = tl[(s + 1) * (CPW * TW)]; }
             }
+            // (testing help * (cum + count) of the chosen entry instead -- no load, branch rarely taken -- measured
+            //  slower: 2.94 vs 2.69 ms at 8 lanes per chunk, 15.2 vs 13.0 ms at 2)
+            const uint32_t tmp = help * (ent >> 16);          // decode_update
+            X -= 2 * tmp;
+            range = (s != lastsym) ? help * (ent & 0xFFFFu) : range - tmp;
+            return s;
+        };
+        uint32_t head = (4u - ((uint32_t)(unsigned long long)op & 3u)) & 3u;
+        if (head > cnt) head = cnt;
+        uint32_t i = 0;
+#pragma unroll 1
+        for (; i < head; i++) op[i] = (uint8_t)step();
+        const uint32_t ngroups = (cnt - head) >> 2;
+        uint32_t* __restrict__ o32 = reinterpret_cast<uint32_t*>(op + head);
+#pragma unroll 1
+        for (uint32_t gq = 0; gq < ngroups; gq++) {
+            const uint32_t b0 = step(), b1 = step(), b2 = step(), b3 = step();
+            o32[gq] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
         }
+        i = head + 4u * ngroups;
+#pragma unroll 1
+        for (; i < cnt; i++) op[i] = (uint8_t)step();
         };
         if (__all_sync(__activemask(), bs >= 256u)) symbol_loop(std::true_type{}); else symbol_loop(std::false_type{});
-        if (kPack) {                              // ragged tail (and head, when the run ends inside its first word)
-            uint8_t* q = reinterpret_cast<uint8_t*>((unsigned long long)oend & ~3ull);
-            if (q < ostart) q = ostart;
-            for (; q < oend; q++) *q = (uint8_t)(pack >> (8 * ((uint32_t)(unsigned long long)q & 3u)));
-        }
         d.X = X; d.range = range; d.ip = a - boff;
         n += bs;
         if (NSUB > 1) {
