@@ -499,7 +499,7 @@ __device__ __forceinline__ uint32_t dec_short(Dec& d)
     return t;
 }
 
-constexpr int kDecVariantDefault = 2;     // packed stores, eager stream loads (fastest measured at 512^3: 5.38 ms)     // see range_decode_kernel
+constexpr int kDecVariantDefault = 3;     // bit 0: lazy stream loads (see range_decode_kernel); bit 1 is unused since the stores are always packed
 // Table footprint per chunk decides how many chunks an SM can hold (227 KB of shared memory), and with one or two lanes
 // per chunk that is what bounds the decoder: those variants take the compact form (single table entries, 128-wide LUT
 // buckets: 1.5 KB per chunk), four and eight lanes per chunk the fast form (entry pairs, 64-wide buckets: 3 KB).
@@ -618,6 +618,7 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
         uint32_t a = boff + d.ip;
         auto ldw = [&](uint32_t widx) -> uint32_t { return kLdg ? __ldg(wbase + widx) : wbase[widx]; };
         uint32_t w0 = ldw(a >> 2), w1 = ldw((a >> 2) + 1);
+        uint32_t w2 = kLazy ? ldw((a >> 2) + 2) : 0u;
         uint32_t sel = 0x0123u + 0x1111u * (a & 3u);
         uint32_t X = d.X, range = d.range;
         // Symbols leave through 32-bit stores: a lane's run may start at any byte of the (flat) symbol buffer, so up to
@@ -642,7 +643,10 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
             range <<= sh;
             const uint32_t an = a + (sh >> 3);
             if (kLazy) {
-                if ((an ^ a) & 4u) { w0 = w1; w1 = ldw((an >> 2) + 1); }      // at most 2 bytes per step: one word boundary
+                // at most 2 bytes per step: one word boundary.  The word fetched is the one AFTER the next: it is first
+                // touched four stream bytes later, so even an L1 miss (one per 32-byte sector and lane, i.e. every few
+                // symbols somewhere in the warp) is off the dependency chain.
+                if ((an ^ a) & 4u) { w0 = w1; w1 = w2; w2 = ldw((an >> 2) + 2); }
             } else {
                 if ((an ^ a) & 0x80u) asm volatile("prefetch.global.L1 [%0];" :: "l"(wbase + (an >> 2) + 64));
                 w0 = ldw(an >> 2);
@@ -726,9 +730,9 @@ void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, co
     const unsigned int cpw = 32 / nsub;
     dim3 grid((g.nchunks + cpw - 1) / cpw, nlay, 1);
     int variant = -1;
-    // eager stream loads win while one or two warps share a scheduler; with 8 lanes per chunk (~3 warps) the
-    // L1 wavefronts of two 32-sector loads per symbol cost more than the occasional dependent load (3.42 -> 3.23 ms)
-    if (variant < 0) { const char* e = getenv("WRB_DEC_VARIANT"); variant = (e && *e) ? (atoi(e) & 3) : (nsub >= 8 ? 3 : kDecVariantDefault); }
+    // lazy stream loads with one word of lookahead beat two 32-sector loads per symbol at every lane count
+    // (512^3, 1 / 3 / 7 seek points: 12.4 vs 13.1, 5.01 vs 5.59, 2.67 vs 3.11 ms)
+    if (variant < 0) { const char* e = getenv("WRB_DEC_VARIANT"); variant = (e && *e) ? (atoi(e) & 3) : kDecVariantDefault; }
     const int smem = (257 * 4 * (dec_pair_table((int)nsub) ? 2 : 1) + ((dec_lut_size((int)nsub) + 3) & ~3)) * (int)cpw;
 #define WRB_DEC_LAUNCH(NS, V)                                                                                          \
     do {                                                                                                               \
