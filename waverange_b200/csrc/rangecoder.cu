@@ -111,11 +111,16 @@ __device__ __forceinline__ void enc_finish(Enc& e)
 
 // Code one symbol (rangecod.c:217-229).  ent = cum << 16 | count; `last`: the symbol is the last
 // one with a non-zero count, the only one with lt + sy == tot.  Branch-free: the (at most two) raw
-// entries go out through predicated stores and the shifted state is chosen with selects.
+// entries go out through predicated stores and the shifted state is chosen with selects.  ONE: the block
+// holds a single symbol (tot == 1: no division); decided per block, outside the symbol loop, so that the
+// choice costs no select on the range recurrence.
+template <bool ONE>
 __device__ __forceinline__ void enc_symbol(Enc& e, uint32_t ent, bool last, const Magic& mg)
 {
     const uint32_t range = e.range, low = e.low;
     uint16_t* w = e.raw + e.pos;
+    // (plain `if (k1) w[0] = ...` makes the compiler branch around the stores: 38 instructions per symbol and a
+    //  reconvergence point; the predicated stores are spelled out instead)
     asm volatile(
         "{\n\t"
         ".reg .pred p1, p2;\n\t"
@@ -130,7 +135,7 @@ __device__ __forceinline__ void enc_symbol(Enc& e, uint32_t ent, bool last, cons
     e.pos += (k1 ? 1u : 0u) + (k2 ? 1u : 0u);
     const uint32_t rs = k2 ? (range << 16) : (k1 ? (range << 8) : range);
     const uint32_t ls = k2 ? ((low << 16) & (kTop - 1)) : (k1 ? ((low << 8) & (kTop - 1)) : low);   // carry bit survives k == 0
-    const uint32_t r = div_magic(rs, mg);                    // exact range / bs
+    const uint32_t r = ONE ? rs : (__umulhi(rs, mg.mul) >> mg.sh);               // exact range / bs
     const uint32_t t = r * (ent >> 16);
     e.low = ls + t;
     e.range = last ? rs - t : r * (ent & 0xFFFFu);
@@ -186,6 +191,8 @@ __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restr
         const Magic mg = make_magic(bs);
         const uint4* __restrict__ p = reinterpret_cast<const uint4*>(in + done);
         const uint32_t nfull = bs >> 4;
+        auto code_block = [&](auto one_tag) {
+        constexpr bool ONE = decltype(one_tag)::value;
         uint4 w = (bs > 0) ? p[0] : make_uint4(0, 0, 0, 0);
         uint32_t until_seek = sub16, nsk = 0;
         for (uint32_t i = 0; i < nfull; i++) {
@@ -208,7 +215,7 @@ __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restr
                 ent[k] = tl[cs[k] * 32];
             }
 #pragma unroll
-            for (int k = 0; k < 16; k++) enc_symbol(e, ent[k], cs[k] == lastsym, mg);
+            for (int k = 0; k < 16; k++) enc_symbol<ONE>(e, ent[k], cs[k] == lastsym, mg);
             w = wn;
         }
         {
@@ -219,10 +226,12 @@ __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restr
             }
             for (uint32_t k = 0; k < rem; k++) {
                 const uint32_t c = (ww[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
-                enc_symbol(e, tl[c * 32], c == lastsym, mg);
+                enc_symbol<ONE>(e, tl[c * 32], c == lastsym, mg);
             }
         }
         for (; g.nseek && nsk < g.nseek; nsk++) { sk[nsk * 3 + 0] = 0; sk[nsk * 3 + 1] = 0; sk[nsk * 3 + 2] = 0; }
+        };
+        if (mg.one) code_block(std::true_type{}); else code_block(std::false_type{});     // single-symbol blocks are rare
         done += bs;
         hrow += 256;
         if (bs < kBlock) break;
