@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from util import SYM_GENS, bits_equal, sha
+from util import SYM_GENS, bits_equal, header_tuple, sha
 
 pytestmark = pytest.mark.gpu
 
@@ -282,6 +282,30 @@ def test_f32_roundtrip_host_api(codec, torch_cuda, oracle):
     want_rec = oracle.decode(f.shape, want["header"], want["data"]).astype(np.float32)
     assert bits_equal(rec, want_rec)
     assert np.abs(rec.astype(np.float64) - f).max() <= 1e-4 * np.abs(f).max()
+
+
+def test_pageable_host_buffers_take_the_staged_path(product_lib, codec, torch_cuda, oracle):
+    """ordinary (pageable) arrays, as a program written for the reference passes them, go through the pinned staging ring
+    (three slabs here, so the ring wraps): same header, same bytes and same reconstruction as from pinned buffers"""
+    from waverange_b200 import api
+    shape, tol = (220, 200, 200), 1e-6                       # 70.4 MB as float64
+    f = oracle.probe_field(shape, seed=3, nm=16)
+    h1, d1 = api.encoding_wrap(f, tol)                        # reference entry point, pageable in and out
+    pin = torch_cuda.empty(shape, dtype=torch_cuda.float64, pin_memory=True)
+    pin.copy_(torch_cuda.from_numpy(f))
+    pout = torch_cuda.empty(f.nbytes, dtype=torch_cuda.uint8, pin_memory=True)
+    h2, d2 = codec.encode_host(pin.numpy(), tol, out=pout.numpy())
+    assert header_tuple(h1) == header_tuple(h2) and h1.ntot_enc == h2.ntot_enc
+    assert np.array_equal(np.asarray(d1), np.asarray(d2)[:h2.ntot_enc])
+    r1 = api.decoding_wrap(shape, h1, d1)                     # pageable out (first touched by the copy threads)
+    prec = torch_cuda.empty(shape, dtype=torch_cuda.float64, pin_memory=True)
+    codec.decode_host(shape, h2, d2, out=prec.numpy())
+    assert bits_equal(r1, prec.numpy())
+    assert np.abs(r1 - f).max() <= tol * np.abs(f).max()
+    f32 = f.astype(np.float32)                                # pageable float32 through the handle API
+    h3, d3 = codec.encode_host(f32, tol)
+    r3 = codec.decode_host(shape, h3, d3, dtype=np.float32)
+    assert np.abs(r3.astype(np.float64) - f32).max() <= tol * np.abs(f32).max()
 
 
 def test_overflow_is_reported(codec, torch_cuda, oracle):

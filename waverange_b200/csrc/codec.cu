@@ -10,8 +10,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <algorithm>
 #include <atomic>
 #include <new>
+#include <thread>
+#include <vector>
 #include "wr_common.cuh"
 #include "wr_kernels.h"
 #include "../../include/waverange_b200.h"
@@ -54,6 +57,12 @@ struct wrb_codec {
     int timing = 0;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float stage_ms[4] = {0, 0, 0, 0};
+    // pinned staging ring for pageable host buffers (wrb_encode_host / wrb_decode_host), allocated on first use
+    void* stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    // second stream + events: wrb_decode_host copies finished z-pieces of the field out while the rest is computed
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t piece_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 #define CK(call)                                                                                   \
@@ -66,6 +75,99 @@ struct wrb_codec {
     } while (0)
 
 static int fail(wrb_codec* c, int code, const char* msg) { c->err = msg; return code; }
+
+// ---- host <-> device transfers of caller-owned buffers ---------------------------------------------------
+// A program written for the reference hands encoding_wrap()/decoding_wrap() ordinary (pageable) arrays.  One
+// cudaMemcpy of such a buffer runs at ~10 GB/s (the driver stages it on one thread; a fresh output array is also
+// first-touched page by page): 123 / 237 ms for a 512^3 double field against 24 ms from pinned memory.  Pageable
+// buffers therefore go through a ring of two pinned slabs: several host threads copy slab i+1 (touching the pages in
+// parallel) while the DMA engine moves slab i.  Pinned or registered buffers are copied directly.
+static constexpr size_t kStageBytes = 32ull << 20;
+
+static bool host_ptr_is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static void parallel_memcpy(void* dst, const void* src, size_t n)
+{
+    static const unsigned hw = std::thread::hardware_concurrency();
+    const unsigned want = hw >= 16 ? 8u : (hw >= 4 ? hw / 2 : 1u);
+    const size_t per = 2ull << 20;                               // at least 2 MiB per thread
+    unsigned nt = (unsigned)std::min<size_t>(want, (n + per - 1) / per);
+    if (nt <= 1) { memcpy(dst, src, n); return; }
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    const size_t slice = ((n / nt) + 4095) & ~(size_t)4095;
+    for (unsigned t = 1; t < nt; t++) {
+        const size_t o = slice * t;
+        if (o >= n) break;
+        const size_t len = std::min(slice, n - o);
+        th.emplace_back([=]() { memcpy((char*)dst + o, (const char*)src + o, len); });
+    }
+    memcpy(dst, src, std::min(slice, n));
+    for (auto& x : th) x.join();
+}
+
+static int ensure_stage(wrb_codec* c)
+{
+    for (int i = 0; i < 2; i++) {
+        if (!c->stage[i]) CK(cudaHostAlloc(&c->stage[i], kStageBytes, cudaHostAllocDefault));
+        if (!c->stage_ev[i]) CK(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+// host -> device on the codec's stream; returns once the last slab is enqueued (pageable source: already consumed)
+static int copy_to_device(wrb_codec* c, void* d_dst, const void* h_src, size_t n)
+{
+    if (n == 0) return 0;
+    if (n < (4ull << 20) || host_ptr_is_pinned(h_src)) {
+        CK(cudaMemcpyAsync(d_dst, h_src, n, cudaMemcpyHostToDevice, c->stream));
+        return 0;
+    }
+    int rc = ensure_stage(c);
+    if (rc) return rc;
+    size_t off = 0;
+    for (int i = 0; off < n; i++, off += kStageBytes) {
+        const int b = i & 1;
+        const size_t len = std::min(kStageBytes, n - off);
+        CK(cudaEventSynchronize(c->stage_ev[b]));        // slab b has left for the device (also from an earlier call)
+        parallel_memcpy(c->stage[b], (const char*)h_src + off, len);
+        CK(cudaMemcpyAsync((char*)d_dst + off, c->stage[b], len, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaEventRecord(c->stage_ev[b], c->stream));
+    }
+    return 0;
+}
+
+// device -> host after everything enqueued on the codec's stream; returns when the data is in h_dst
+static int copy_to_host(wrb_codec* c, void* h_dst, const void* d_src, size_t n)
+{
+    if (n == 0) return 0;
+    if (n < (4ull << 20) || host_ptr_is_pinned(h_dst)) {
+        CK(cudaMemcpyAsync(h_dst, d_src, n, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+    int rc = ensure_stage(c);
+    if (rc) return rc;
+    const size_t nslab = (n + kStageBytes - 1) / kStageBytes;
+    auto issue = [&](size_t i) -> cudaError_t {
+        const size_t off = i * kStageBytes, len = std::min(kStageBytes, n - off);
+        cudaError_t e = cudaMemcpyAsync(c->stage[i & 1], (const char*)d_src + off, len, cudaMemcpyDeviceToHost, c->stream);
+        return e != cudaSuccess ? e : cudaEventRecord(c->stage_ev[i & 1], c->stream);
+    };
+    CK(issue(0));
+    for (size_t i = 0; i < nslab; i++) {
+        if (i + 1 < nslab) CK(issue(i + 1));                                     // the other slab fills meanwhile
+        CK(cudaEventSynchronize(c->stage_ev[i & 1]));
+        const size_t off = i * kStageBytes, len = std::min(kStageBytes, n - off);
+        parallel_memcpy((char*)h_dst + off, c->stage[i & 1], len);
+    }
+    return 0;
+}
 
 static unsigned long long chunk_len_of(const wrb_codec* c)
 {
@@ -118,6 +220,12 @@ void wrb_destroy(wrb_codec* c)
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_u64) cudaFreeHost(c->h_u64);
     for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 2; i++) {
+        if (c->stage[i]) cudaFreeHost(c->stage[i]);
+        if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
+    }
+    for (int i = 0; i < 4; i++) if (c->piece_ev[i]) cudaEventDestroy(c->piece_ev[i]);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }
 
@@ -510,7 +618,8 @@ int wrb_quantise_slab_device(wrb_codec* c, const void* d_field_slab, int dtype, 
 // d_sym_flat != null: the layers' symbols are given (nlay planes of ntot bytes, array order) instead of coded data --
 // the parse and range-decoder stages are skipped (wrb_decode_symbols_device, wrb_decode_slab_symbols_device)
 static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int nz, const wrb_header* hdr,
-                       const unsigned char* d_data_enc, const SlabGeom* sg, const unsigned char* d_sym_flat = nullptr)
+                       const unsigned char* d_data_enc, const SlabGeom* sg, const unsigned char* d_sym_flat = nullptr,
+                       HostSink* sink = nullptr)
 {
     if (!c || !d_out || !hdr || nx < 1 || ny < 1 || nz < 1 || (dtype != WRB_F64 && dtype != WRB_F32))
         return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
@@ -609,7 +718,7 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
         if (fuse_deq)
             wavelet_inverse((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, d_out, dtype == WRB_F32,
                             nx, ny, nz, (int)hdr->wlev, s, (const uint8_t*)c->sym.p, lstride, g.chunk_len, g.pitch, nlay,
-                            hdr->deps_vec, hdr->minval_vec);
+                            hdr->deps_vec, hdr->minval_vec, sink);
         else
             wavelet_inverse((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, d_out, dtype == WRB_F32,
                             nx, ny, nz, (int)hdr->wlev, s);
@@ -669,12 +778,11 @@ int wrb_encode_host(wrb_codec* c, const void* field, int dtype, int nx, int ny, 
     const size_t esz = dtype == WRB_F32 ? 4 : 8;
     CK(c->field.ensure(ntot * esz));
     CK(c->blob.ensure((size_t)cap + 64));
-    CK(cudaMemcpyAsync(c->field.p, field, ntot * esz, cudaMemcpyHostToDevice, c->stream));
-    int rc = wrb_encode_device(c, c->field.p, dtype, nx, ny, nz, wtflag, tolrel, hdr, (unsigned char*)c->blob.p, cap);
+    int rc = copy_to_device(c, c->field.p, field, ntot * esz);
     if (rc) return rc;
-    if (hdr->ntot_enc) CK(cudaMemcpyAsync(data_enc, c->blob.p, hdr->ntot_enc, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    return 0;
+    rc = wrb_encode_device(c, c->field.p, dtype, nx, ny, nz, wtflag, tolrel, hdr, (unsigned char*)c->blob.p, cap);
+    if (rc) return rc;
+    return copy_to_host(c, data_enc, c->blob.p, hdr->ntot_enc);
 }
 
 int wrb_decode_host(wrb_codec* c, void* field_out, int dtype, int nx, int ny, int nz, const wrb_header* hdr,
@@ -689,14 +797,29 @@ int wrb_decode_host(wrb_codec* c, void* field_out, int dtype, int nx, int ny, in
     CK(c->blob.ensure((size_t)hdr->ntot_enc + 64));
     if (hdr->ntot_enc) {
         if (!data_enc) return fail(c, WRB_E_ARG, "data_enc is null");
-        CK(cudaMemcpyAsync(c->blob.p, data_enc, hdr->ntot_enc, cudaMemcpyHostToDevice, c->stream));
+        const int rcc = copy_to_device(c, c->blob.p, data_enc, hdr->ntot_enc);
+        if (rcc) return rcc;
         CK(cudaMemsetAsync((unsigned char*)c->blob.p + hdr->ntot_enc, 0, 64, c->stream));
     }
-    int rc = wrb_decode_device(c, c->field.p, dtype, nx, ny, nz, hdr, (const unsigned char*)c->blob.p);
+    // pinned destination: the last inverse level hands its z-pieces to a copy stream as they finish
+    HostSink sink{};
+    HostSink* use = nullptr;
+    if (ntot * esz >= (32ull << 20) && host_ptr_is_pinned(field_out)) {
+        if (!c->copy_stream) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 4; i++) if (!c->piece_ev[i]) CK(cudaEventCreateWithFlags(&c->piece_ev[i], cudaEventDisableTiming));
+        sink.host = field_out; sink.copy = c->copy_stream; sink.used = 0;
+        for (int i = 0; i < 4; i++) sink.ev[i] = c->piece_ev[i];
+        use = &sink;
+    }
+    int rc = decode_impl(c, c->field.p, dtype, nx, ny, nz, hdr, (const unsigned char*)c->blob.p, nullptr, nullptr, use);
+    if (use && sink.used) {                     // also on failure: nothing of ours may still be writing the caller's buffer
+        cudaError_t e = cudaStreamSynchronize(c->copy_stream);
+        if (rc) return rc;
+        CK(e);
+        return 0;
+    }
     if (rc) return rc;
-    CK(cudaMemcpyAsync(field_out, c->field.p, ntot * esz, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    return 0;
+    return copy_to_host(c, field_out, c->field.p, ntot * esz);
 }
 
 int wrb_wavelet3d_device(wrb_codec* c, double* d_x, int nx, int ny, int nz, int lvl)

@@ -374,15 +374,29 @@ __global__ void __launch_bounds__(256) assemble_copy_kernel(const uint8_t* __res
     const uint16_t* __restrict__ raw = reinterpret_cast<const uint16_t*>(slots + id * slot_pitch);
     uint8_t* __restrict__ dst = blob + dst_off[id];
     const uint32_t n = (uint32_t)lens[id];
-    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
-        const uint32_t v = raw[j];
-        uint32_t k = j + 1, cin = 0;
-        while (k < n) {                              // first later entry that is not a plain 0xFF decides
+    // eight entries per thread (one 16-byte load; slots are 16-byte aligned): the carry into entry i is decided by the
+    // first later entry that is not a plain 0xFF, resolved backwards inside the group from the decision for entry 8
+    for (uint32_t j = 8u * threadIdx.x; j < n; j += 8u * blockDim.x) {
+        const uint4 q = *reinterpret_cast<const uint4*>(raw + j);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const uint32_t m = (n - j < 8u) ? n - j : 8u;        // valid entries of this group
+        uint32_t k = j + m, dec = 0;                          // decision carried into the group's last valid entry
+        while (k < n) {
             const uint32_t u = raw[k];
-            if ((u & kTerm) || (u & 0x7FFFu) != 0xFFu) { cin = raw_carry(u); break; }
+            if ((u & kTerm) || (u & 0x7FFFu) != 0xFFu) { dec = raw_carry(u); break; }
             k++;
         }
-        dst[j] = (uint8_t)((v & 0x7FFFu) + cin);
+        uint8_t ob[8];
+#pragma unroll
+        for (int i = 7; i >= 0; i--) {
+            const uint32_t v = (w[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu;
+            if ((uint32_t)i < m) {
+                ob[i] = (uint8_t)((v & 0x7FFFu) + dec);
+                if ((v & kTerm) || (v & 0x7FFFu) != 0xFFu) dec = raw_carry(v);     // a plain 0xFF passes the decision on
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) if ((uint32_t)i < m) dst[j + i] = ob[i];
     }
     const uint32_t keep = (uint32_t)st->nseek_keep;
     if (chunked && keep) {

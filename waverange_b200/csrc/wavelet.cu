@@ -393,7 +393,7 @@ static inline int ceil_shift(int n, int k) { return (int)(((long long)n + (1ll <
 void wavelet_inverse(double* coef, double* tmp, double* lllA, double* lllB, void* out, int out_is_f32,
                      int nx, int ny, int nz, int levels, cudaStream_t s, const uint8_t* sym,
                      unsigned long long layer_stride, unsigned long long chunk_len, unsigned long long pitch, int nlay,
-                     const double* deps, const double* minval)
+                     const double* deps, const double* minval, HostSink* sink)
 {
     DequantSrc dq{};
     dq.sym = sym; dq.layer_stride = layer_stride; dq.chunk_len = chunk_len; dq.pitch = pitch; dq.nlay = nlay;
@@ -418,7 +418,21 @@ void wavelet_inverse(double* coef, double* tmp, double* lllA, double* lllB, void
         const double* prev = nullptr;
         for (int k = levels - 1; k >= 0; k--) {
             const int n0 = ceil_shift(nx, k), n1 = ceil_shift(ny, k), n2 = ceil_shift(nz, k);
-            if (k == 0) {
+            if (k == 0 && sink != nullptr && n2 / 2 >= 64) {
+                // Four z-pieces; piece i leaves for the host on the copy stream while piece i+1 is computed (the copy of a
+                // 512^3 float field takes ~10 ms, the level ~1.4 ms: only the first piece's compute stays exposed).
+                const int q2 = n2 / 2;
+                const size_t esz = out_is_f32 ? 4 : 8;
+                for (int i = 0; i < 4; i++) {
+                    const int p0 = (int)((long long)q2 * i / 4), p1 = (int)((long long)q2 * (i + 1) / 4);
+                    fused_inverse_level(coef, ay, az, sym, layer_stride, nlay, deps, minval, prev, out, out_is_f32, ay, az, n0, n1, n2, s, p0, p1);
+                    cudaEventRecord(sink->ev[i], s);
+                    cudaStreamWaitEvent(sink->copy, sink->ev[i], 0);
+                    const size_t off = (size_t)(2 * p0) * (size_t)az * esz, len = (size_t)(2 * (p1 - p0)) * (size_t)az * esz;
+                    cudaMemcpyAsync((char*)sink->host + off, (const char*)out + off, len, cudaMemcpyDeviceToHost, sink->copy);
+                }
+                sink->used = 1;
+            } else if (k == 0) {
                 fused_inverse_level(coef, ay, az, sym, layer_stride, nlay, deps, minval, prev, out, out_is_f32, ay, az, n0, n1, n2, s);
             } else {
                 double* nxt = (k & 1) ? lllA : lllB;

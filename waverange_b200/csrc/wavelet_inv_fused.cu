@@ -47,6 +47,7 @@ struct FusedInvArgs {
     void* dst; long long dsy, dsz;            // this level's output (x stride 1)
     int n0, n1, n2;                           // box extents (even)
     int zpairs;                               // output pairs per z-segment
+    int seg_lo, seg_hi;                       // output pairs [seg_lo, seg_hi) this launch produces (whole box: 0, n2/2)
     int vec_ok;                               // output rows are 16-byte aligned: vector stores allowed
     // z-slab mode (NLAY == 0 only): the coefficients come from two band buffers that hold this rank's pairs
     // [pair_lo, pair_lo + nown) of the GLOBAL line plus `halo` planes of the neighbours on either side (own pair p at
@@ -105,8 +106,8 @@ __global__ void __launch_bounds__(ITHREADS, 1) inv_level_fused_kernel(FusedInvAr
     const int q0 = a.n0 >> 1, q1 = a.n1 >> 1, q2 = a.n2 >> 1;
     const int px0 = blockIdx.x * IPX, py0 = blockIdx.y * IPY;
     const bool band = (NLAY == 0) && a.lowb != nullptr;
-    const int pair_lo = band ? a.pair_lo : 0, pair_hi = band ? a.pair_lo + a.nown : q2;
-    const int e0 = pair_lo + blockIdx.z * a.zpairs;
+    const int pair_lo = band ? a.pair_lo : 0, pair_hi = band ? a.pair_lo + a.nown : a.seg_hi;
+    const int e0 = (band ? pair_lo : a.seg_lo) + blockIdx.z * a.zpairs;
     const int e1 = (e0 + a.zpairs < pair_hi) ? e0 + a.zpairs : pair_hi;
     // ---- coefficient positions of this thread: flat index tid + k*ITHREADS over ICY x ICX ----
     int coff[ISLOTS], loff[ISLOTS], soff[ISLOTS];
@@ -247,7 +248,8 @@ bool fused_inverse_supported(int n0, int n1, int n2)
 // One level: coefficients of box (n0,n1,n2) [symbols or coef, + lll for the low-low-low octant] -> dst.
 void fused_inverse_level(const double* coef, long long ay, long long az, const uint8_t* sym, unsigned long long lstride,
                          int nlay, const double* deps, const double* minval, const double* lll, void* dst,
-                         int dst_is_f32, long long dsy, long long dsz, int n0, int n1, int n2, cudaStream_t s)
+                         int dst_is_f32, long long dsy, long long dsz, int n0, int n1, int n2, cudaStream_t s,
+                         int seg_lo, int seg_hi)
 {
     FusedInvArgs a{};
     a.coef = coef; a.ay = ay; a.az = az; a.sym = sym; a.lstride = lstride; a.nlay = nlay;
@@ -258,10 +260,14 @@ void fused_inverse_level(const double* coef, long long ay, long long az, const u
     a.vec_ok = ((reinterpret_cast<size_t>(dst) % 16) == 0 && (dsy * esz) % 16 == 0 && (dsz * esz) % 16 == 0) ? 1 : 0;
     const int q0 = n0 / 2, q1 = n1 / 2, q2 = n2 / 2;
     const int gx = (q0 + IPX - 1) / IPX, gy = (q1 + IPY - 1) / IPY;
+    a.seg_lo = (seg_lo < 0) ? 0 : seg_lo;
+    a.seg_hi = (seg_hi < 0 || seg_hi > q2) ? q2 : seg_hi;
+    const int npairs = a.seg_hi - a.seg_lo;
+    if (npairs <= 0) return;
     // z-segments: shortest critical path for one resident CTA per SM (512^3 level 1: 4 segments, 7 waves)
-    const int zp = pick_zpairs((long long)gx * gy, q2, 148, 4, 4);
+    const int zp = pick_zpairs((long long)gx * gy, npairs, 148, 4, 4);
     a.zpairs = zp;
-    dim3 grid(gx, gy, (q2 + zp - 1) / zp);
+    dim3 grid(gx, gy, (npairs + zp - 1) / zp);
 #define WRB_INV_LAUNCH(NL)                                                                          \
     do {                                                                                            \
         if (dst_is_f32) inv_level_fused_kernel<float, NL><<<grid, ITHREADS, 0, s>>>(a);             \

@@ -11,10 +11,13 @@ void wavelet_forward(const void* src, int src_is_f32, double* coef, double* tmp,
                      int nx, int ny, int nz, int levels, DevState* st, cudaStream_t s);
 // sym != null: the detail coefficients are rebuilt from the symbol planes inside the z pass (coef is then only
 // scratch); requires nz > 1 at every level, otherwise dequantise into coef first and pass sym = null
+// sink != null (and every level fused): the last level runs in z-pieces and every finished piece of `out` is copied
+// to sink->host on sink->copy while the next one is computed; sink->used tells the caller whether that happened
+struct HostSink { void* host; cudaStream_t copy; cudaEvent_t ev[4]; int used; };
 void wavelet_inverse(double* coef, double* tmp, double* lllA, double* lllB, void* out, int out_is_f32,
                      int nx, int ny, int nz, int levels, cudaStream_t s, const uint8_t* sym = nullptr,
                      unsigned long long layer_stride = 0, unsigned long long chunk_len = 0, unsigned long long pitch = 0,
-                     int nlay = 0, const double* deps = nullptr, const double* minval = nullptr);
+                     int nlay = 0, const double* deps = nullptr, const double* minval = nullptr, HostSink* sink = nullptr);
 
 void wavelet_xy_passes(const void* cur, int cur_is_f32, long long csy, long long csz, double* scratch, long long ay,
                        long long az, double* dst, long long dsy, long long dsz, int n0, int n1, int n2,
@@ -56,7 +59,8 @@ bool fused_inverse_supported(int n0, int n1, int n2);
 // sym != null: coefficients are rebuilt from the FLAT symbol planes (layer l at sym + l*lstride); else read from coef
 void fused_inverse_level(const double* coef, long long ay, long long az, const uint8_t* sym, unsigned long long lstride,
                          int nlay, const double* deps, const double* minval, const double* lll, void* dst,
-                         int dst_is_f32, long long dsy, long long dsz, int n0, int n1, int n2, cudaStream_t s);
+                         int dst_is_f32, long long dsy, long long dsz, int n0, int n1, int n2, cudaStream_t s,
+                         int seg_lo = -1, int seg_hi = -1);          // output pairs [seg_lo, seg_hi) only (default: all)
 
 void fused_inverse_level_bands(const double* lowb, const double* highb, long long bsy, long long bsz, int halo, int pair_lo,
                                int nown, void* dst, int dst_is_f32, long long dsy, long long dsz, int n0, int n1, int n2g,
