@@ -63,6 +63,7 @@ struct wrb_codec {
     // second stream + events: wrb_decode_host copies finished z-pieces of the field out while the rest is computed
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t piece_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    HostSource* src_pipe = nullptr;   // set by wrb_encode_host for the duration of one call: the field arrives in z-pieces
 };
 
 #define CK(call)                                                                                   \
@@ -460,7 +461,7 @@ static int run_transform_and_quantise(wrb_codec* c, const void* d_field, int dty
         if (rc) return fail(c, WRB_E_CUDA, "halo exchange callback failed");
     } else {
         wavelet_forward(d_field, dtype == WRB_F32, (double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p,
-                        (double*)c->lllB.p, nx, ny, nz, wtflag ? kWavLvl : 0, st, s);
+                        (double*)c->lllB.p, nx, ny, nz, wtflag ? kWavLvl : 0, st, s, c->src_pipe);
     }
     if (dist && reduce_extrema(c, &st->fmin_key, &st->fmax_key)) return fail(c, WRB_E_CUDA, "reduce callback failed");
     state_prepare(st, tolrel, s);
@@ -778,9 +779,32 @@ int wrb_encode_host(wrb_codec* c, const void* field, int dtype, int nx, int ny, 
     const size_t esz = dtype == WRB_F32 ? 4 : 8;
     CK(c->field.ensure(ntot * esz));
     CK(c->blob.ensure((size_t)cap + 64));
-    int rc = copy_to_device(c, c->field.p, field, ntot * esz);
-    if (rc) return rc;
-    rc = wrb_encode_device(c, c->field.p, dtype, nx, ny, nz, wtflag, tolrel, hdr, (unsigned char*)c->blob.p, cap);
+    int rc;
+    // pinned source and a level-1 box the one-pass kernel takes: the field is copied in four z-pieces on a second stream
+    // and level 1 of the transform follows piece by piece (only the last piece's share of it stays exposed)
+    if (wtflag && nz / 2 >= 64 && (nz & 1) == 0 && ntot * esz >= (32ull << 20) && fused_forward_supported(nx, ny, nz) &&
+        host_ptr_is_pinned(field)) {
+        if (!c->copy_stream) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 4; i++) if (!c->piece_ev[i]) CK(cudaEventCreateWithFlags(&c->piece_ev[i], cudaEventDisableTiming));
+        HostSource pipe{};
+        const size_t plane = (size_t)nx * ny * esz;
+        const int m2 = nz / 2;
+        for (int i = 0; i < 4; i++) {
+            const size_t z0 = 2 * (size_t)((long long)m2 * i / 4), z1 = 2 * (size_t)((long long)m2 * (i + 1) / 4);
+            CK(cudaMemcpyAsync((char*)c->field.p + z0 * plane, (const char*)field + z0 * plane, (z1 - z0) * plane,
+                               cudaMemcpyHostToDevice, c->copy_stream));
+            CK(cudaEventRecord(c->piece_ev[i], c->copy_stream));
+            pipe.ev[i] = c->piece_ev[i];
+        }
+        c->src_pipe = &pipe;
+        rc = wrb_encode_device(c, c->field.p, dtype, nx, ny, nz, wtflag, tolrel, hdr, (unsigned char*)c->blob.p, cap);
+        c->src_pipe = nullptr;
+        (void)pipe.used;                        // wavelet_forward waits for the whole copy itself when it cannot follow it
+    } else {
+        rc = copy_to_device(c, c->field.p, field, ntot * esz);
+        if (rc) return rc;
+        rc = wrb_encode_device(c, c->field.p, dtype, nx, ny, nz, wtflag, tolrel, hdr, (unsigned char*)c->blob.p, cap);
+    }
     if (rc) return rc;
     return copy_to_host(c, data_enc, c->blob.p, hdr->ntot_enc);
 }

@@ -310,11 +310,13 @@ static inline int half_up(int n) { return (n + 1) / 2; }
 // scratches for the low-low-low octants (>= ceil(n/2)^3 and ceil(n/4)^3 doubles).
 // Field extrema -> st->fmin/fmax keys, coefficient extrema -> st->rmin_key[0]/rmax_key[0].
 void wavelet_forward(const void* src, int src_is_f32, double* coef, double* tmp, double* lllA, double* lllB,
-                     int nx, int ny, int nz, int levels, DevState* st, cudaStream_t s)
+                     int nx, int ny, int nz, int levels, DevState* st, cudaStream_t s, HostSource* pipe)
 {
     const long long ay = nx, az = (long long)nx * ny;
     unsigned long long* fmin = &st->fmin_key; unsigned long long* fmax = &st->fmax_key;
     unsigned long long* cmin = &st->rmin_key[0]; unsigned long long* cmax = &st->rmax_key[0];
+    const bool piecewise = pipe != nullptr && levels >= 1 && fused_forward_supported(nx, ny, nz) && nz / 2 >= 64;
+    if (pipe != nullptr && !piecewise) cudaStreamWaitEvent(s, pipe->ev[3], 0);      // cannot follow the copy: wait for all of it
     if (levels == 0) {
         unsigned long long n = (unsigned long long)nx * ny * nz;
         int blocks = (int)((n + 256ull * 8 - 1) / (256ull * 8));
@@ -333,6 +335,17 @@ void wavelet_forward(const void* src, int src_is_f32, double* coef, double* tmp,
         const bool last = (k == levels);
         double* lll = last ? nullptr : ((k & 1) ? lllA : lllB);
         if (fused_forward_supported(n0, n1, n2)) {          // one HBM round trip for this level
+            if (k == 1 && piecewise) {
+                // the output pairs [p0, p1) of piece i need input planes 2 p0 - 4 .. 2 p1 + 2: copy pieces 0 .. i+1
+                for (int i = 0; i < 4; i++) {
+                    const int p0 = (int)((long long)m2 * i / 4), p1 = (int)((long long)m2 * (i + 1) / 4);
+                    cudaStreamWaitEvent(s, pipe->ev[i < 3 ? i + 1 : 3], 0);
+                    fused_forward_level(cur, cur_f32 ? 1 : 0, csy, csz, coef + (long long)p0 * az, ay, az,
+                                        lll ? lll + (long long)p0 * m0 * m1 : nullptr, n0, n1, n2, fmin, fmax, cmin, cmax, s,
+                                        0, p0, p1 - p0, m2);
+                }
+                pipe->used = 1;
+            } else
             fused_forward_level(cur, cur_f32 ? 1 : 0, csy, csz, coef, ay, az, lll, n0, n1, n2, (k == 1) ? fmin : nullptr,
                                 (k == 1) ? fmax : nullptr, cmin, cmax, s);
             cur = lll; csy = m0; csz = (long long)m0 * m1; cur_f32 = false;

@@ -36,6 +36,8 @@ struct FusedFwdArgs {
     int zoff;                                   // slab mode: global z of plane 0 of src (0 otherwise)
     int pair_lo, nl;                            // owned global pairs [pair_lo, pair_lo + nl) (0, n2/2 otherwise)
     int zpairs;                                 // output pairs per z-segment
+    int hi_off;                                 // plane offset of the z-high band relative to the z-low band (nl, or the
+                                                // global n2/2 when a piece of a whole box is produced)
     unsigned long long* in_min;  unsigned long long* in_max;     // field extrema keys (or null)
     unsigned long long* out_min; unsigned long long* out_max;    // coefficient extrema keys
 };
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) fwd_level_fused_kernel(FusedFwdAr
     // plane pointers of output pair mo = e0 - 4 (advanced once per pair; dereferenced for mo >= e0 only)
     const long long s01 = to_lll ? a.lsz : a.az;
     double* plo = a.coef + (long long)(e0 - 4 - a.pair_lo) * a.az;
-    double* phi = plo + (long long)a.nl * a.az;
+    double* phi = plo + (long long)a.hi_off * a.az;
     double* p01 = (to_lll ? a.lll : a.coef) + (long long)(e0 - 4 - a.pair_lo) * s01;
     double s0p[4] = {0, 0, 0, 0}, d0p[4] = {0, 0, 0, 0}, d1p[4] = {0, 0, 0, 0}, s1p[4] = {0, 0, 0, 0}, d2p[4] = {0, 0, 0, 0};
     const double kInf = __longlong_as_double(0x7ff0000000000000ll);
@@ -209,13 +211,14 @@ bool fused_forward_supported(int n0, int n1, int n2)
 void fused_forward_level(const void* src, int src_is_f32, long long ssy, long long ssz, double* coef, long long ay,
                          long long az, double* lll, int n0, int n1, int n2, unsigned long long* in_min,
                          unsigned long long* in_max, unsigned long long* out_min, unsigned long long* out_max,
-                         cudaStream_t s, int zoff, int pair_lo, int nl)
+                         cudaStream_t s, int zoff, int pair_lo, int nl, int hi_off)
 {
     FusedFwdArgs a{};
     a.src = src; a.ssy = ssy; a.ssz = ssz; a.coef = coef; a.ay = ay; a.az = az;
     a.lll = lll; a.lsy = n0 / 2; a.lsz = (long long)(n0 / 2) * (n1 / 2);
     a.n0 = n0; a.n1 = n1; a.n2 = n2;
     a.zoff = zoff; a.pair_lo = pair_lo; a.nl = (nl < 0) ? n2 / 2 : nl;
+    a.hi_off = (hi_off < 0) ? a.nl : hi_off;
     a.in_min = in_min; a.in_max = in_max; a.out_min = out_min; a.out_max = out_max;
     const int m0 = n0 / 2, m1 = n1 / 2, m2 = a.nl;
     const int gx = (m0 + FPX - 1) / FPX, gy = (m1 + FPY - 1) / FPY;

@@ -7,8 +7,11 @@
 namespace wrb {
 
 // ---- wavelet.cu ---------------------------------------------------------------------------
+// pipe != null (and level 1 fused, nz/2 >= 64): the field arrives in four z-pieces on another stream, pipe->ev[i] marks
+// piece i complete; level 1 then runs piece by piece behind the copy.  pipe->used tells the caller whether it did.
+struct HostSource { cudaEvent_t ev[4]; int used; };
 void wavelet_forward(const void* src, int src_is_f32, double* coef, double* tmp, double* lllA, double* lllB,
-                     int nx, int ny, int nz, int levels, DevState* st, cudaStream_t s);
+                     int nx, int ny, int nz, int levels, DevState* st, cudaStream_t s, HostSource* pipe = nullptr);
 // sym != null: the detail coefficients are rebuilt from the symbol planes inside the z pass (coef is then only
 // scratch); requires nz > 1 at every level, otherwise dequantise into coef first and pass sym = null
 // sink != null (and every level fused): the last level runs in z-pieces and every finished piece of `out` is copied
@@ -52,7 +55,7 @@ bool fused_forward_supported(int n0, int n1, int n2);
 void fused_forward_level(const void* src, int src_is_f32, long long ssy, long long ssz, double* coef, long long ay,
                          long long az, double* lll, int n0, int n1, int n2, unsigned long long* in_min,
                          unsigned long long* in_max, unsigned long long* out_min, unsigned long long* out_max,
-                         cudaStream_t s, int zoff = 0, int pair_lo = 0, int nl = -1);
+                         cudaStream_t s, int zoff = 0, int pair_lo = 0, int nl = -1, int hi_off = -1);
 
 // ---- wavelet_inv_fused.cu -----------------------------------------------------------------
 bool fused_inverse_supported(int n0, int n1, int n2);
