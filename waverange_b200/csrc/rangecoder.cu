@@ -522,7 +522,7 @@ __device__ __forceinline__ uint32_t dec_short(Dec& d)
     return t;
 }
 
-constexpr int kDecVariantDefault = 3;     // bit 0: lazy stream loads (see range_decode_kernel); bit 1 is unused since the stores are always packed
+constexpr int kDecVariantDefault = 1;     // bit 0: lazy stream loads (see range_decode_kernel)
 // Table footprint per chunk decides how many chunks an SM can hold (227 KB of shared memory), and with one or two lanes
 // per chunk that is what bounds the decoder: those variants take the compact form (single table entries, 128-wide LUT
 // buckets: 1.5 KB per chunk), four and eight lanes per chunk the fast form (entry pairs, 64-wide buckets: 3 KB).
@@ -537,17 +537,15 @@ __host__ __device__ constexpr bool dec_pair_table(int nsub) { return nsub >= 4; 
 // a short forward scan over the packed (cum, count) table (zero-count symbols are skipped by the
 // same scan, wrappers.cpp:205).  The lanes that share a chunk share its tables (column = chunk slot
 // inside the warp): all of them decode the identical table and store identical values.
-// The symbol loop is one dependency chain per lane and the warps are few (1-2 per scheduler), so what counts is
-// the length of that chain and the load/store unit time the warp's uncoalesced accesses take:
+// The symbol loop is one dependency chain per lane; with one or two lanes per chunk the warps are few and the length
+// of that chain counts, with eight lanes per chunk (~3 warps per scheduler) the number of instructions does:
 //   * stream words come through the read-only path (ld.global.nc);
 //   * renormalisation is branch-free (one funnel shift by 0/8/16);
-//   * pair table: entry s holds (ent[s], ent[s+1]) so one 64-bit shared load serves both probes.
-// VAR selects further variants (WRB_DEC_VARIANT, for A/B timing; all bit-identical):
-//   bit 0: lazy stream loads -- a new word is fetched (predicated) only by the lanes that crossed a word
-//          boundary, instead of two 32-sector loads per symbol;
-//   bit 1: packed stores -- a lane stores a 32-bit word when its output address completes one, bytes only
-//          for a ragged head/tail, instead of one 32-sector byte store per symbol.
-template <int NSUB, int VAR>
+//   * pair table: entry s holds (ent[s], ent[s+1]) so one 64-bit shared load serves both probes;
+//   * symbols leave as 32-bit words (groups of four), bytes only for a ragged head/tail.
+// LAZY (WRB_DEC_VARIANT bit 0, for A/B timing; both bit-identical): a new stream word is fetched (predicated) only
+// by the lanes that crossed a word boundary, one word ahead of its use, instead of two 32-sector loads per symbol.
+template <int NSUB, bool LAZY>
 __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restrict__ blob,
                                                           const unsigned long long* __restrict__ offs,
                                                           const unsigned long long* __restrict__ lay_off, ChunkGeom g,
@@ -555,9 +553,8 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
                                                           int* error)
 {
     constexpr unsigned int CPW = 32 / NSUB;
-    constexpr bool kLdg = true, kBranchFree = true, kPair = dec_pair_table(NSUB);
+    constexpr bool kPair = dec_pair_table(NSUB), kLazy = LAZY;
     constexpr int kLutShift = dec_lut_shift(NSUB), kLutSize = dec_lut_size(NSUB);
-    constexpr bool kLazy = (VAR & 1) != 0, kPack = (VAR & 2) != 0;
     constexpr unsigned int TW = kPair ? 2 : 1;                            // words per table entry
     extern __shared__ __align__(16) uint32_t smem_dyn[];
     uint32_t* tab = smem_dyn;                                             // [symbol][column] = cum << 16 | count (+ sentinel row)
@@ -639,7 +636,7 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
         const uint32_t* __restrict__ wbase = reinterpret_cast<const uint32_t*>(pa & ~3ull);
         const uint32_t boff = (uint32_t)(pa & 3ull);
         uint32_t a = boff + d.ip;
-        auto ldw = [&](uint32_t widx) -> uint32_t { return kLdg ? __ldg(wbase + widx) : wbase[widx]; };
+        auto ldw = [&](uint32_t widx) -> uint32_t { return __ldg(wbase + widx); };
         uint32_t w0 = ldw(a >> 2), w1 = ldw((a >> 2) + 1);
         uint32_t w2 = kLazy ? ldw((a >> 2) + 2) : 0u;
         uint32_t sel = 0x0123u + 0x1111u * (a & 3u);
@@ -752,10 +749,10 @@ void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, co
     const unsigned int nsub = g.nseek + 1;        // make_geom grants 0, 1, 3 or 7 seek points
     const unsigned int cpw = 32 / nsub;
     dim3 grid((g.nchunks + cpw - 1) / cpw, nlay, 1);
-    int variant = -1;
     // lazy stream loads with one word of lookahead beat two 32-sector loads per symbol at every lane count
     // (512^3, 1 / 3 / 7 seek points: 12.4 vs 13.1, 5.01 vs 5.59, 2.67 vs 3.11 ms)
-    if (variant < 0) { const char* e = getenv("WRB_DEC_VARIANT"); variant = (e && *e) ? (atoi(e) & 3) : kDecVariantDefault; }
+    const char* e = getenv("WRB_DEC_VARIANT");
+    const bool lazy = ((e && *e) ? atoi(e) : kDecVariantDefault) & 1;
     const int smem = (257 * 4 * (dec_pair_table((int)nsub) ? 2 : 1) + ((dec_lut_size((int)nsub) + 3) & ~3)) * (int)cpw;
 #define WRB_DEC_LAUNCH(NS, V)                                                                                          \
     do {                                                                                                               \
@@ -767,10 +764,7 @@ void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, co
         range_decode_kernel<NS, V><<<grid, 32, smem, s>>>(blob, offs, lay_off, g, sym, sym_layer_stride, error);       \
     } while (0)
 #define WRB_DEC_VARIANTS(NS)                                                                   \
-    switch (variant) {                                                                         \
-    case 0: WRB_DEC_LAUNCH(NS, 0); break; case 1: WRB_DEC_LAUNCH(NS, 1); break;                \
-    case 2: WRB_DEC_LAUNCH(NS, 2); break; default: WRB_DEC_LAUNCH(NS, 3); break;               \
-    }
+    do { if (lazy) WRB_DEC_LAUNCH(NS, true); else WRB_DEC_LAUNCH(NS, false); } while (0)
     switch (nsub) {
     case 1: WRB_DEC_VARIANTS(1); break;
     case 2: WRB_DEC_VARIANTS(2); break;
