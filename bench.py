@@ -187,7 +187,7 @@ def run_reference(args, rank, world):
                                        "(the reference is single-threaded); host has %d cores"
                                        % (edge, "field (the whole workload)" if edge == N_FIELD else "sub-cube", os.cpu_count())},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -370,7 +370,21 @@ def run_ours(args, rank, world, local_rank):
     if cpu is not None:
         line["cpu_baseline"] = cpu
         line["ratio_check"] = ratio_check
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the one JSON line, on the process's real stdout"""
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, text.encode())
 
 
 def main():
@@ -390,9 +404,13 @@ def main():
         run_reference(args, rank, world)
         return
     if world > 1:
-        # stdout must carry exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and "NCCL_DEBUG_FILE" not in os.environ:
-            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        # stdout must carry exactly one JSON line.  NCCL prints its version banner straight to file descriptor 1 (the
+        # torch-bundled build does so whatever NCCL_DEBUG_FILE says), so descriptor 1 points at stderr while the run
+        # lasts and the JSON line goes to the saved descriptor (emit()).
+        global _REAL_STDOUT
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
