@@ -84,7 +84,7 @@ def synth_field(torch, n, seed, device, dtype, nm=48, expo=-5.0 / 6.0, nz_total=
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -98,39 +98,61 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile(prefix="wrb_clocks_", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=f,
+                                          "--format=csv,noheader,nounits", "-lms", "10"], stdout=f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    @staticmethod
+    def _stamp(text):
+        """nvidia-smi timestamp 'YYYY/MM/DD HH:MM:SS.mmm' (local time) -> seconds since the epoch"""
+        import datetime
+        try:
+            return datetime.datetime.strptime(text, "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, t0=None, t1=None):
+        """Median clock and throttle reasons of the samples taken inside [t0, t1] (time.time() at the ends of the timed
+        region; nvidia-smi runs since before the warm-up, so it is sampling when the region starts).  A region shorter
+        than the sampling interval can hold none: then the samples of the 50 ms around it are used and `window` says so."""
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 p = [s.strip() for s in line.split(",")]
                 if len(p) < 9:
                     continue
                 try:
-                    sm.append(float(p[1])); mx.append(float(p[2]))
+                    rows.append((self._stamp(p[0]), float(p[1]), float(p[2]), p[5:9]))
                 except ValueError:
                     continue
-                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], p[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        window = "timed region"
+        pick = rows
+        if t0 is not None and t1 is not None and any(r[0] is not None for r in rows):
+            pick = [r for r in rows if r[0] is not None and t0 <= r[0] <= t1]
+            if len(pick) < 2:
+                pick = [r for r in rows if r[0] is not None and t0 - 0.05 <= r[0] <= t1 + 0.05]
+                window = "timed region +- 50 ms (region shorter than the sampling interval)"
+        reasons = set()
+        for r in pick:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if pick:
+            out.update(sm_mhz=statistics.median([r[1] for r in pick]), sm_max_mhz=max(r[2] for r in pick),
+                       reasons=sorted(reasons), samples=len(pick), window=window, samples_whole_run=len(rows))
         return out
 
 
@@ -207,6 +229,9 @@ def run_ours(args, rank, world, local_rank):
     field = synth_field(torch, n, 1234, dev, torch.float32, nz_total=nz_total, z0=z0, nzl=n)
     nbytes = ntot * 4
 
+    sampler = ClockSampler(local_rank)          # started before the warm-up: nvidia-smi needs ~0.1 s to produce its first line
+    if rank == 0:
+        sampler.start()
     stream = torch.cuda.current_stream()
     codec = api.Codec(device=local_rank, stream=stream.cuda_stream)
     codec.set_timing(True)
@@ -243,11 +268,9 @@ def run_ours(args, rank, world, local_rank):
         h = encode_dev(field.data_ptr(), blob.data_ptr())
         decode_dev(recon.data_ptr(), h, blob.data_ptr())
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = codec.launch_count()
     t_wall0 = time.perf_counter()
+    t_region0 = time.time()
     tot_ev0 = torch.cuda.Event(enable_timing=True)
     tot_ev1 = torch.cuda.Event(enable_timing=True)
     tot_ev0.record(stream)
@@ -266,8 +289,8 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     launches = codec.launch_count() - launches0
     step_ms = tot_ev0.elapsed_time(tot_ev1) / args.steps
-    clocks = sampler.stop() if rank == 0 else None
     wall_ms = (time.perf_counter() - t_wall0) * 1e3 / args.steps
+    clocks = sampler.stop(t_region0, time.time()) if rank == 0 else None
 
     # correctness guard inside the bench: the reconstruction meets the requested tolerance
     errt = torch.stack([(recon.view(n, n, n).double() - field.double()).abs().max(), field.double().abs().max()])
