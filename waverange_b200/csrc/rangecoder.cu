@@ -524,11 +524,16 @@ __device__ __forceinline__ uint32_t dec_short(Dec& d)
 
 constexpr int kDecVariantDefault = 1;     // bit 0: lazy stream loads (see range_decode_kernel)
 // Table footprint per chunk decides how many chunks an SM can hold (227 KB of shared memory), and with one or two lanes
-// per chunk that is what bounds the decoder: those variants take the compact form (single table entries, 128-wide LUT
-// buckets: 1.5 KB per chunk), four and eight lanes per chunk the fast form (entry pairs, 64-wide buckets: 3 KB).
+// per chunk that is what bounds the decoder: those variants take the compact form (16-bit cumulative counts only -- a
+// count is the difference of two neighbours -- and 128-wide LUT buckets: 1 KB per chunk), four and eight lanes per
+// chunk the fast form (cum/count entry pairs, 64-wide buckets: 3 KB).
 __host__ __device__ constexpr int dec_lut_shift(int nsub) { return nsub >= 4 ? 6 : 7; }
 __host__ __device__ constexpr int dec_lut_size(int nsub) { return (kBlock >> dec_lut_shift(nsub)) + 1; }   // 938 / 469 buckets
 __host__ __device__ constexpr bool dec_pair_table(int nsub) { return nsub >= 4; }
+__host__ __device__ constexpr int dec_table_bytes(int nsub)      // per chunk: symbol table + LUT (rounded to words)
+{
+    return (dec_pair_table(nsub) ? 257 * 8 : 258 * 2) + ((dec_lut_size(nsub) + 3) & ~3);
+}
 
 // grid (ceil(nchunks/CPW), layers), block 32: lane == (chunk column, sub-chunk); NSUB lanes decode one
 // chunk, CPW = 32/NSUB chunks per warp.   wrappers.cpp:153-224
@@ -558,7 +563,9 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
     constexpr unsigned int TW = kPair ? 2 : 1;                            // words per table entry
     extern __shared__ __align__(16) uint32_t smem_dyn[];
     uint32_t* tab = smem_dyn;                                             // [symbol][column] = cum << 16 | count (+ sentinel row)
-    uint8_t* lut = reinterpret_cast<uint8_t*>(smem_dyn + 257 * CPW * TW); // [bucket][column]
+    uint16_t* cum16 = reinterpret_cast<uint16_t*>(smem_dyn);              // compact form: [symbol 0..257][column] = cum
+    uint8_t* lut = kPair ? reinterpret_cast<uint8_t*>(smem_dyn + 257 * CPW * TW)      // [bucket][column]
+                         : reinterpret_cast<uint8_t*>(smem_dyn) + 258 * CPW * 2;
     const int layer = blockIdx.y;
     const unsigned int lane = threadIdx.x;
     const unsigned int col = lane / NSUB, sub = lane % NSUB;
@@ -588,8 +595,12 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
         int nextb = 0;                            // first bucket not yet assigned
         for (int s = 0; s < 256; s++) {           // readcounts (rangecod.c:400-404) + prefix sums
             const uint32_t c = dec_short(d);
-            tab[(s * CPW + col) * TW] = (acc << 16) | c;
-            if (kPair && s > 0) tab[((s - 1) * CPW + col) * TW + 1] = (acc << 16) | c;
+            if (kPair) {
+                tab[(s * CPW + col) * TW] = (acc << 16) | c;
+                if (s > 0) tab[((s - 1) * CPW + col) * TW + 1] = (acc << 16) | c;
+            } else {
+                cum16[s * CPW + col] = (uint16_t)acc;
+            }
             if (c) {
                 const int lastb = (int)((acc + c - 1) >> kLutShift);
                 if (lastb < kLutSize) for (; nextb <= lastb; nextb++) lut[nextb * CPW + col] = (uint8_t)s;
@@ -599,8 +610,13 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
             if (acc > kBlock) { bad = true; break; }
         }
         if (bad) break;
-        tab[(256 * CPW + col) * TW] = 0xFFFF0000u;       // sentinel: never satisfies cum + count <= cf
-        if (kPair) { tab[(255 * CPW + col) * TW + 1] = 0xFFFF0000u; tab[(256 * CPW + col) * TW + 1] = 0xFFFF0000u; }
+        if (kPair) {                                     // entries past the last symbol: read, never chosen (s < lastsym guards)
+            tab[(256 * CPW + col) * TW] = 0xFFFF0000u;
+            tab[(255 * CPW + col) * TW + 1] = 0xFFFF0000u; tab[(256 * CPW + col) * TW + 1] = 0xFFFF0000u;
+        } else {
+            cum16[256 * CPW + col] = (uint16_t)acc;      // cum[256] = block size: count[255] = cum[256] - cum[255]
+            cum16[257 * CPW + col] = (uint16_t)acc;
+        }
         const uint32_t bs = acc;
         if (n + bs > clen) { bad = true; break; }
         uint32_t s0 = 0, s1 = bs;
@@ -689,27 +705,34 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
             }
             q = min(q, bs - 1);                   // V / help can exceed tot (the remainder range / tot leaves): last bucket
             uint32_t s = ll[(q >> kLutShift) * CPW];
-            uint32_t e0, e1;                      // entries s and s + 1, both loads issued together
+            uint32_t lt, sy;                      // cum and count of the symbol found
             if (kPair) {
-                const uint2 e = *reinterpret_cast<const uint2*>(tl + s * (CPW * 2));
-                e0 = e.x; e1 = e.y;
+                const uint2 e = *reinterpret_cast<const uint2*>(tl + s * (CPW * 2));      // entries s and s + 1 in one load
+                const bool adv = s < lastsym && help * (e.y >> 16) <= V;
+                uint32_t ent = adv ? e.y : e.x;
+                s += adv ? 1u : 0u;
+                if (adv) {                        // rare: more than one step from the bucket's first symbol
+                    uint32_t nx = tl[(s + 1) * (CPW * TW)];
+                    while (s < lastsym && help * (nx >> 16) <= V) { s++; ent = nx; nx = tl[(s + 1) * (CPW * TW)]; }
+                }
+                // (testing help * (cum + count) of the chosen entry instead -- no load, branch rarely taken -- measured
+                //  slower: 2.94 vs 2.69 ms at 8 lanes per chunk, 15.2 vs 13.0 ms at 2)
+                lt = ent >> 16; sy = ent & 0xFFFFu;
             } else {
-                const uint32_t sa = (uint32_t)__cvta_generic_to_shared(tl + s * CPW);
-                asm volatile("ld.shared.u32 %0, [%2];\n\tld.shared.u32 %1, [%2+%3];"
-                             : "=r"(e0), "=r"(e1) : "r"(sa), "n"(CPW * 4));
+                const uint16_t* cl = cum16 + col + s * CPW;                               // cum[s], cum[s+1], cum[s+2]
+                const uint32_t c0 = cl[0], c1 = cl[CPW], c2 = cl[2 * CPW];
+                const bool adv = s < lastsym && help * c1 <= V;
+                lt = adv ? c1 : c0;
+                uint32_t nx = adv ? c2 : c1;
+                s += adv ? 1u : 0u;
+                if (adv) {
+                    while (s < lastsym && help * nx <= V) { s++; lt = nx; nx = cum16[col + (s + 1) * CPW]; }
+                }
+                sy = nx - lt;
             }
-            const bool adv = s < lastsym && help * (e1 >> 16) <= V;
-            uint32_t ent = adv ? e1 : e0;
-            s += adv ? 1u : 0u;
-            if (adv) {                            // rare: more than one step from the bucket's first symbol
-                uint32_t nx = tl[(s + 1) * (CPW * TW)];
-                while (s < lastsym && help * (nx >> 16) <= V) { s++; ent = nx; nx = tl[(s + 1) * (CPW * TW)]; }
-            }
-            // (testing help * (cum + count) of the chosen entry instead -- no load, branch rarely taken -- measured
-            //  slower: 2.94 vs 2.69 ms at 8 lanes per chunk, 15.2 vs 13.0 ms at 2)
-            const uint32_t tmp = help * (ent >> 16);          // decode_update
+            const uint32_t tmp = help * lt;                   // decode_update
             X -= 2 * tmp;
-            range = (s != lastsym) ? help * (ent & 0xFFFFu) : range - tmp;
+            range = (s != lastsym) ? help * sy : range - tmp;
             return s;
         };
         uint32_t head = (4u - ((uint32_t)(unsigned long long)op & 3u)) & 3u;
@@ -753,7 +776,7 @@ void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, co
     // (512^3, 1 / 3 / 7 seek points: 12.4 vs 13.1, 5.01 vs 5.59, 2.67 vs 3.11 ms)
     const char* e = getenv("WRB_DEC_VARIANT");
     const bool lazy = ((e && *e) ? atoi(e) : kDecVariantDefault) & 1;
-    const int smem = (257 * 4 * (dec_pair_table((int)nsub) ? 2 : 1) + ((dec_lut_size((int)nsub) + 3) & ~3)) * (int)cpw;
+    const int smem = dec_table_bytes((int)nsub) * (int)cpw;
 #define WRB_DEC_LAUNCH(NS, V)                                                                                          \
     do {                                                                                                               \
         static bool configured = false;                                                                                \
