@@ -185,13 +185,17 @@ def test_encode_chunks_bit_exact_and_decode(codec, torch_cuda, oracle, shape, to
     assert np.abs(want_rec - f).max() <= tol * np.abs(f).max()
 
 
+@pytest.mark.parametrize("tables", ["auto", "pair", "compact"])
 @pytest.mark.parametrize("nseek", [-1, 0, 1, 3, 7])
-def test_seek_points_change_neither_streams_nor_reconstruction(product_lib, torch_cuda, oracle, nseek):
+def test_seek_points_change_neither_streams_nor_reconstruction(product_lib, torch_cuda, oracle, monkeypatch, nseek, tables):
     """Seek points (decoder entry points inside a chunk) only add table bytes: for every setting the chunk streams are the
     oracle's and the decoder -- running nseek+1 lanes per chunk -- returns the reference's reconstruction.  The field has a
     short last chunk (lanes without work, unused table entries).  -1 = the encoder's own choice, bounded to keep the
-    container within 1 % of the reference's streams."""
+    container within 1 % of the reference's streams.  The decoder's two table forms (WRB_DEC_TABLES; by default chosen
+    from the grid size) must both give the same symbols."""
     from waverange_b200 import api
+    if tables != "auto":                                  # both table forms of the decoder at every lane count
+        monkeypatch.setenv("WRB_DEC_TABLES", tables)
     shape, tol = (70, 64, 96), 1e-7                      # 430080 symbols: 7 full chunks + one of 10087
     f = oracle.probe_field(shape, seed=11, nm=20)
     c = api.Codec(device=0)

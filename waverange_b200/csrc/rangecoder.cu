@@ -524,15 +524,27 @@ __device__ __forceinline__ uint32_t dec_short(Dec& d)
 
 constexpr int kDecVariantDefault = 1;     // bit 0: lazy stream loads (see range_decode_kernel)
 // Table footprint per chunk decides how many chunks an SM can hold (227 KB of shared memory), and with one or two lanes
-// per chunk that is what bounds the decoder: those variants take the compact form (16-bit cumulative counts only -- a
-// count is the difference of two neighbours -- and 128-wide LUT buckets: 1 KB per chunk), four and eight lanes per
-// chunk the fast form (cum/count entry pairs, 64-wide buckets: 3 KB).
-__host__ __device__ constexpr int dec_lut_shift(int nsub) { return nsub >= 4 ? 6 : 7; }
-__host__ __device__ constexpr int dec_lut_size(int nsub) { return (kBlock >> dec_lut_shift(nsub)) + 1; }   // 938 / 469 buckets
-__host__ __device__ constexpr bool dec_pair_table(int nsub) { return nsub >= 4; }
-__host__ __device__ constexpr int dec_table_bytes(int nsub)      // per chunk: symbol table + LUT (rounded to words)
+// per chunk that is what bounds the decoder.  Two forms: compact (16-bit cumulative counts only -- a count is the
+// difference of two neighbours -- and 128-wide LUT buckets: 1 KB per chunk) and fast (cum/count entry pairs, 64-wide
+// buckets: 3 KB, three instructions per symbol fewer).
+// The form is a launch-time choice (decode_uses_pair_tables): the fast form while the whole grid is resident with it,
+// the compact form for one and two lanes per chunk and whenever shared memory would cap the resident blocks.
+__host__ __device__ constexpr int dec_lut_shift(bool pair) { return pair ? 6 : 7; }
+__host__ __device__ constexpr int dec_lut_size(bool pair) { return (kBlock >> dec_lut_shift(pair)) + 1; }   // 938 / 469 buckets
+__host__ __device__ constexpr int dec_table_bytes(bool pair)     // per chunk: symbol table + LUT (rounded to words)
 {
-    return (dec_pair_table(nsub) ? 257 * 8 : 258 * 2) + ((dec_lut_size(nsub) + 3) & ~3);
+    return (pair ? 257 * 8 : 258 * 2) + ((dec_lut_size(pair) + 3) & ~3);
+}
+static bool decode_uses_pair_tables(unsigned int nsub, unsigned long long blocks)
+{
+    const char* e = getenv("WRB_DEC_TABLES");                     // "pair" / "compact": force a form (tests, A/B timing)
+    if (e && *e == 'p') return true;
+    if (e && *e == 'c') return false;
+    if (nsub < 4) return false;
+    const unsigned long long per_block = (unsigned long long)dec_table_bytes(true) * (32 / nsub);
+    unsigned long long resident = (227ull * 1024) / per_block;    // blocks of one warp per SM, by shared memory
+    if (resident > 32) resident = 32;
+    return blocks <= 148ull * resident;
 }
 
 // grid (ceil(nchunks/CPW), layers), block 32: lane == (chunk column, sub-chunk); NSUB lanes decode one
@@ -550,7 +562,7 @@ __host__ __device__ constexpr int dec_table_bytes(int nsub)      // per chunk: s
 //   * symbols leave as 32-bit words (groups of four), bytes only for a ragged head/tail.
 // LAZY (WRB_DEC_VARIANT bit 0, for A/B timing; both bit-identical): a new stream word is fetched (predicated) only
 // by the lanes that crossed a word boundary, one word ahead of its use, instead of two 32-sector loads per symbol.
-template <int NSUB, bool LAZY>
+template <int NSUB, bool LAZY, bool PAIR>
 __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restrict__ blob,
                                                           const unsigned long long* __restrict__ offs,
                                                           const unsigned long long* __restrict__ lay_off, ChunkGeom g,
@@ -558,8 +570,8 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
                                                           int* error)
 {
     constexpr unsigned int CPW = 32 / NSUB;
-    constexpr bool kPair = dec_pair_table(NSUB), kLazy = LAZY;
-    constexpr int kLutShift = dec_lut_shift(NSUB), kLutSize = dec_lut_size(NSUB);
+    constexpr bool kPair = PAIR, kLazy = LAZY;
+    constexpr int kLutShift = dec_lut_shift(PAIR), kLutSize = dec_lut_size(PAIR);
     constexpr unsigned int TW = kPair ? 2 : 1;                            // words per table entry
     extern __shared__ __align__(16) uint32_t smem_dyn[];
     uint32_t* tab = smem_dyn;                                             // [symbol][column] = cum << 16 | count (+ sentinel row)
@@ -776,18 +788,22 @@ void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, co
     // (512^3, 1 / 3 / 7 seek points: 12.4 vs 13.1, 5.01 vs 5.59, 2.67 vs 3.11 ms)
     const char* e = getenv("WRB_DEC_VARIANT");
     const bool lazy = ((e && *e) ? atoi(e) : kDecVariantDefault) & 1;
-    const int smem = dec_table_bytes((int)nsub) * (int)cpw;
-#define WRB_DEC_LAUNCH(NS, V)                                                                                          \
+    const bool pair = decode_uses_pair_tables(nsub, (unsigned long long)grid.x * grid.y);
+    const int smem = dec_table_bytes(pair) * (int)cpw;
+#define WRB_DEC_LAUNCH(NS, V, P)                                                                                       \
     do {                                                                                                               \
         static bool configured = false;                                                                                \
-        if (!configured) {      /* one lane per chunk needs more than the 48 KB default */                             \
-            cudaFuncSetAttribute(range_decode_kernel<NS, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
+        if (!configured) {      /* the fast form with one lane per chunk needs more than the 48 KB default */           \
+            cudaFuncSetAttribute(range_decode_kernel<NS, V, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
             configured = true;                                                                                         \
         }                                                                                                              \
-        range_decode_kernel<NS, V><<<grid, 32, smem, s>>>(blob, offs, lay_off, g, sym, sym_layer_stride, error);       \
+        range_decode_kernel<NS, V, P><<<grid, 32, smem, s>>>(blob, offs, lay_off, g, sym, sym_layer_stride, error);    \
     } while (0)
-#define WRB_DEC_VARIANTS(NS)                                                                   \
-    do { if (lazy) WRB_DEC_LAUNCH(NS, true); else WRB_DEC_LAUNCH(NS, false); } while (0)
+#define WRB_DEC_VARIANTS(NS)                                                                                 \
+    do {                                                                                                     \
+        if (pair) { if (lazy) WRB_DEC_LAUNCH(NS, true, true); else WRB_DEC_LAUNCH(NS, false, true); }        \
+        else      { if (lazy) WRB_DEC_LAUNCH(NS, true, false); else WRB_DEC_LAUNCH(NS, false, false); }      \
+    } while (0)
     switch (nsub) {
     case 1: WRB_DEC_VARIANTS(1); break;
     case 2: WRB_DEC_VARIANTS(2); break;
