@@ -17,6 +17,10 @@
                                  .wrh/.wrb file-format parity tests
      wrmssgenc_ref, wrmssgdec_ref  the reference's MSSG front-ends (strict flags), used by the MSSG
                                  file-layout parity tests
+     *_dropin                    the reference's front-end sources (gen_enc.cpp, gen_dec.cpp, mssg_enc.cpp,
+                                 mssg_dec.cpp + their aux files) compiled unmodified and linked against
+                                 waverange_b200/libwaverange_b200.so INSTEAD of the reference's library objects:
+                                 the drop-in claim at link level (tests/test_dropin_gpu.py runs them on the GPU)
    The reference's own Makefiles are not run: three C/C++ files are compiled
    directly (src/core/Makefile:6-23 lists the same three objects).
 """
@@ -116,10 +120,37 @@ def build_ref(force=False):
     return outs
 
 
+def build_dropin(force=False):
+    """reference front-ends + the product library (built before this is called; skipped when it is missing)"""
+    src = os.path.join(REF, "src")
+    lib = os.path.join(os.path.dirname(HERE), "waverange_b200", "libwaverange_b200.so")
+    if not os.path.isdir(src) or not os.path.exists(lib):
+        return None
+    outdir = os.path.join(HERE, "_ref")
+    os.makedirs(outdir, exist_ok=True)
+    flags = ["-O2", "-ffp-contract=off", "-w", "-D__STDC_LIMIT_MACROS"]
+    link = ["-L" + os.path.dirname(lib), "-lwaverange_b200", "-Wl,-rpath,$ORIGIN/../../waverange_b200"]
+    jobs = {
+        "wrenc_dropin": ["generic/gen_enc.cpp", "generic/gen_aux.cpp"],
+        "wrdec_dropin": ["generic/gen_dec.cpp", "generic/gen_aux.cpp"],
+        "wrmssgenc_dropin": ["mssg/mssg_enc.cpp", "mssg/ctrl_aux.cpp"],
+        "wrmssgdec_dropin": ["mssg/mssg_dec.cpp", "mssg/ctrl_aux.cpp"],
+    }
+    outs = {}
+    for exe, rel in jobs.items():
+        out = os.path.join(outdir, exe)
+        srcs = [os.path.join(src, r) for r in rel]
+        if force or newer(out, srcs + [lib, __file__]):
+            run(["g++"] + flags + ["-o", out] + srcs + link)
+        outs[exe] = out
+    return outs
+
+
 def main():
     force = "--force" in sys.argv
     build_restatement(force)
     build_ref(force)
+    build_dropin(force)
 
 
 if __name__ == "__main__":

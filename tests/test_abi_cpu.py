@@ -65,3 +65,45 @@ def test_product_does_not_reference_oracle():
                 if f == "api.py" and re.search(r"import\s+oracle|from\s+oracle|wr_oracle", txt):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_public_headers_compile_as_plain_c(tmp_path):
+    """the device / file / MSSG headers are a C ABI: they must compile as C99 (waverange.h carries the reference's C++
+    reference parameters and is checked as C++)"""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    inc = os.path.join(ROOT, "include")
+    for h in ("waverange_b200.h", "waverange_files.h", "waverange_mssg.h"):
+        src = tmp_path / (h + ".c")
+        src.write_text('#include "%s"\nint main(void) { return 0; }\n' % os.path.join(inc, h))
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", str(src)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    src = tmp_path / "ref.cpp"
+    src.write_text('#include "%s"\nint main() { return 0; }\n' % os.path.join(inc, "waverange.h"))
+    r = subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_reference_front_ends_link_against_the_library_and_refuse_to_run_without_a_gpu(product_lib, tmp_path):
+    """oracle/_ref/*_dropin = the reference's unmodified front-end sources linked against libwaverange_b200.so: the
+    link succeeds (every symbol they need is exported with the reference's ABI) and, without a CUDA device, the run
+    fails loudly instead of falling back to a CPU path"""
+    import subprocess
+    import torch
+    from oracle import build_oracle
+    if os.path.isdir("/root/reference/src"):
+        build_oracle.build_dropin()
+    exe = os.path.join(ROOT, "oracle", "_ref", "wrenc_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/wrenc_dropin not built")
+    r = subprocess.run(["ldd", exe], capture_output=True, text=True)
+    assert "libwaverange_b200.so" in r.stdout and "not found" not in r.stdout
+    if torch.cuda.is_available():
+        return
+    np.arange(16 ** 3, dtype=np.float64).tofile(tmp_path / "data.bin")
+    r = subprocess.run([exe, "data.bin", "data.wrb", "data.wrh", "2", "0", "1", "2", "16", "16", "16", "1e-6"], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
