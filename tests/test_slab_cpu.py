@@ -148,3 +148,17 @@ def test_global_order_maps(world, shape):
         allruns[r, :len(x)] = torch.from_numpy(x)
     for r, go in enumerate(gos):
         assert np.array_equal(go.scatter_local(allruns, pitch).numpy(), local[r])
+
+
+def test_wrck_container_helper_matches_the_parser():
+    """slab.wrck_container (joins the chunk streams the ranks coded in global symbol order) writes what
+    api.parse_container -- and the decoder -- read: version 3, no seek points, u32 lengths, streams back to back"""
+    import numpy as np
+    from waverange_b200 import api, slab
+    rng = np.random.default_rng(0)
+    streams = [bytes(rng.integers(0, 256, n, dtype=np.uint8)) for n in (7, 513, 1, 9000)]
+    blob = slab.wrck_container(59999, 3 * 59999 + 17, [len(s) for s in streams], b"".join(streams))
+    assert blob[:4] == b"WRCK" and int.from_bytes(blob[4:8], "little") == 3
+    assert int.from_bytes(blob[24:28], "little") == 4 and int.from_bytes(blob[28:32], "little") == 0
+    chunk_len, got = api.parse_container(np.frombuffer(blob, dtype=np.uint8))
+    assert chunk_len == 59999 and got == streams
