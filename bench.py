@@ -13,7 +13,13 @@ D2H copies inside the timed region).  With N > 1 (torchrun) every rank codes its
 (independent fields shard with no data-path collective) -> weak scaling.
 
 --impl reference times the reference's own CPU implementation (oracle/_ref, stock-style FMA
-build; single-threaded like the reference) on a bounded 256^3 sample of the same field.
+build; single-threaded like the reference) on the whole 512^3 field (about 20 s per step on one core; with N > 1
+on one rank's 512^3 share of the N-times larger field, a bounded sample).
+
+At N = 1 the line also carries a `configs` block (outside the headline's timed region): the other configurations of
+BASELINE.json -- C1 256^3 incl. the wall clock of the reference's wrenc/wrdec beside this repo's, C3 1024^3 float64
+(one field and the four fields of a backup), C5 512^3 float64 at three tolerances -- each with device GB/s, the
+fraction of the HBM roofline of its transform + quantise scope, layer count and size.  --no-configs skips it.
 """
 import argparse
 import json
@@ -33,12 +39,42 @@ import numpy as np  # noqa: E402
 
 N_FIELD = 512
 TOL = 1e-4
-SAMPLE = 256            # edge of the CPU-baseline sample cube when the whole workload would take too long (2 s per pass)
+SAMPLE = 256            # edge of the CPU-baseline sample cube, only used when the whole-field leg fails (host memory)
 METRIC = "raw-field compress+decompress throughput (device-timed)"
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the forward-wavelet + quantise kernels of one compress of
-# the default workload, from the ncu --set full capture profiles/r1j_ncu_raw_512.csv:
-# forward levels 1-4: 1.578 + 0.249 + 0.017 + 0.002 GB, quantise 3 x (1.076 + 0.131) GB
-NCU_TRAFFIC_512 = int((1.578 + 0.249 + 0.017 + 0.002 + 3 * (1.076 + 0.131)) * 1e9)
+KERNEL_SOURCES = ["wavelet_fused.cu", "wavelet_pairs.cuh", "wr_common.cuh", "quant.cu"]     # the roofline scope's kernels
+
+
+def kernels_sha():
+    """hash of the sources of the kernels the roofline is quoted on: an ncu traffic figure is only printed when it
+    was captured from exactly these sources"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "waverange_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(n, nlay):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the forward-transform + quantise kernels of ONE compress, from the
+    newest profiles/traffic_*.json (written by tools/ncu_traffic.py from an `ncu --set full` capture) that was taken
+    on the current kernel sources at this size and layer count; None (-> null) otherwise."""
+    import glob
+    best = None
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json"))):
+        try:
+            t = json.load(open(p))
+            t["_file"] = p
+        except Exception:
+            continue
+        if t.get("kernels_sha") == kernels_sha() and t.get("edge") == n and t.get("nlay") == nlay:
+            best = t
+    if best is None:
+        return None, None
+    return int(best["dram_bytes"]), {"file": "profiles/" + os.path.basename(best["_file"]), "commit": best.get("commit"),
+                                     "kernels_sha": best.get("kernels_sha")}
+
+
 UNIT = "GB/s"
 
 
@@ -156,6 +192,22 @@ class ClockSampler:
         return out
 
 
+def workload_config(n, world):
+    """`config` of the JSON line: the same dict in both arms (it describes the workload, not the result)"""
+    if world == 1:
+        shape = "%d^3" % n
+        fields = "one %dx%dx%d field" % (n, n, n)
+    else:
+        shape = "%dx%dx%d" % (n, n, n * world)
+        fields = ("one %dx%dx%d field, z-slab partitioned over %d GPUs (%d planes each): NCCL halo exchange per level "
+                  "(4 planes below / 3 above), all-reduce of the extrema per layer" % (n, n, n * world, world, n))
+    tag = " (BASELINE.json configs[1])" if (n == N_FIELD and world == 1) else \
+          (" (configs[1]'s field extended along z, weak scaling; configs[3]'s partition)" if n == N_FIELD else " (profiling size)")
+    return {"workload": "%s float32 turbulence-like field, tol 1e-4%s" % (shape, tag),
+            "field_bytes": n * n * n * world * 4, "tolerance": TOL, "fields": fields,
+            "l2": "inputs (0.5 GB field per GPU, 1-2 GB of coefficients and symbols) exceed the 126 MB L2; no explicit flush"}
+
+
 def reference_lib():
     from oracle.binding import Reference, Restatement
     if Reference.available("fma"):
@@ -177,16 +229,16 @@ def cpu_time_sample(sample_f64, tol):
 
 
 def run_reference(args, rank, world):
+    """The reference's own code (oracle/_ref) on the host, single-threaded like the reference, on the WHOLE 512^3 field of
+    the N = 1 workload -- the same config as our arm.  With N > 1 our arm codes an N-times larger field in z-slabs; the
+    reference (about 20 s per 512^3 on one core) then codes one rank's 512^3 share of it per step: a bounded sample."""
     if rank != 0:
         return
     import torch
     dev = "cuda" if torch.cuda.is_available() else "cpu"
-    n = N_FIELD if dev == "cuda" else SAMPLE
-    fld = synth_field(torch, n, 1234, dev, torch.float32)
-    # the whole 512^3 workload (17 s of single-threaded CPU work per step) when the run stays within a few minutes,
-    # else the 256^3 corner of it
-    edge = n if (n == N_FIELD and args.steps + args.warmup <= 10) else SAMPLE
-    sample = fld[:edge, :edge, :edge].contiguous().cpu().numpy().astype(np.float64)
+    n = args.size if dev == "cuda" else min(args.size, SAMPLE)      # without a GPU (this container): a small smoke run
+    fld = synth_field(torch, n, 1234, dev, torch.float32, nz_total=n * world, z0=0, nzl=n)
+    sample = fld.contiguous().cpu().numpy().astype(np.float64)
     del fld
     times = []
     kind = "port"
@@ -198,16 +250,17 @@ def run_reference(args, rank, world):
     td = statistics.mean(t[1] for t in times)
     nbytes = sample.size * 4
     val = 2 * nbytes / (te + td) / 1e9
+    what = ("the whole %d^3 field" % n) if world == 1 else \
+           ("rank 0's %d^3 slab of the %dx%dx%d field (1/%d of the workload per step)" % (n, n, n, n * world, world))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": (te + td) * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "512^3 float32 turbulence-like field, tol 1e-4 (BASELINE.json configs[1])",
-                       "sample": ("the whole field" if edge == N_FIELD else "%d^3 corner sub-cube of the same field" % edge)},
+            "vs_baseline": None, "dtype": "f64", "input_dtype": "f32", "data": "synthetic",
+            "config": workload_config(n, world),
+            "result": {"nlay": int(h.nlay), "ntot_enc": int(h.ntot_enc), "ratio_vs_f32": nbytes / max(1, int(h.ntot_enc))},
             "compress_gbs": nbytes / te / 1e9, "decompress_gbs": nbytes / td / 1e9,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind,
-                             "sample": "%d^3 f32-valued %s, encoding_wrap+decoding_wrap in process, 1 thread "
-                                       "(the reference is single-threaded); host has %d cores"
-                                       % (edge, "field (the whole workload)" if edge == N_FIELD else "sub-cube", os.cpu_count())},
+                             "sample": "%s, encoding_wrap %.2f s + decoding_wrap %.2f s in process, 1 thread (the "
+                                       "reference is single-threaded); host has %d cores" % (what, te, td, os.cpu_count())},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -369,17 +422,15 @@ def run_ours(args, rank, world, local_rank):
             print("bench: cpu_baseline on the whole field failed (%r); using the %d^3 sample" % (exc, SAMPLE), file=sys.stderr)
             ratio_check, cpu = cpu_leg(min(n, SAMPLE))
 
+    traffic, traffic_src = measured_traffic(n, nlay) if not slab_mode else (None, None)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "input_dtype": "f32",          # arithmetic of the path (transform + quantiser in f64, coder in u32) / the field's own type
         "data": "synthetic",
-        "config": {"workload": "%d^3 float32 turbulence-like field, tol 1e-4%s" % (n, " (BASELINE.json configs[1])" if n == N_FIELD else " (profiling size)"),
-                   "field_bytes": nbytes, "tolerance": TOL, "nlay": nlay, "ntot_enc": int(h.ntot_enc),
-                   "ratio_vs_f32": nbytes / max(1, int(h.ntot_enc)), "chunk_symbols": 59999,
-                   "fields": ("one %dx%dx%d field" % (n, n, n)) if world == 1 else
-                             ("one %dx%dx%d field, z-slab partitioned over %d GPUs: NCCL halo exchange per level "
-                              "(4 planes below / 3 above), all_reduce of extrema per layer" % (n, n, n * world, world)),
-                   "l2": "working set (0.5 GB field + 2 GB scratch) exceeds the 126 MB L2; no explicit flush"},
+        "config": workload_config(n, world),
+        "result": {"nlay": nlay, "ntot_enc": int(h.ntot_enc), "ratio_vs_f32": nbytes / max(1, int(h.ntot_enc)),
+                   "chunk_symbols": 59999, "layer_guess_misses": codec.layer_guess_misses()},
         "compress_gbs": world * nbytes / (enc_mean * 1e-3) / 1e9,
         "decompress_gbs": world * nbytes / (dec_mean * 1e-3) / 1e9,
         "rel_linf_error": err / amax,
@@ -388,10 +439,17 @@ def run_ours(args, rank, world, local_rank):
                       "encode_total": enc_mean, "decode_total": dec_mean},
         "roofline": {"bound": "hbm", "scope": "forward wavelet + quantise kernels of one compress (stage events)",
                      "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     # dram__bytes_read+write of those kernels from the ncu --set full captures of this workload
-                     # (profiles/r1j_ncu_raw_512.csv), per compress
-                     "traffic": (NCU_TRAFFIC_512 if (n == N_FIELD and nlay == 3 and not slab_mode) else None),
-                     "algorithmic_bytes": a_c, "peak_source": peak_src},
+                     "frac_of_nominal_8TBs": achieved / 8000.0,
+                     # dram__bytes_read+write of those kernels per compress from an ncu --set full capture of THESE kernel
+                     # sources (profiles/traffic_*.json, tools/ncu_traffic.py); null when no capture matches them
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes": a_c, "peak_source": peak_src,
+                     "decode_scope": {"what": "inverse transform incl. dequantiser (A_d = ntot * (nlay + 4))",
+                                      "achieved": ntot * (nlay + 4) / max(1e-9, sd[3] * 1e-3) / 1e9,
+                                      "frac": ntot * (nlay + 4) / max(1e-9, sd[3] * 1e-3) / 1e9 / hbm},
+                     "coder_scope": {"what": "range coder, A_rc = ntot * nlay + ntot_enc (no HBM target: serial chains)",
+                                     "encode_frac": (ntot * nlay + int(h.ntot_enc)) / max(1e-9, se[2] * 1e-3) / 1e9 / hbm,
+                                     "decode_frac": (ntot * nlay + int(h.ntot_enc)) / max(1e-9, sd[1] * 1e-3) / 1e9 / hbm}},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": world * (nbytes + int(h.ntot_enc)),
                 "d2h_bytes_per_step": world * (nbytes + int(h.ntot_enc)), "ms_per_step": e2e_step,
                 "api": "wrb_encode_host + wrb_decode_host (f32 pinned host buffers)" if world == 1 else
@@ -403,7 +461,144 @@ def run_ours(args, rank, world, local_rank):
     if cpu is not None:
         line["cpu_baseline"] = cpu
         line["ratio_check"] = ratio_check
+    if world == 1 and not args.no_configs and n == N_FIELD:
+        del field, recon, blob
+        codec.trim()
+        torch.cuda.empty_cache()
+        try:
+            line["configs"] = other_configs(torch, codec, dev, hbm)
+        except Exception as exc:                          # the headline line must not be lost to a side measurement
+            line["configs"] = {"error": repr(exc)}
     emit(line)
+
+
+def _time_field(torch, codec, api, field, n, tol, hbm, reps=3, warm=1):
+    """device-timed compress + decompress of one n^3 field already in HBM: means over `reps`, stage times, roofline
+    fraction of the forward-transform + quantise scope (A_c) and of the inverse (A_d)"""
+    code = api.F64 if field.dtype == torch.float64 else api.F32
+    esz = field.element_size()
+    ntot = n ** 3
+    _, cap = api.setup_wr(n, n, n)
+    cap = min(cap, ntot * esz + (64 << 20))
+    blob = torch.empty(cap + 64, dtype=torch.uint8, device=field.device)
+    rec = torch.empty(ntot, dtype=field.dtype, device=field.device)
+    stream = torch.cuda.current_stream()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    enc, dec, se, sd = [], [], [], []
+    h = None
+    for it in range(warm + reps):
+        ev[0].record(stream)
+        h = codec.encode_device(field.data_ptr(), code, n, n, n, tol, blob.data_ptr(), cap)
+        a = codec.stage_ms()
+        ev[1].record(stream)
+        codec.decode_device(rec.data_ptr(), code, n, n, n, h, blob.data_ptr())
+        b = codec.stage_ms()
+        ev[2].record(stream)
+        torch.cuda.synchronize()
+        if it >= warm:
+            enc.append(ev[0].elapsed_time(ev[1])); dec.append(ev[1].elapsed_time(ev[2])); se.append(a); sd.append(b)
+    amax = field.abs().max().item()
+    err = 0.0
+    step = max(1, n // 8) * n * n
+    fv = field.view(-1)
+    for a0 in range(0, ntot, step):
+        err = max(err, (rec[a0:a0 + step].double() - fv[a0:a0 + step].double()).abs().max().item())
+    nlay = int(h.nlay)
+    te, td = statistics.mean(enc), statistics.mean(dec)
+    t_wq = statistics.mean(x[0] + x[1] for x in se) * 1e-3
+    t_inv = statistics.mean(x[3] for x in sd) * 1e-3
+    a_c, a_d = ntot * (esz + 8 + 9 * nlay), ntot * (nlay + esz)
+    nch = (ntot + 59998) // 59999
+    nseek = max(0, (int(h.len_enc_vec[0]) and int.from_bytes(blob[28:32].cpu().numpy().tobytes(), "little")))
+    out = {"compress_gbs": ntot * esz / te / 1e6, "decompress_gbs": ntot * esz / td / 1e6,
+           "value_gbs": 2 * ntot * esz / (te + td) / 1e6, "compress_ms": te, "decompress_ms": td,
+           "nlay": nlay, "ntot_enc": int(h.ntot_enc), "ratio": ntot * esz / max(1, int(h.ntot_enc)),
+           "rel_linf_error": err / amax,
+           "stages_ms": {"transform": statistics.mean(x[0] for x in se), "quantise": statistics.mean(x[1] for x in se),
+                         "range_encode": statistics.mean(x[2] for x in se), "assemble": statistics.mean(x[3] for x in se),
+                         "range_decode": statistics.mean(x[1] for x in sd), "inverse_transform": statistics.mean(x[3] for x in sd)},
+           "roofline_frac": a_c / t_wq / 1e9 / hbm, "roofline_frac_inverse": a_d / t_inv / 1e9 / hbm,
+           # the container's own bytes on top of the chunk streams (layer header, chunk lengths, seek entries): what it
+           # adds to the reference's single-stream layers besides ~7 bytes of framing per chunk
+           "container_table_bytes": nlay * (32 + nch * (4 + 10 * nseek)), "seek_points": nseek}
+    del blob, rec
+    return out
+
+
+def other_configs(torch, codec, dev, hbm):
+    """BASELINE.json configs other than the headline's, measured after it (device-timed like `value`; C1 also through
+    the executables beside the reference's).  The reference's single-threaded CPU code is timed only where it takes
+    seconds (C1); C2's is the headline's cpu_baseline."""
+    import shutil
+    from waverange_b200 import api
+    out = {}
+    # ---- C1: 256^3 float32, tol 1e-5: device, and wrenc/wrdec wall clock against the reference's executables -------
+    n, tol = 256, 1e-5
+    f = synth_field(torch, n, 1234, dev, torch.float32)
+    c1 = _time_field(torch, codec, api, f, n, tol, hbm)
+    c1["workload"] = "256^3 float32, tol 1e-5, C layout (configs[0])"
+    bin_dir = os.path.join(ROOT, "waverange_b200", "bin")
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    tmp = tempfile.mkdtemp(prefix="wrb_c1_")
+    try:
+        f.cpu().numpy().tofile(os.path.join(tmp, "data.bin"))
+        enc_args = ["data.bin", "data.wrb", "data.wrh", "2", "0", "1", "1", str(n), str(n), str(n), str(tol)]
+        dec_args = ["data.wrb", "data.wrh", "datarec.bin", "2", "0"]
+
+        def cli(enc, dec, sub):
+            d = os.path.join(tmp, sub)
+            os.makedirs(d)
+            os.symlink(os.path.join(tmp, "data.bin"), os.path.join(d, "data.bin"))
+            t0 = time.perf_counter()
+            subprocess.run([enc] + enc_args, cwd=d, check=True, stdout=subprocess.DEVNULL)
+            t1 = time.perf_counter()
+            subprocess.run([dec] + dec_args, cwd=d, check=True, stdout=subprocess.DEVNULL)
+            t2 = time.perf_counter()
+            return t1 - t0, t2 - t1, os.path.getsize(os.path.join(d, "data.wrb")), os.path.join(d, "datarec.bin")
+        if os.path.exists(os.path.join(bin_dir, "wrenc")):
+            cli(os.path.join(bin_dir, "wrenc"), os.path.join(bin_dir, "wrdec"), "warm")        # page cache, driver start-up
+            te, td, size, rec_ours = cli(os.path.join(bin_dir, "wrenc"), os.path.join(bin_dir, "wrdec"), "ours")
+            c1["cli"] = {"wrenc_s": te, "wrdec_s": td, "wrb_bytes": size,
+                         "note": "process start + CUDA context creation + file I/O + codec, wall clock"}
+            if os.path.exists(os.path.join(ref_dir, "wrenc_ref")):
+                re_, rd, rsize, rec_ref = cli(os.path.join(ref_dir, "wrenc_ref"), os.path.join(ref_dir, "wrdec_ref"), "ref")
+                c1["cli_reference"] = {"wrenc_s": re_, "wrdec_s": rd, "wrb_bytes": rsize, "cores": 1,
+                                       "note": "the reference's own executables (oracle/_ref, unmodified sources), same file"}
+                c1["cli"]["size_vs_reference"] = size / rsize - 1.0
+                c1["cli"]["reconstruction_equal_to_reference"] = open(rec_ours, "rb").read() == open(rec_ref, "rb").read()
+                c1["cli"]["speedup_wall"] = (re_ + rd) / (te + td)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    out["C1"] = c1
+    del f
+    # ---- C5: 512^3 float64 at both ends and the middle of the tolerance sweep ----------------------------------------
+    n = 512
+    f = synth_field(torch, n, 5, dev, torch.float64)
+    c5 = {"workload": "512^3 float64, tolerance sweep (configs[4]); 1e-16 is the 8-layer coder stress case", "points": {}}
+    for tol in (1e-3, 1e-8, 1e-16):
+        c5["points"]["%g" % tol] = _time_field(torch, codec, api, f, n, tol, hbm, reps=2)
+    out["C5"] = c5
+    del f
+    codec.trim()
+    torch.cuda.empty_cache()
+    # ---- C3: four 1024^3 float64 fields (ux, uy, uz, p), tol 1e-8, one after another through one handle ------------
+    n, tol = 1024, 1e-8
+    per = []
+    for k in range(4):
+        f = synth_field(torch, n, 100 + k, dev, torch.float64, expo=(-7.0 / 6.0 if k == 3 else -5.0 / 6.0))
+        per.append(_time_field(torch, codec, api, f, n, tol, hbm, reps=2 if k == 0 else 1, warm=1 if k == 0 else 0))
+        del f
+    tot_ms = sum(p["compress_ms"] + p["decompress_ms"] for p in per)
+    out["C3"] = {"workload": "4 x 1024^3 float64 (ux, uy, uz, p), tol 1e-8 (configs[2]), fields back to back",
+                 "one_field": per[0], "four_fields_value_gbs": 2 * 4 * n ** 3 * 8 / tot_ms / 1e6,
+                 "four_fields_ms": tot_ms, "nlay": [p["nlay"] for p in per], "ratio": [p["ratio"] for p in per],
+                 "note": "independent fields: with one GPU per field (4 GPUs) they run concurrently with no data-path "
+                         "collective; tools/multi_field.py overlaps them on one GPU with one stream per field"}
+    out["C4"] = {"workload": "2048^3 float32 in z-slabs over 2/4/8 GPUs (configs[3])",
+                 "note": "needs several GPUs: `bench.py --gpus N` (weak-scaling stand-in, driver's SCALE run) and "
+                         "tools/run_c4.py; results archived under profiles/"}
+    codec.trim()
+    return out
 
 
 _REAL_STDOUT = None
@@ -429,6 +624,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--size", type=int, default=N_FIELD, help="field edge (default 512 = BASELINE configs[1]; other sizes are for profiling only)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (profiling only)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (C1, C3, C5 beside the headline)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -85,6 +85,13 @@ int wrb_set_local_cutoff(wrb_codec* c, int mx, int my, int mz, const double* cut
 unsigned long long wrb_launch_count(const wrb_codec* c);
 /* Release cached device scratch (it is otherwise kept and grown on demand). */
 int wrb_trim(wrb_codec* c);
+/* The calling thread's current CUDA device (cudaGetDevice); the drop-in entry points of waverange.h create their
+ * per-thread handle on it. */
+int wrb_current_device(int* device);
+/* The encoder launches only as many layer passes as the tolerance can need and repeats the call with all 8 when that
+ * bound did not hold (the stream is the same either way, the call takes twice as long): how often that happened on
+ * this handle since creation.  Expected: 0. */
+unsigned long long wrb_layer_guess_misses(const wrb_codec* c);
 
 /* ---- sizes: replaces setup_wr() (reference wrappers.cpp:531-541) ------------------------------ */
 void wrb_setup(int nx, int ny, int nz, unsigned char* nlaymax, unsigned long* ntot_enc_max);

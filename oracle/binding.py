@@ -78,6 +78,13 @@ class Restatement:
         L.wro_fnv1a.restype = C.c_uint64
         L.wro_fnv1a.argtypes = [u8p, C.c_size_t]
         L.wro_ind_p2w.argtypes = [C.c_int] * 7 + [C.POINTER(C.c_int)] * 4
+        u64p = C.POINTER(C.c_uint64)
+        L.wro_wavelet3d_mt.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, f64p]
+        L.wro_encode_digest.restype = C.c_int
+        L.wro_encode_digest.argtypes = [C.c_int, C.c_int, C.c_int, f64p, C.c_int, C.c_double, C.c_uint64,
+                                        C.POINTER(Header), u32p, u64p, u64p, C.c_longlong, u8p]
+        L.wro_fnv1a_many.argtypes = [u8p, u64p, u64p, C.c_size_t, u64p]
+        L.wro_decode_symbols_mt.argtypes = [C.c_int, C.c_int, C.c_int, f64p, C.POINTER(Header), u8p]
 
     # -- wavelet ---------------------------------------------------------
     def wavelet3d(self, a, lvl):
@@ -131,6 +138,50 @@ class Restatement:
                     symbols=sym[:nlay * ntot].reshape(nlay, ntot).copy() if want_symbols else None,
                     chunk_lens=cl[:nlay * nch].reshape(nlay, nch).copy() if nlay else cl[:0],
                     residual=a)
+
+    def encode_digest(self, fld, tol, chunk_len, wtflag=1, sample_chunk=-1, inplace=False):
+        """The encode of a LARGE field, multi-threaded, keeping only a digest (oracle/wr_oracle.c wro_encode_digest):
+        dict(header, chunk_lens[nlay, nch], stream_hash[nlay, nch], symbol_hash[nlay, nch], sample[nlay, chunk_len]).
+        inplace: fld (float64, C-contiguous) is clobbered instead of copied."""
+        a = fld if inplace else np.ascontiguousarray(fld, dtype=np.float64).copy()
+        assert a.dtype == np.float64 and a.flags.c_contiguous
+        nz, ny, nx = a.shape
+        nch = (a.size + chunk_len - 1) // chunk_len
+        cl = np.zeros(NLAYMAX * nch, dtype=np.uint32)
+        sh = np.zeros(NLAYMAX * nch, dtype=np.uint64)
+        qh = np.zeros(NLAYMAX * nch, dtype=np.uint64)
+        sample = np.zeros(NLAYMAX * chunk_len, dtype=np.uint8) if sample_chunk >= 0 else None
+        hdr = Header()
+        u64p = C.POINTER(C.c_uint64)
+        rc = self.lib.wro_encode_digest(nx, ny, nz, _p(a, f64p), wtflag, tol, chunk_len, C.byref(hdr), _p(cl, u32p),
+                                        _p(sh, u64p), _p(qh, u64p), sample_chunk,
+                                        _p(sample, u8p) if sample is not None else None)
+        if rc != 0:
+            raise RuntimeError("oracle digest encode failed (%d)" % rc)
+        n = hdr.nlay
+        return dict(header=hdr, chunk_lens=cl[:n * nch].reshape(n, nch), stream_hash=sh[:n * nch].reshape(n, nch),
+                    symbol_hash=qh[:n * nch].reshape(n, nch),
+                    sample=sample[:n * chunk_len].reshape(n, chunk_len) if sample is not None else None)
+
+    def fnv1a_many(self, data, offs, lens):
+        """FNV-1a of every byte range data[offs[i] : offs[i] + lens[i]] (multi-threaded)"""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.uint64)
+        assert offs.size == lens.size and (offs.size == 0 or int((offs + lens).max()) <= data.size)
+        out = np.zeros(offs.size, dtype=np.uint64)
+        u64p = C.POINTER(C.c_uint64)
+        self.lib.wro_fnv1a_many(_p(data, u8p), _p(offs, u64p), _p(lens, u64p), offs.size, _p(out, u64p))
+        return out
+
+    def decode_symbols(self, shape, hdr, sym):
+        """accumulate + inverse transform of given symbol planes (nlay, ntot), multi-threaded"""
+        nz, ny, nx = shape
+        sym = np.ascontiguousarray(sym, dtype=np.uint8)
+        assert sym.size == hdr.nlay * nx * ny * nz
+        out = np.empty(shape, dtype=np.float64)
+        self.lib.wro_decode_symbols_mt(nx, ny, nz, _p(out, f64p), C.byref(hdr), _p(sym, u8p))
+        return out
 
     def decode(self, shape, hdr, data, chunk_len=0, chunk_lens=None):
         nz, ny, nx = shape

@@ -1,9 +1,13 @@
 """The five configurations of BASELINE.json at their FULL sizes on the GPU.
 
-Where the oracle finishes in seconds (C1 256^3, C2 512^3) every chunk stream, the header doubles and the
-reconstruction are compared bit for bit.  At 1024^3 (C3) and for the 14-point tolerance sweep (C5) the checks are
-the size-independent ones: round trip within the requested relative L-infinity tolerance, determinism, layer and
-size monotonicity, and sampled chunk streams against the oracle's range_encode of the very same symbols.
+C1 256^3 and C2 512^3: every chunk stream byte for byte, the header doubles and the reconstruction against the
+oracle's single-threaded encode.  C3 (one 1024^3 float64 field, tol 1e-8), C5 (512^3 float64 at 1e-3 / 1e-8 / 1e-16:
+3 / 5 / 8 layers) and a field of more than 2^31 points (64-bit index paths) against the oracle's multi-threaded
+DIGEST encode (oracle/wr_oracle.c wro_encode_digest: the same steps, lines / elements / chunks shared out over the
+host cores, keeping per chunk the stream length, the stream hash and the symbol hash): header doubles bit-equal, every
+chunk length equal, the FNV-1a hash of EVERY chunk stream and of every chunk's symbols equal, reconstruction bit-equal
+to the oracle's inverse of the same symbols (C3, C5).  The whole 14-point tolerance sweep of C5 additionally runs through
+the size-independent checks (tolerance met, layer and size monotonicity) and bit for bit at 64^3.
 C4 (2048^3, z-slabs over 2/4/8 GPUs) needs several GPUs: tools/run_c4.py under `gpurun --gpus N`; its
 partition logic is covered at reduced size in tests/test_slab_gpu.py and tests/test_slab_cpu.py.
 """
@@ -105,39 +109,141 @@ def test_c2_512_f32_tol1e4_bit_exact(codec, torch_cuda, oracle):
     assert h2.ntot_enc == h.ntot_enc and torch.equal(blob2[:h.ntot_enc], blob[:h.ntot_enc])
 
 
-def test_c3_1024_f64_tol1e8_properties(codec, torch_cuda, oracle):
-    """configs[2]: one 1024^3 float64 field of the FluSI-style backup (the four fields are independent)"""
+def container_tables(torch, blob, h, ntot):
+    """per layer: (chunk byte lengths, byte offset of every chunk stream inside the blob) from the WRCK tables"""
+    nch = (ntot + L1 - 1) // L1
+    out, off = [], 0
+    for l in range(h.nlay):
+        hdr = blob[off:off + 32].cpu().numpy().tobytes()
+        assert hdr[:4] == b"WRCK" and int.from_bytes(hdr[8:16], "little") == L1 and int.from_bytes(hdr[24:28], "little") == nch
+        nseek = int.from_bytes(hdr[28:32], "little")
+        lens = np.frombuffer(blob[off + 32:off + 32 + 4 * nch].cpu().numpy().tobytes(), dtype="<u4").astype(np.uint64)
+        starts = np.uint64(off + 32 + 4 * nch + 10 * nseek * nch) + np.concatenate([[0], np.cumsum(lens[:-1], dtype=np.uint64)]).astype(np.uint64)
+        assert int(starts[-1] + lens[-1]) == off + h.len_enc_vec[l]
+        out.append((lens, starts))
+        off += h.len_enc_vec[l]
+    assert off == h.ntot_enc
+    return out
+
+
+def compare_with_digest(torch, oracle, field, shape, tol, h, blob, codec=None, check_symbols=True, check_recon=True):
+    """Full-size parity against the oracle's digest encode of the same field: header doubles, every chunk length, the hash
+    of every chunk stream; optionally the hash of every chunk's symbols (quantiser output pulled from the device) and
+    the reconstruction against the oracle's inverse of those symbols.  Returns the GPU reconstruction error."""
+    nz, ny, nx = shape
+    ntot = nx * ny * nz
+    host = field.cpu().numpy().reshape(shape)
+    host = host.astype(np.float64) if host.dtype != np.float64 else host        # f32 widened exactly (gen_aux.cpp:305-309)
+    want = oracle.encode_digest(host, tol, L1, inplace=True)
+    del host
+    hw = want["header"]
+    assert (h.nlay, h.wlev) == (hw.nlay, hw.wlev), (h.nlay, hw.nlay)
+    assert bits_equal(np.array([h.tolabs, h.midval, h.halfspanval]), np.array([hw.tolabs, hw.midval, hw.halfspan]))
+    assert bits_equal(np.array(list(h.deps_vec)[:h.nlay]), np.array(list(hw.deps)[:h.nlay]))
+    assert bits_equal(np.array(list(h.minval_vec)[:h.nlay]), np.array(list(hw.minval)[:h.nlay]))
+    tables = container_tables(torch, blob, h, ntot)
+    data = blob[:h.ntot_enc].cpu().numpy()
+    nstreams = 0
+    for l, (lens, starts) in enumerate(tables):
+        assert np.array_equal(lens, want["chunk_lens"][l].astype(np.uint64)), "chunk lengths of layer %d differ" % l
+        got = oracle.fnv1a_many(data, starts, lens)
+        bad = np.nonzero(got != want["stream_hash"][l])[0]
+        assert bad.size == 0, "layer %d: %d chunk streams differ, first chunk %d" % (l, bad.size, bad[0])
+        nstreams += lens.size
+    del data
+    assert nstreams == h.nlay * ((ntot + L1 - 1) // L1)
+    if not (check_symbols or check_recon):
+        return None
+    # symbols the quantiser produced (stage entry point): hash per chunk, then the oracle's inverse of exactly these
+    dt = F32 if field.dtype == torch.float32 else F64
+    sym = torch.empty(h.nlay * ntot, dtype=torch.uint8, device="cuda")
+    hq = codec.quantise_device(field.data_ptr(), dt, nx, ny, nz, tol, d_sym=sym.data_ptr())
+    assert hq.nlay == h.nlay
+    codec.trim()
+    hsym = sym.cpu().numpy()
+    del sym
+    nch = (ntot + L1 - 1) // L1
+    coff = np.arange(nch, dtype=np.uint64) * np.uint64(L1)
+    clen = np.minimum(np.uint64(L1), np.uint64(ntot) - coff)
+    for l in range(h.nlay):
+        got = oracle.fnv1a_many(hsym, np.uint64(l * ntot) + coff, clen)
+        bad = np.nonzero(got != want["symbol_hash"][l])[0]
+        assert bad.size == 0, "layer %d: symbols of %d chunks differ, first chunk %d" % (l, bad.size, bad[0])
+    if not check_recon:
+        return None
+    want_rec = oracle.decode_symbols(shape, hw, hsym)
+    del hsym
+    rec = torch.empty(ntot, dtype=torch.float64, device="cuda")
+    codec.decode_device(rec.data_ptr(), F64, nx, ny, nz, h, blob.data_ptr())
+    err = rel_err(torch, rec, field.view(-1))
+    step = max(1, nz // 8)
+    for z0 in range(0, nz, step):                        # slab by slab: never two whole copies on the host
+        z1 = min(nz, z0 + step)
+        got = rec[z0 * nx * ny:z1 * nx * ny].cpu().numpy().reshape(z1 - z0, ny, nx)
+        assert bits_equal(got, want_rec[z0:z1]), "reconstruction differs from the oracle in planes %d..%d" % (z0, z1)
+    return err
+
+
+def test_c3_1024_f64_tol1e8_bit_exact(codec, torch_cuda, oracle):
+    """configs[2]: one 1024^3 float64 field of the FluSI-style backup (the four fields are independent), tol 1e-8:
+    header doubles, every chunk length, stream hash and symbol hash, and the reconstruction, against the oracle"""
     torch = torch_cuda
     n, tol = 1024, 1e-8
     field = bench_field(torch, n, torch.float64, seed=77)
     h, blob = encode(codec, torch, field, n, tol)
     assert 3 <= h.nlay <= 8 and h.wlev == 4
     assert sum(h.len_enc_vec[:h.nlay]) == h.ntot_enc
-    rec = torch.empty(n ** 3, dtype=torch.float64, device="cuda")
-    codec.decode_device(rec.data_ptr(), F64, n, n, n, h, blob.data_ptr())
-    assert rel_err(torch, rec, field) <= SLACK * tol
-    del rec
-    # sampled chunks: the stream stored for chunk c of layer l is the oracle's range_encode of the symbols the
-    # quantiser produced for that chunk
+    codec.trim()
+    err = compare_with_digest(torch, oracle, field, (n, n, n), tol, h, blob, codec)
+    assert err <= SLACK * tol
+
+
+@pytest.mark.parametrize("tol", [1e-3, 1e-8, 1e-16])
+def test_c5_512_f64_bit_exact(codec, torch_cuda, oracle, tol):
+    """configs[4] at its stated size, both ends and the middle of the sweep (3 / 5 / 8 layers; the deep layers are nearly
+    incompressible: the coder stress case): everything against the oracle's digest"""
+    torch = torch_cuda
+    n = 512
+    field = bench_field(torch, n, torch.float64, seed=5)
+    h, blob = encode(codec, torch, field, n, tol)
+    codec.trim()
+    err = compare_with_digest(torch, oracle, field, (n, n, n), tol, h, blob, codec)
+    assert err <= max(SLACK * tol, 1e-14)
+    print("tol %g: nlay %d ratio %.3f err %.2e" % (tol, h.nlay, 8 * n ** 3 / h.ntot_enc, err))
+
+
+def test_more_than_2_31_points_bit_exact(codec, torch_cuda, oracle):
+    """1280 x 1024 x 1648 = 2.16e9 > 2^31 points (float32, tol 1e-3): the 64-bit index paths of every kernel.  Header
+    doubles, every chunk length and every chunk-stream hash against the oracle's digest (equal streams imply equal
+    symbols: the reference's decoder inverts them); round trip within tolerance on the device."""
+    torch = torch_cuda
+    import bench
+    nx, ny, nz, tol = 1280, 1024, 1648, 1e-3
+    ntot = nx * ny * nz
+    assert ntot > 2 ** 31
+    # the benchmark's generator makes n x n x nzl slabs: build the field from x-halves of a 1280-wide period
+    field = torch.empty((nz, ny, nx), dtype=torch.float32, device="cuda")
+    for z0 in range(0, nz, 206):
+        z1 = min(nz, z0 + 206)
+        part = bench.synth_field(torch, 1280, 4242, torch.device("cuda", 0), torch.float32, nz_total=nz, z0=z0, nzl=z1 - z0)
+        field[z0:z1] = part[:, :ny, :]
+        del part
     from waverange_b200 import api
-    sym = torch.empty(8 * n ** 3, dtype=torch.uint8, device="cuda")
-    hq = codec.quantise_device(field.data_ptr(), F64, n, n, n, tol, d_sym=sym.data_ptr())
-    assert hq.nlay == h.nlay and list(hq.deps_vec)[:h.nlay] == list(h.deps_vec)[:h.nlay]
-    nch = (n ** 3 + L1 - 1) // L1
-    off = 0
-    for l in range(h.nlay):
-        hdr = blob[off:off + 32].cpu().numpy().tobytes()
-        assert hdr[:4] == b"WRCK"
-        nseek = int.from_bytes(hdr[28:32], "little")
-        lens = np.frombuffer(blob[off + 32:off + 32 + 4 * nch].cpu().numpy().tobytes(), dtype="<u4")
-        starts = off + 32 + 4 * nch + 10 * nseek * nch + np.concatenate([[0], np.cumsum(lens[:-1], dtype=np.int64)])
-        for c in (0, 1, nch // 3, nch - 2, nch - 1):
-            s0 = c * L1
-            s1 = min(n ** 3, s0 + L1)
-            symbols = sym[l * n ** 3 + s0:l * n ** 3 + s1].cpu().numpy()
-            got = blob[int(starts[c]):int(starts[c]) + int(lens[c])].cpu().numpy().tobytes()
-            assert got == oracle.range_encode(symbols).tobytes(), "layer %d chunk %d" % (l, c)
-        off += h.len_enc_vec[l]
+    _, cap = api.setup_wr(nx, ny, nz)
+    cap = min(cap, ntot * 2)
+    blob = torch.zeros(cap + 64, dtype=torch.uint8, device="cuda")
+    h = codec.encode_device(field.data_ptr(), F32, nx, ny, nz, tol, blob.data_ptr(), cap)
+    assert h.wlev == 4 and 1 <= h.nlay <= 4
+    compare_with_digest(torch, oracle, field, (nz, ny, nx), tol, h, blob, check_symbols=False, check_recon=False)
+    rec = torch.empty(ntot, dtype=torch.float32, device="cuda")
+    codec.decode_device(rec.data_ptr(), F32, nx, ny, nz, h, blob.data_ptr())
+    amax = field.abs().max().item()
+    err = 0.0
+    for z0 in range(0, nz, 103):
+        a, b = z0 * nx * ny, min(nz, z0 + 103) * nx * ny
+        err = max(err, (rec[a:b].double() - field.view(-1)[a:b].double()).abs().max().item())
+    assert err / amax <= SLACK * tol
+    codec.trim()
 
 
 TOLS = [10.0 ** (-k) for k in range(3, 17)]

@@ -331,6 +331,92 @@ def test_corrupt_container_is_rejected(codec, torch_cuda, oracle):
         codec.decode_device(rec.data_ptr(), F64, 32, 32, 32, h, out.data_ptr())
 
 
+def _put(out, off, value, nbytes):
+    import torch
+    out[off:off + nbytes] = torch.tensor(list(int(value).to_bytes(nbytes, "little")), dtype=torch.uint8, device=out.device)
+
+
+@pytest.mark.parametrize("case", ["second_layer_magic", "nchunks_huge", "chunk_len_tiny", "len_table_garbage", "seek_pos_far",
+                                  "truncated_layers", "stream_garbage", "len_sum_shifted"])
+def test_malformed_containers_fail_cleanly(codec, torch_cuda, oracle, case):
+    """A corrupt or truncated container must come back as an error (WRB_E_FORMAT) -- never as an out-of-bounds read: the
+    blob sits at the very end of its allocation (no slack beyond the 64 bytes the interface asks for), and the handle
+    must still work afterwards (a fault would leave a sticky context error)."""
+    from waverange_b200 import api
+    torch = torch_cuda
+    f = oracle.probe_field((80, 96, 112), seed=2, nm=14)          # 860160 points: 15 chunks, seek points granted
+    nz, ny, nx = f.shape
+    h, out = encode_dev(codec, torch, f, 1e-5)
+    assert h.nlay >= 2
+    good = out[:h.ntot_enc + 64].clone()
+    blob = good.clone()
+    l1 = h.len_enc_vec[0]                                          # offset of the second layer
+    nch = (f.size + L1 - 1) // L1
+    nseek = int.from_bytes(blob[28:32].cpu().numpy().tobytes(), "little")
+    h2 = api.Header.from_buffer_copy(bytes(h))
+    if case == "second_layer_magic":
+        blob[l1] = 0x55
+    elif case == "nchunks_huge":
+        _put(blob, 24, 0x7FFFFFF0, 4)
+    elif case == "chunk_len_tiny":
+        _put(blob, 8, 3, 8); _put(blob, 24, (f.size + 2) // 3, 4)
+    elif case == "len_table_garbage":
+        _put(blob, 32 + 4 * 3, 0xFFFFFFF0, 4)
+    elif case == "seek_pos_far":
+        assert nseek > 0
+        for k in range(nseek):
+            _put(blob, 32 + 4 * nch + 10 * (nseek * 2 + k) + 8, 0xFFFF, 2)
+    elif case == "truncated_layers":
+        h2.len_enc_vec[h.nlay - 1] = 40; h2.ntot_enc = sum(h2.len_enc_vec[:h.nlay])
+        blob = blob[:h2.ntot_enc + 64].clone()
+    elif case == "stream_garbage":
+        a = 32 + 4 * nch + 10 * nseek * nch + 700
+        blob[a:a + 4000] = torch.randint(0, 256, (4000,), dtype=torch.uint8, device="cuda")
+    elif case == "len_sum_shifted":
+        v = int.from_bytes(blob[32:36].cpu().numpy().tobytes(), "little")
+        _put(blob, 32, v + 5, 4); w = int.from_bytes(blob[36:40].cpu().numpy().tobytes(), "little"); _put(blob, 36, w - 5, 4)
+    rec = torch.zeros(f.size, dtype=torch.float64, device="cuda")
+    if case in ("stream_garbage", "len_sum_shifted"):
+        # random bytes inside a stream / a shifted stream start may still decode to *something*: what matters is that nothing faults
+        try:
+            codec.decode_device(rec.data_ptr(), F64, nx, ny, nz, h2, blob.data_ptr())
+        except api.WaveRangeError:
+            pass
+    else:
+        with pytest.raises(api.WaveRangeError):
+            codec.decode_device(rec.data_ptr(), F64, nx, ny, nz, h2, blob.data_ptr())
+    torch.cuda.synchronize()                                       # no sticky error
+    codec.decode_device(rec.data_ptr(), F64, nx, ny, nz, h, good.data_ptr())
+    whole = oracle.encode(f, 1e-5)
+    assert bits_equal(rec.cpu().numpy().reshape(f.shape), oracle.decode(f.shape, whole["header"], whole["data"]))
+
+
+def test_codec_handles_on_one_device_from_threads(torch_cuda, oracle):
+    """several handles driven from several host threads: the one-time kernel attribute setup is per device and guarded"""
+    import threading
+    from waverange_b200 import api
+    f = oracle.probe_field((40, 48, 56), seed=4, nm=10)
+    want = oracle.encode(f, 1e-6, chunk_len=L1)
+    errs = []
+
+    def work():
+        try:
+            c = api.Codec(device=0)
+            h, out = encode_dev(c, torch_cuda, f, 1e-6)
+            assert h.ntot_enc > 0 and h.nlay == want["header"].nlay
+            rec = torch_cuda.zeros(f.size, dtype=torch_cuda.float64, device="cuda")
+            c.decode_device(rec.data_ptr(), F64, 56, 48, 40, h, out.data_ptr())
+            c.close()
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+    ts = [threading.Thread(target=work) for _ in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+
+
 def test_layer_count_guess_falls_back_to_all_layers(codec, torch_cuda, oracle, monkeypatch):
     """the encoder launches only as many layers as the tolerance can need (codec.cu layer_guess); when the guess is
     too small the `done` flag of the device state is clear and the call repeats with all eight: same bytes"""
@@ -338,8 +424,10 @@ def test_layer_count_guess_falls_back_to_all_layers(codec, torch_cuda, oracle, m
     tol = 1e-9
     h0, out0 = encode_dev(codec, torch_cuda, f, tol)
     assert h0.nlay >= 4
+    assert codec.layer_guess_misses() == 0
     monkeypatch.setenv("WRB_LAYER_GUESS", "2")
     h1, out1 = encode_dev(codec, torch_cuda, f, tol)
+    assert codec.layer_guess_misses() == 1
     assert h1.nlay == h0.nlay and h1.ntot_enc == h0.ntot_enc
     assert torch_cuda.equal(out0[:h0.ntot_enc], out1[:h1.ntot_enc])
 

@@ -141,3 +141,52 @@ def test_local_cutoff_restatement_vs_reference(oracle, ref, wt, grid):
         assert u["data"].tobytes() == a["data"].tobytes()
     else:
         assert a["header"].ntot_enc < u["header"].ntot_enc
+
+
+DIGEST_CASES = [((40, 33, 50), 1e-6, 1, 59999), ((24, 20, 28), 1e-9, 1, 999), ((1, 7, 300), 1e-3, 1, 59999),
+                ((30, 30, 30), 1e-4, 0, 4999), ((65, 64, 63), 1e-12, 1, 59999)]
+
+
+@pytest.mark.parametrize("shape,tol,wt,cl", DIGEST_CASES)
+def test_digest_encode_equals_plain_encode(oracle, shape, tol, wt, cl):
+    """The multi-threaded digest encode used by the full-size GPU parity tests (wro_encode_digest: same steps, work
+    shared out over threads, only hashes kept) against the plain single-threaded restatement -- which the tests above
+    pin to the reference: header bytes, chunk lengths, every stream hash and every chunk's symbol hash."""
+    f = oracle.probe_field(shape, seed=11, nm=10)
+    w = oracle.encode(f, tol, wtflag=wt, chunk_len=cl, want_symbols=True)
+    d = oracle.encode_digest(f, tol, cl, wtflag=wt, sample_chunk=1)
+    hw, hd = w["header"], d["header"]
+    assert bytes(hw) == bytes(hd)
+    assert np.array_equal(w["chunk_lens"], d["chunk_lens"])
+    ntot = f.size
+    off = 0
+    for l in range(hw.nlay):
+        for c, n in enumerate(w["chunk_lens"][l]):
+            n = int(n)
+            assert oracle.fnv1a(w["data"][off:off + n]) == int(d["stream_hash"][l, c])
+            s0, s1 = c * cl, min(ntot, (c + 1) * cl)
+            assert oracle.fnv1a(w["symbols"][l][s0:s1]) == int(d["symbol_hash"][l, c])
+            off += n
+        if ntot > cl:
+            s1 = min(ntot, 2 * cl)
+            assert np.array_equal(d["sample"][l][:s1 - cl], w["symbols"][l][cl:s1])
+    # hashes of byte ranges pulled from a container, and the inverse from symbols
+    offs = np.concatenate([[0], np.cumsum(w["chunk_lens"].ravel().astype(np.uint64))[:-1]]).astype(np.uint64)
+    assert np.array_equal(oracle.fnv1a_many(w["data"], offs, w["chunk_lens"].ravel().astype(np.uint64)), d["stream_hash"].ravel())
+    whole = oracle.encode(f, tol, wtflag=wt)
+    assert bits_equal(oracle.decode_symbols(shape, hw, w["symbols"]), oracle.decode(shape, whole["header"], whole["data"]))
+
+
+def test_threaded_transform_equals_plain(oracle, ref):
+    """wro_wavelet3d_mt (lines shared out over threads) against the compiled reference, odd sizes included"""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    for shape in [(33, 18, 47), (16, 16, 16), (1, 9, 64)]:
+        x = rng.standard_normal(shape)
+        for lvl in (1, 4):
+            a = x.copy()
+            nz, ny, nx = shape
+            oracle.lib.wro_wavelet3d_mt(nx, ny, nz, lvl, a.ctypes.data_as(C.POINTER(C.c_double)))
+            assert bits_equal(a, ref.wavelet3d(x, lvl))
+            oracle.lib.wro_wavelet3d_mt(nx, ny, nz, -lvl, a.ctypes.data_as(C.POINTER(C.c_double)))
+            assert bits_equal(a, ref.wavelet3d(ref.wavelet3d(x, lvl), -lvl))

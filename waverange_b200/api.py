@@ -72,7 +72,7 @@ _lib = None
 
 # every symbol include/waverange_b200.h and include/waverange.h declare
 EXPORTS = ["wrb_create", "wrb_destroy", "wrb_last_error", "wrb_set_stream", "wrb_set_chunk_blocks", "wrb_set_seek_points",
-           "wrb_set_local_cutoff", "wrb_launch_count", "wrb_trim", "wrb_setup", "wrb_encode_device", "wrb_decode_device",
+           "wrb_set_local_cutoff", "wrb_launch_count", "wrb_trim", "wrb_current_device", "wrb_layer_guess_misses", "wrb_setup", "wrb_encode_device", "wrb_decode_device",
            "wrb_encode_host", "wrb_decode_host", "wrb_decode_symbols_device", "wrb_decode_slab_symbols_device", "wrb_set_slab", "wrb_encode_slab_device", "wrb_decode_slab_device", "wrb_quantise_slab_device", "wrb_wavelet3d_device", "wrb_quantise_device",
            "wrb_range_encode_device", "wrb_range_decode_device", "wrb_ind_p2w_3d", "wrb_set_timing",
            "wrb_last_stage_ms",
@@ -104,6 +104,9 @@ def lib():
     L.wrb_launch_count.argtypes = [vp]
     L.wrb_launch_count.restype = C.c_ulonglong
     L.wrb_trim.argtypes = [vp]
+    L.wrb_current_device.argtypes = [C.POINTER(i)]
+    L.wrb_layer_guess_misses.argtypes = [vp]
+    L.wrb_layer_guess_misses.restype = C.c_ulonglong
     L.wrb_setup.argtypes = [i, i, i, C.POINTER(C.c_ubyte), C.POINTER(ul)]
     L.wrb_setup.restype = None
     L.wrb_encode_device.argtypes = [vp, vp, i, i, i, i, i, d, H, vp, ul]
@@ -385,6 +388,9 @@ class Codec:
 
     def trim(self):
         self._ck(self.L.wrb_trim(self.h))
+
+    def layer_guess_misses(self):
+        return int(self.L.wrb_layer_guess_misses(self.h))
 
     # ---- device path -----------------------------------------------------------------------
     def encode_device(self, d_field, dtype, nx, ny, nz, tol, d_out, cap, wtflag=1):

@@ -64,6 +64,7 @@ struct wrb_codec {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t piece_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     HostSource* src_pipe = nullptr;   // set by wrb_encode_host for the duration of one call: the field arrives in z-pieces
+    unsigned long long guess_misses = 0;      // encodes that had to be repeated with all 8 layers (layer_guess)
 };
 
 #define CK(call)                                                                                   \
@@ -208,8 +209,9 @@ int wrb_trim(wrb_codec* c)
     if (!c) return WRB_E_ARG;
     cudaSetDevice(c->device);
     DevBuf* all[] = {&c->coef, &c->tmp, &c->lllA, &c->lllB, &c->sym, &c->hist, &c->slots, &c->lens,
-                     &c->dstoff, &c->seek, &c->blob, &c->field, &c->offs, &c->layoff, &c->misc, &c->ext};
+                     &c->dstoff, &c->seek, &c->blob, &c->field, &c->offs, &c->layoff, &c->misc, &c->ext, &c->lcut};
     for (DevBuf* b : all) b->release();
+    c->lc_mx = c->lc_my = c->lc_mz = 0;                  // the local-cutoff grid went with lcut: off until set again
     return 0;
 }
 
@@ -249,6 +251,12 @@ int wrb_set_local_cutoff(wrb_codec* c, int mx, int my, int mz, const double* cut
 }
 int wrb_set_seek_points(wrb_codec* c, int n) { if (!c || n < -1 || n > 15) return WRB_E_ARG; c->seek_points = n; return 0; }
 unsigned long long wrb_launch_count(const wrb_codec*) { return g_launches.load(); }
+unsigned long long wrb_layer_guess_misses(const wrb_codec* c) { return c ? c->guess_misses : 0ull; }
+int wrb_current_device(int* device)
+{
+    if (!device) return WRB_E_ARG;
+    return cudaGetDevice(device) == cudaSuccess ? 0 : WRB_E_CUDA;
+}
 int wrb_set_timing(wrb_codec* c, int on) { if (!c) return WRB_E_ARG; c->timing = on; return 0; }
 int wrb_last_stage_ms(const wrb_codec* c, float ms[4])
 {
@@ -378,10 +386,10 @@ static int ensure_transform_buffers(wrb_codec* c, int nx, int ny, int nz, bool s
     return 0;
 }
 
-static int ensure_coder_buffers(wrb_codec* c, const ChunkGeom& g, int nlayers, bool need_slots)
+static int ensure_coder_buffers(wrb_codec* c, const ChunkGeom& g, int nlayers, bool need_slots, bool need_hist = true)
 {
     CK(c->sym.ensure((size_t)nlayers * g.nchunks * g.pitch + 64));
-    CK(c->hist.ensure((size_t)nlayers * g.nblocks * 256 * 4));
+    if (need_hist) CK(c->hist.ensure((size_t)nlayers * g.nblocks * 256 * 4));
     if (need_slots) {
         CK(c->slots.ensure((size_t)nlayers * g.nchunks * chunk_slot_pitch(g)));
         CK(c->lens.ensure((size_t)nlayers * g.nchunks * 8));
@@ -524,8 +532,10 @@ static int encode_impl(wrb_codec* c, const void* d_field, int dtype, int nx, int
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     if (c->timing) for (int i = 0; i < 4; i++) cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]);
-    if (!c->h_state->trivial && !c->h_state->done && nlayers < kNLayMax)       // the layer bound did not hold: all 8
+    if (!c->h_state->trivial && !c->h_state->done && nlayers < kNLayMax) {     // the layer bound did not hold: all 8
+        c->guess_misses++;
         return encode_impl(c, d_field, dtype, nx, ny, nz, wtflag, tolrel, hdr, d_data_enc, cap, sg, kNLayMax);
+    }
     header_from_state(*c->h_state, wtflag, hdr);
     if (c->h_state->error) return fail(c, WRB_E_OVERFLOW, "encoded data does not fit in data_enc");
     return 0;
@@ -668,33 +678,48 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
     lay[0] = 0;
     for (int l = 0; l < nlay; l++) lay[l + 1] = lay[l] + hdr->len_enc_vec[l];
     if (lay[nlay] != hdr->ntot_enc) return fail(c, WRB_E_FORMAT, "len_enc_vec does not sum to ntot_enc");
-    // container geometry from the first layer's header (all layers share it)
+    // container geometry from the layers' headers: every layer is checked on the host before any kernel reads its
+    // tables (a truncated or corrupt file must end in WRB_E_FORMAT, not in an out-of-bounds read on the device)
     unsigned char* peek = (unsigned char*)(c->h_u64 + 64);
-    const size_t npeek = hdr->len_enc_vec[0] < 32 ? hdr->len_enc_vec[0] : 32;
     if (c->timing) cudaEventRecord(c->ev[0], s);
-    CK(cudaMemcpyAsync(peek, d_data_enc, npeek, cudaMemcpyDeviceToHost, s));
+    size_t npeek[kNLayMax];
+    for (int l = 0; l < nlay; l++) {
+        npeek[l] = hdr->len_enc_vec[l] < 32 ? hdr->len_enc_vec[l] : 32;
+        if (npeek[l] == 0) return fail(c, WRB_E_FORMAT, "empty layer");
+        CK(cudaMemcpyAsync(peek + 32 * l, d_data_enc + lay[l], npeek[l], cudaMemcpyDeviceToHost, s));
+    }
     CK(cudaStreamSynchronize(s));
     int chunked = 0;
     unsigned long long chunk_len = 0, nseek = 0;
-    if (npeek >= 32 && peek[0] == 'W' && peek[1] == 'R' && peek[2] == 'C' && peek[3] == 'K') {
-        chunked = 1;
-        unsigned long long nsym = 0, nch = 0, ver = 0;
-        for (int k = 0; k < 8; k++) { chunk_len |= (unsigned long long)peek[8 + k] << (8 * k); nsym |= (unsigned long long)peek[16 + k] << (8 * k); }
-        for (int k = 0; k < 4; k++) { ver |= (unsigned long long)peek[4 + k] << (8 * k); nch |= (unsigned long long)peek[24 + k] << (8 * k); nseek |= (unsigned long long)peek[28 + k] << (8 * k); }
-        // version 3: 10-byte seek entries on nested grids; a version-2 container without seek points has the same layout
-        if (!(ver == 3 || (ver == 2 && nseek == 0)) || nsym != ntot || chunk_len == 0 || chunk_len > ntot || nch != (ntot + chunk_len - 1) / chunk_len || nseek > 15)
-            return fail(c, WRB_E_FORMAT, "chunk container header does not match the field size");
-    } else if (npeek >= 1 && peek[0] != 0x00) {
-        return fail(c, WRB_E_FORMAT, "layer is neither a WRCK container nor a reference stream");
+    for (int l = 0; l < nlay; l++) {
+        const unsigned char* pk = peek + 32 * l;
+        const bool wrck = npeek[l] >= 32 && pk[0] == 'W' && pk[1] == 'R' && pk[2] == 'C' && pk[3] == 'K';
+        if (l > 0 && (int)wrck != chunked) return fail(c, WRB_E_FORMAT, "layers mix container and stream layouts");
+        if (wrck) {
+            chunked = 1;
+            unsigned long long cl = 0, nsym = 0, nch = 0, ver = 0, nsk = 0;
+            for (int k = 0; k < 8; k++) { cl |= (unsigned long long)pk[8 + k] << (8 * k); nsym |= (unsigned long long)pk[16 + k] << (8 * k); }
+            for (int k = 0; k < 4; k++) { ver |= (unsigned long long)pk[4 + k] << (8 * k); nch |= (unsigned long long)pk[24 + k] << (8 * k); nsk |= (unsigned long long)pk[28 + k] << (8 * k); }
+            // version 3: 10-byte seek entries on nested grids; a version-2 container without seek points has the same layout
+            if (!(ver == 3 || (ver == 2 && nsk == 0)) || nsym != ntot || cl == 0 || cl > ntot || nch != (ntot + cl - 1) / cl || nsk > 15)
+                return fail(c, WRB_E_FORMAT, "chunk container header does not match the field size");
+            if (l > 0 && (cl != chunk_len || nsk != nseek)) return fail(c, WRB_E_FORMAT, "layers disagree on the chunk geometry");
+            // header + tables + the shortest possible streams must fit into the layer: this also bounds every
+            // allocation derived from the chunk count by the size of the data actually handed in
+            if (32ull + (4ull + 10ull * nsk + 8ull) * nch > hdr->len_enc_vec[l]) return fail(c, WRB_E_FORMAT, "chunk tables exceed the layer");
+            chunk_len = cl; nseek = nsk;
+        } else if (pk[0] != 0x00) {
+            return fail(c, WRB_E_FORMAT, "layer is neither a WRCK container nor a reference stream");
+        }
     }
     ChunkGeom g = make_geom(ntot, chunk_len, (unsigned)nseek);
     if (g.nseek != nseek) return fail(c, WRB_E_FORMAT, "seek table does not match the chunk geometry");
-    if (getenv("WRB_DEC_PADDED") == nullptr) g.pitch = g.chunk_len;        // decoded symbols are kept flat (array order): the inverse transform indexes them directly
+    g.pitch = g.chunk_len;        // decoded symbols are kept flat (array order): the inverse transform indexes them directly
     int rc;
     const bool fused_all = sg == nullptr && all_levels_fused(nx, ny, nz, (int)hdr->wlev) && nz >= (1 << hdr->wlev) &&
                            getenv("WRB_NO_FUSED_DEQUANT") == nullptr;
     if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr, !fused_all, !fused_all))) return rc;
-    if ((rc = ensure_coder_buffers(c, g, nlay, false))) return rc;
+    if ((rc = ensure_coder_buffers(c, g, nlay, false, false))) return rc;
     int* d_err = (int*)c->misc.p;
     CK(cudaMemsetAsync(d_err, 0, sizeof(int), s));
     CK(cudaMemcpyAsync(c->layoff.p, lay, (nlay + 1) * 8, cudaMemcpyHostToDevice, s));
@@ -702,7 +727,7 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
     if (c->timing) cudaEventRecord(c->ev[1], s);
     const unsigned long long lstride = (unsigned long long)g.nchunks * g.pitch;
     range_decode_chunks(d_data_enc, (const unsigned long long*)c->offs.p, (const unsigned long long*)c->layoff.p, g, nlay,
-                        (uint8_t*)c->sym.p, lstride, d_err, s);
+                        (uint8_t*)c->sym.p, lstride, (unsigned long long)hdr->ntot_enc, d_err, s);
     if (c->timing) cudaEventRecord(c->ev[2], s);
     // The inverse z pass rebuilds the coefficients from the symbols itself; a separate dequantise pass is only
     // needed without a transform, for extent-1 z, and in slab mode (its band buffers are built from coef).
@@ -799,7 +824,9 @@ int wrb_encode_host(wrb_codec* c, const void* field, int dtype, int nx, int ny, 
         c->src_pipe = &pipe;
         rc = wrb_encode_device(c, c->field.p, dtype, nx, ny, nz, wtflag, tolrel, hdr, (unsigned char*)c->blob.p, cap);
         c->src_pipe = nullptr;
-        (void)pipe.used;                        // wavelet_forward waits for the whole copy itself when it cannot follow it
+        // on failure (or when the transform could not follow the pieces) nothing of ours may still be reading the
+        // caller's buffer when this call returns
+        if (rc || !pipe.used) cudaStreamSynchronize(c->copy_stream);
     } else {
         rc = copy_to_device(c, c->field.p, field, ntot * esz);
         if (rc) return rc;
@@ -926,7 +953,7 @@ int wrb_range_decode_device(wrb_codec* c, const unsigned char* d_in, const unsig
     cudaError_t e3 = cudaStreamSynchronize(s);
     free(offs);
     CK(e1); CK(e2); CK(e3);
-    range_decode_chunks(d_in, (const unsigned long long*)c->offs.p, nullptr, g, 1, (uint8_t*)c->sym.p, 0, d_err, s);
+    range_decode_chunks(d_in, (const unsigned long long*)c->offs.p, nullptr, g, 1, (uint8_t*)c->sym.p, 0, acc, d_err, s);
     unsigned long long per = (g.chunk_len + 255) / 256;
     unsigned int gy = (unsigned int)(per < 64 ? (per ? per : 1) : 64);
     dim3 grid(g.nchunks, gy, 1);

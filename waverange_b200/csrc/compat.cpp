@@ -10,28 +10,40 @@
 #include <cstdlib>
 #include <exception>
 #include <iostream>
-#include <mutex>
 #include <stdexcept>
 #include <string>
 #include "../../include/waverange_b200.h"
 #include "../../include/waverange.h"
 
 namespace {
-std::mutex g_mu;
-wrb_codec* g_codec = nullptr;
+// One codec handle per (host thread, device): the reference's entry points are re-entrant on distinct buffers
+// (SURVEY.md section 8b "callable from one host thread per GPU/stream"), so two threads -- on one GPU or on two --
+// must neither serialise on a lock nor share scratch buffers.  The device is the calling thread's current CUDA device
+// (cudaSetDevice before the call, as with any CUDA library); WRB_DEVICE overrides it for programs that never touch CUDA.
+struct ThreadCodecs {
+    struct Entry { int dev; wrb_codec* c; };
+    Entry e[16];
+    int n = 0;
+    ~ThreadCodecs() { for (int i = 0; i < n; i++) wrb_destroy(e[i].c); }
+};
+thread_local ThreadCodecs t_codecs;
 
 wrb_codec* codec()
 {
-    if (!g_codec) {
-        int dev = 0;
-        if (const char* e = getenv("WRB_DEVICE")) dev = atoi(e);
-        int rc = wrb_create(&g_codec, dev);
-        if (rc != 0 || !g_codec) {
-            fprintf(stderr, "waverange_b200: no usable CUDA device (wrb_create -> %d); there is no CPU fallback\n", rc);
-            throw std::runtime_error("waverange_b200: CUDA device unavailable");
-        }
+    int dev = 0;
+    const char* env = getenv("WRB_DEVICE");
+    if (env && *env) dev = atoi(env);
+    else if (wrb_current_device(&dev) != 0) dev = 0;
+    for (int i = 0; i < t_codecs.n; i++) if (t_codecs.e[i].dev == dev) return t_codecs.e[i].c;
+    wrb_codec* c = nullptr;
+    int rc = wrb_create(&c, dev);
+    if (rc != 0 || !c) {
+        fprintf(stderr, "waverange_b200: no usable CUDA device (wrb_create -> %d); there is no CPU fallback\n", rc);
+        throw std::runtime_error("waverange_b200: CUDA device unavailable");
     }
-    return g_codec;
+    if (t_codecs.n < 16) { t_codecs.e[t_codecs.n].dev = dev; t_codecs.e[t_codecs.n].c = c; t_codecs.n++; }
+    else { wrb_destroy(t_codecs.e[0].c); t_codecs.e[0].dev = dev; t_codecs.e[0].c = c; }
+    return c;
 }
 bool verbose() { const char* e = getenv("WRB_VERBOSE"); return e && *e && *e != '0'; }
 }  // namespace
@@ -41,13 +53,12 @@ extern "C" void encoding_wrap(int nx, int ny, int nz, double* fld_1d, int wtflag
                               unsigned char& wlev, unsigned char& nlay, unsigned long int& ntot_enc, double* deps_vec,
                               double* minval_vec, unsigned long int* len_enc_vec, unsigned char* data_enc)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
     wrb_codec* c = codec();
     // minimum cutoff (wrappers.cpp:292-293); mx*my*mz > 1 selects the spatially varying branch (:343-379)
     unsigned int mtot = (unsigned int)(mx * my * mz);
     double tolrel = cutoffvec[0];
     for (unsigned int k = 1; k < mtot; k++) if (cutoffvec[k] < tolrel) tolrel = cutoffvec[k];
-    struct LocalGuard {                      // the handle is process-global: never leave the local cutoff set
+    struct LocalGuard {                      // the handle outlives the call: never leave the local cutoff set
         wrb_codec* c; bool on;
         ~LocalGuard() { if (on) wrb_set_local_cutoff(c, 0, 0, 0, nullptr); }
     } guard{c, mtot > 1};
@@ -79,7 +90,6 @@ extern "C" void decoding_wrap(int nx, int ny, int nz, double* fld_1d, double& to
                               unsigned long int& ntot_enc, double* deps_vec, double* minval_vec,
                               unsigned long int* len_enc_vec, unsigned char* data_enc)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
     wrb_codec* c = codec();
     wrb_header h{};
     h.tolabs = tolabs; h.midval = midval; h.halfspanval = halfspanval;

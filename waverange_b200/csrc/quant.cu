@@ -245,11 +245,8 @@ template <int LAYER>
 static void launch_quantise(const double* coef, const ChunkGeom& g, int layer, DevState* st, uint8_t* sym, uint32_t* hist,
                             cudaStream_t s)
 {
-    static bool configured = false;                       // 64 KiB dynamic shared memory: above the 48 KiB default
-    if (!configured) {
-        cudaFuncSetAttribute(quantise_kernel<LAYER>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQHistBytes);
-        configured = true;
-    }
+    static DeviceOnce once;                               // 64 KiB dynamic shared memory: above the 48 KiB default (per device)
+    once.run([] { cudaFuncSetAttribute(quantise_kernel<LAYER>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQHistBytes); });
     quantise_kernel<LAYER><<<dim3(g.nblocks, kQSub, 1), kQThreads, kQHistBytes, s>>>(coef, g, layer, st, sym, hist);
 }
 

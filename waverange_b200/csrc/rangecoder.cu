@@ -501,12 +501,17 @@ __device__ __forceinline__ uint32_t div_small_quot_fast(uint32_t a, uint32_t b)
 struct Dec {
     uint32_t X, range;
     uint32_t ip;                    // index of the next stream byte
+    uint32_t lim;                   // last byte index that may be read: stream length + kDecSlack - 1
     const uint8_t* p;               // stream start
 };
+// A well-formed stream is never read more than a few bytes past its end (the reference's decoder does the same); a
+// corrupt one must not walk out of the blob: reads are clamped to stream end + kDecSlack (inside the 64 bytes of slack
+// every blob has) and a position beyond that flags the chunk as malformed.
+constexpr uint32_t kDecSlack = 12;
 
 __device__ __forceinline__ void dec_renorm(Dec& d)
 {
-    while (d.range <= kBottom) { d.X = (d.X << 8) | d.p[d.ip++]; d.range <<= 8; }
+    while (d.range <= kBottom) { d.X = (d.X << 8) | d.p[min(d.ip, d.lim)]; d.ip++; d.range <<= 8; }
 }
 
 // rangecod.c:321-331 + :362-366 (decode_short), :339-351 (decode_update)
@@ -567,7 +572,7 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
                                                           const unsigned long long* __restrict__ offs,
                                                           const unsigned long long* __restrict__ lay_off, ChunkGeom g,
                                                           uint8_t* __restrict__ sym, unsigned long long sym_layer_stride,
-                                                          int* error)
+                                                          unsigned long long blob_len, int* error)
 {
     constexpr unsigned int CPW = 32 / NSUB;
     constexpr bool kPair = PAIR, kLazy = LAZY;
@@ -588,7 +593,14 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
     if (sub > 0 && (unsigned long long)sub * g.sub_len >= clen) return;       // nothing for this lane
     uint8_t* __restrict__ outb = sym + (unsigned long long)layer * sym_layer_stride + (unsigned long long)chunk * g.pitch;
     Dec d;
-    d.p = blob + offs[(unsigned long long)layer * g.nchunks + chunk];
+    // byte range of this chunk's stream; everything read below stays inside [start, end + kDecSlack)
+    const unsigned long long oidx = (unsigned long long)layer * g.nchunks + chunk;
+    const unsigned long long cbeg = offs[oidx];
+    const unsigned long long cend = (chunk + 1 < g.nchunks) ? offs[oidx + 1] : (lay_off != nullptr ? lay_off[layer + 1] : blob_len);
+    if (cend > blob_len || cbeg + 8 > cend || cend - cbeg > 0x7FFFFFFFull) { atomicExch(error, 4); return; }   // shortest stream: 8 bytes
+    const uint32_t slen = (uint32_t)(cend - cbeg);
+    d.lim = slen + kDecSlack - 1;
+    d.p = blob + cbeg;
     d.X = d.p[1];                                 // lead byte skipped (rangecod.c:283-288)
     d.ip = 2;
     d.range = 1u << 7;
@@ -646,6 +658,7 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
                     const uint8_t* q = sp - (unsigned long long)kSeekBytes * j;
                     spos += q[8] | (q[9] << 8);
                 }
+                if (spos + 4 > slen) { bad = true; break; }           // the entry point must lie inside the stream
                 const uint8_t* q = d.p + spos;
                 const uint32_t W = ((uint32_t)q[0] << 24) | (q[1] << 16) | (q[2] << 8) | q[3];
                 d.X = W - 2 * slow;
@@ -664,7 +677,8 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
         const uint32_t* __restrict__ wbase = reinterpret_cast<const uint32_t*>(pa & ~3ull);
         const uint32_t boff = (uint32_t)(pa & 3ull);
         uint32_t a = boff + d.ip;
-        auto ldw = [&](uint32_t widx) -> uint32_t { return __ldg(wbase + widx); };
+        const uint32_t wmax = (boff + d.lim) >> 2;            // last word that may be read (see kDecSlack)
+        auto ldw = [&](uint32_t widx) -> uint32_t { return __ldg(wbase + min(widx, wmax)); };
         uint32_t w0 = ldw(a >> 2), w1 = ldw((a >> 2) + 1);
         uint32_t w2 = kLazy ? ldw((a >> 2) + 2) : 0u;
         uint32_t sel = 0x0123u + 0x1111u * (a & 3u);
@@ -696,7 +710,7 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
                 // symbols somewhere in the warp) is off the dependency chain.
                 if ((an ^ a) & 4u) { w0 = w1; w1 = w2; w2 = ldw((an >> 2) + 2); }
             } else {
-                if ((an ^ a) & 0x80u) asm volatile("prefetch.global.L1 [%0];" :: "l"(wbase + (an >> 2) + 64));
+                if ((an ^ a) & 0x80u) asm volatile("prefetch.global.L1 [%0];" :: "l"(wbase + min((an >> 2) + 64, wmax)));
                 w0 = ldw(an >> 2);
                 w1 = ldw((an >> 2) + 1);
             }
@@ -765,6 +779,7 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
         };
         if (__all_sync(__activemask(), bs >= 256u)) symbol_loop(std::true_type{}); else symbol_loop(std::false_type{});
         d.X = X; d.range = range; d.ip = a - boff;
+        if (d.ip > slen + 4) { bad = true; break; }           // consumed more bytes than the stream has: malformed
         n += bs;
         if (NSUB > 1) {
             if (s1 == bs) {                       // owner of the chunk's last symbol checks the end marker
@@ -778,8 +793,8 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
 }
 
 void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, const unsigned long long* lay_off,
-                         const ChunkGeom& g, int nlay, uint8_t* sym, unsigned long long sym_layer_stride, int* error,
-                         cudaStream_t s)
+                         const ChunkGeom& g, int nlay, uint8_t* sym, unsigned long long sym_layer_stride,
+                         unsigned long long blob_len, int* error, cudaStream_t s)
 {
     const unsigned int nsub = g.nseek + 1;        // make_geom grants 0, 1, 3 or 7 seek points
     const unsigned int cpw = 32 / nsub;
@@ -792,12 +807,10 @@ void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, co
     const int smem = dec_table_bytes(pair) * (int)cpw;
 #define WRB_DEC_LAUNCH(NS, V, P)                                                                                       \
     do {                                                                                                               \
-        static bool configured = false;                                                                                \
-        if (!configured) {      /* the fast form with one lane per chunk needs more than the 48 KB default */           \
-            cudaFuncSetAttribute(range_decode_kernel<NS, V, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
-            configured = true;                                                                                         \
-        }                                                                                                              \
-        range_decode_kernel<NS, V, P><<<grid, 32, smem, s>>>(blob, offs, lay_off, g, sym, sym_layer_stride, error);    \
+        /* the fast form with one lane per chunk needs more than the 48 KB default; the attribute is per device */      \
+        static DeviceOnce once;                                                                                        \
+        once.run([] { cudaFuncSetAttribute(range_decode_kernel<NS, V, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }); \
+        range_decode_kernel<NS, V, P><<<grid, 32, smem, s>>>(blob, offs, lay_off, g, sym, sym_layer_stride, blob_len, error); \
     } while (0)
 #define WRB_DEC_VARIANTS(NS)                                                                                 \
     do {                                                                                                     \

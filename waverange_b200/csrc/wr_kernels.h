@@ -1,5 +1,6 @@
 // wr_kernels.h -- internal launcher interface between codec.cu and the kernel files.
 #pragma once
+#include <mutex>
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "wr_common.cuh"
@@ -120,10 +121,26 @@ void assemble_container(const uint8_t* slots, unsigned long long slot_pitch, con
 void parse_container(const uint8_t* blob, const ChunkGeom& g, int chunked, int nlay, const unsigned long long* lay_off,
                      unsigned long long* offs, int* error, cudaStream_t s);
 void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, const unsigned long long* lay_off,
-                         const ChunkGeom& g, int nlay, uint8_t* sym, unsigned long long sym_layer_stride, int* error,
-                         cudaStream_t s);
+                         const ChunkGeom& g, int nlay, uint8_t* sym, unsigned long long sym_layer_stride,
+                         unsigned long long blob_len, int* error, cudaStream_t s);
 
 // ---- codec.cu -----------------------------------------------------------------------------
 void note_launch(int n);   // kernel-launch accounting (wrb_launch_count)
+
+// "first use on this device?" for per-device one-time setup (cudaFuncSetAttribute is per device / context, a codec
+// handle may live on any GPU, and several handles may be driven from different host threads)
+struct DeviceOnce {
+    std::mutex m;
+    unsigned long long seen[2] = {0, 0};
+    template <class F> void run(F f)
+    {
+        int dev = 0;
+        const bool known = cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 128;
+        std::lock_guard<std::mutex> lock(m);                  // a second thread must not launch before the first has set it
+        if (known && (seen[dev >> 6] >> (dev & 63) & 1ull)) return;
+        f();
+        if (known) seen[dev >> 6] |= 1ull << (dev & 63);
+    }
+};
 
 }  // namespace wrb

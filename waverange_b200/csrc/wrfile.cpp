@@ -364,6 +364,7 @@ int wrb_file_decode(wrb_codec* c, const char* encoded_name, const char* header_n
         vals.resize(n * (size_t)d.nbytes);
         if (d.icomp) {
             const long long nzh = (long long)d.nz * d.nh;
+            if (nzh > 0x7fffffffll) { rc = fail(WRB_E_FORMAT, "nz*nh in the header does not fit an int"); break; }
             enc.resize(rec.hdr.ntot_enc + 64);
             if (rec.hdr.ntot_enc > 0 && fread(enc.data(), 1, rec.hdr.ntot_enc, fin) != rec.hdr.ntot_enc) {
                 rc = fail(WRB_E_FORMAT, "encoded file is shorter than the header says");
