@@ -112,16 +112,20 @@ int wrb_decode_device(wrb_codec* c, void* d_field_out, int dtype, int nx, int ny
 /* ---- z-slab partition of one large field across the GPUs of a box -------- */
 /* Rank r of n owns the planes [z0, z0+nzl) of an (nx, ny, nz) field (nz % 16 == 0, z0 and nzl multiples
  * of 32).  x/y lifting is slab-local; the z lifting of every level reads 4 planes from below and 3
- * from above (inverse: 2 + 2 per band) that `halo` fetches from the z-neighbours, and the field /
- * coefficient / per-layer residual extrema go through `reduce` (the codec packs them so that one
- * MIN reduction of two int64 values is enough).  Both callbacks must be ordered
- * with the codec's stream (torch.distributed over NCCL in waverange_b200/slab.py).  Each rank gets
- * its own container: the coefficients of the global transform that live on its slab, in the
- * wavelet-space order of a local (nx, ny, nzl) array; deps_vec / minval_vec / nlay are identical on
- * all ranks.  Decompression uses the same partition. */
-typedef int (*wrb_halo_fn)(void* user, void* d_buf, int elem_bytes, long long plane_elems, int nplanes_own,
-                           int halo_lo, int halo_hi);
-/* in-place global MIN over `count` signed 64-bit integers on the device (one all_reduce) */
+ * from above (inverse: 2 + 2 per band) that come from the z-neighbours, and the field / coefficient /
+ * per-layer residual extrema are reduced over all ranks (the codec packs them so that one MIN reduction
+ * of two int64 values is enough).
+ *
+ * The collectives are issued by the library itself over NCCL (wrb_set_comm below: grouped ncclSend /
+ * ncclRecv of whole planes, ncclAllReduce), so a C, C++ or Fortran caller needs nothing else; or they are
+ * injected as callbacks (wrb_set_slab: gloo in the CPU tests, several emulated ranks on one GPU).
+ *   halo  : neighbour exchange along z.  Send down_bytes from send_down to rank-1 and receive as many into
+ *           recv_hi from rank+1; send up_bytes from send_up to rank+1 and receive as many into recv_lo from
+ *           rank-1; nothing at the domain ends.  All pointers are device pointers.
+ *   reduce: in-place global MIN over `count` signed 64-bit integers on the device (one all-reduce).
+ * Both must be ordered with the codec's stream. */
+typedef int (*wrb_halo_fn)(void* user, const void* send_down, const void* send_up, void* recv_lo, void* recv_hi,
+                           unsigned long long down_bytes, unsigned long long up_bytes);
 typedef int (*wrb_reduce_fn)(void* user, long long* d_buf, int count);
 int wrb_set_slab(wrb_codec* c, int rank, int nranks, wrb_halo_fn halo, wrb_reduce_fn reduce, void* user);
 int wrb_encode_slab_device(wrb_codec* c, const void* d_field_slab, int dtype, int nx, int ny, int nz, int z0, int nzl,

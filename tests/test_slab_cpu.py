@@ -64,7 +64,10 @@ def _worker(rank, world, port, q):
     lo, hi, nown, plane = 4, 3, 6, 10
     buf = np.full((lo + nown + hi, plane), -1.0)
     buf[lo:lo + nown] = (100 * rank + np.arange(nown))[:, None] + np.arange(plane)[None, :] / 100.0
-    rc = hk.halo_cb(None, buf.ctypes.data, 8, plane, nown, lo, hi)
+    pb = plane * 8
+    base = buf.ctypes.data
+    # my first `hi` planes go down, my last `lo` planes go up; the halos arrive before / after the own planes
+    rc = hk.halo_cb(None, base + lo * pb, base + nown * pb, base, base + (lo + nown) * pb, hi * pb, lo * pb)
     ok &= rc == 0 and hk.error is None
     own = lambda r: (100 * r + np.arange(nown))[:, None] + np.arange(plane)[None, :] / 100.0
     if rank > 0:

@@ -64,7 +64,7 @@ class WaveRangeError(RuntimeError):
 
 
 # callbacks of the z-slab partition (include/waverange_b200.h: wrb_halo_fn, wrb_reduce_fn)
-HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int)
+HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_ulonglong)
 REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)
 
 

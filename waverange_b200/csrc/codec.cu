@@ -48,7 +48,7 @@ struct wrb_codec {
     int chunk_blocks = 1;
     int seek_points = -1;            // decoder entry points inside a chunk; -1: the encoder decides (assemble_container)
     std::string err;
-    DevBuf coef, tmp, lllA, lllB, sym, hist, slots, lens, dstoff, seek, state, blob, field, offs, layoff, misc, ext, lcut;
+    DevBuf coef, tmp, lllA, lllB, sym, hist, slots, lens, dstoff, seek, state, blob, field, offs, layoff, misc, ext, lcut, zring;
     int lc_mx = 0, lc_my = 0, lc_mz = 0;      // local cutoff grid (0: off), wrb_set_local_cutoff
     double lc_min = 0;
     SlabHooks hooks;                  // z-slab partition collectives (nranks == 1: none)
@@ -209,7 +209,7 @@ int wrb_trim(wrb_codec* c)
     if (!c) return WRB_E_ARG;
     cudaSetDevice(c->device);
     DevBuf* all[] = {&c->coef, &c->tmp, &c->lllA, &c->lllB, &c->sym, &c->hist, &c->slots, &c->lens,
-                     &c->dstoff, &c->seek, &c->blob, &c->field, &c->offs, &c->layoff, &c->misc, &c->ext, &c->lcut};
+                     &c->dstoff, &c->seek, &c->blob, &c->field, &c->offs, &c->layoff, &c->misc, &c->ext, &c->lcut, &c->zring};
     for (DevBuf* b : all) b->release();
     c->lc_mx = c->lc_my = c->lc_mz = 0;                  // the local-cutoff grid went with lcut: off until set again
     return 0;
@@ -371,8 +371,9 @@ static bool all_levels_fused(int nx, int ny, int nz, int levels)
 // scratch of the transform.  need_coef / need_tmp: see all_levels_fused(); the z-slab mode always takes both
 // (its level-1 input is copied into `tmp` with halo room, its inverse may fall back to the line passes)
 static int ensure_transform_buffers(wrb_codec* c, int nx, int ny, int nz, bool slab = false, bool need_coef = true,
-                                    bool need_tmp = true)
+                                    bool need_tmp = true, bool need_zring = false)
 {
+    if (need_zring && inverse_two_pass_enabled()) CK(c->zring.ensure(inverse_two_pass_scratch_bytes(nx, ny, nz)));
     const size_t ntot = (size_t)nx * ny * nz;
     const size_t m1 = (size_t)half_up(nx) * half_up(ny) * half_up(nz);
     const size_t m2 = (size_t)half_up(half_up(nx)) * half_up(half_up(ny)) * half_up(half_up(nz));
@@ -388,7 +389,7 @@ static int ensure_transform_buffers(wrb_codec* c, int nx, int ny, int nz, bool s
 
 static int ensure_coder_buffers(wrb_codec* c, const ChunkGeom& g, int nlayers, bool need_slots, bool need_hist = true)
 {
-    CK(c->sym.ensure((size_t)nlayers * g.nchunks * g.pitch + 64));
+    CK(c->sym.ensure((size_t)nlayers * (((size_t)g.nchunks * g.pitch + 15) & ~(size_t)15) + 64));
     if (need_hist) CK(c->hist.ensure((size_t)nlayers * g.nblocks * 256 * 4));
     if (need_slots) {
         CK(c->slots.ensure((size_t)nlayers * g.nchunks * chunk_slot_pitch(g)));
@@ -650,7 +651,7 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
         ChunkGeom g = make_geom(ntot, 0, 0);
         g.pitch = g.chunk_len;
         int rc;
-        if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr))) return rc;
+        if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr, true, true, sg == nullptr && hdr->wlev > 0))) return rc;
         const unsigned long long lstride = ntot;
         if (c->timing) for (int i = 0; i < 4; i++) cudaEventRecord(c->ev[i], s);
         const bool slab_fused = sg != nullptr && hdr->wlev > 0 && wavelet_inverse_slab_fused_ok(nx, ny, sg->nz_global, nz, (int)hdr->wlev);
@@ -663,10 +664,11 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
                 return fail(c, WRB_E_CUDA, "halo exchange callback failed");
         } else if (fuse) {
             wavelet_inverse((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, d_out, dtype == WRB_F32,
-                            nx, ny, nz, (int)hdr->wlev, s, d_sym_flat, lstride, g.chunk_len, g.pitch, nlay, hdr->deps_vec, hdr->minval_vec);
+                            nx, ny, nz, (int)hdr->wlev, s, d_sym_flat, lstride, g.chunk_len, g.pitch, nlay, hdr->deps_vec, hdr->minval_vec,
+                            nullptr, (double*)c->zring.p, c->zring.cap);
         } else {
             wavelet_inverse((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, d_out, dtype == WRB_F32,
-                            nx, ny, nz, (int)hdr->wlev, s);
+                            nx, ny, nz, (int)hdr->wlev, s, nullptr, 0, 0, 0, 0, nullptr, nullptr, nullptr, (double*)c->zring.p, c->zring.cap);
         }
         if (c->timing) cudaEventRecord(c->ev[4], s);
         CK(cudaStreamSynchronize(s));
@@ -718,14 +720,15 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
     int rc;
     const bool fused_all = sg == nullptr && all_levels_fused(nx, ny, nz, (int)hdr->wlev) && nz >= (1 << hdr->wlev) &&
                            getenv("WRB_NO_FUSED_DEQUANT") == nullptr;
-    if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr, !fused_all, !fused_all))) return rc;
+    if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr, !fused_all, !fused_all, sg == nullptr && hdr->wlev > 0))) return rc;
     if ((rc = ensure_coder_buffers(c, g, nlay, false, false))) return rc;
     int* d_err = (int*)c->misc.p;
     CK(cudaMemsetAsync(d_err, 0, sizeof(int), s));
     CK(cudaMemcpyAsync(c->layoff.p, lay, (nlay + 1) * 8, cudaMemcpyHostToDevice, s));
     parse_container(d_data_enc, g, chunked, nlay, (const unsigned long long*)c->layoff.p, (unsigned long long*)c->offs.p, d_err, s);
     if (c->timing) cudaEventRecord(c->ev[1], s);
-    const unsigned long long lstride = (unsigned long long)g.nchunks * g.pitch;
+    // layer planes of the decoded symbols start 16-byte aligned (the z pass of the inverse reads them as words)
+    const unsigned long long lstride = ((unsigned long long)g.nchunks * g.pitch + 15ull) & ~15ull;
     range_decode_chunks(d_data_enc, (const unsigned long long*)c->offs.p, (const unsigned long long*)c->layoff.p, g, nlay,
                         (uint8_t*)c->sym.p, lstride, (unsigned long long)hdr->ntot_enc, d_err, s);
     if (c->timing) cudaEventRecord(c->ev[2], s);
@@ -744,10 +747,10 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
         if (fuse_deq)
             wavelet_inverse((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, d_out, dtype == WRB_F32,
                             nx, ny, nz, (int)hdr->wlev, s, (const uint8_t*)c->sym.p, lstride, g.chunk_len, g.pitch, nlay,
-                            hdr->deps_vec, hdr->minval_vec, sink);
+                            hdr->deps_vec, hdr->minval_vec, sink, (double*)c->zring.p, c->zring.cap);
         else
             wavelet_inverse((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, d_out, dtype == WRB_F32,
-                            nx, ny, nz, (int)hdr->wlev, s);
+                            nx, ny, nz, (int)hdr->wlev, s, nullptr, 0, 0, 0, 0, nullptr, nullptr, nullptr, (double*)c->zring.p, c->zring.cap);
     }
     if (c->timing) cudaEventRecord(c->ev[4], s);
     int* h_err = (int*)(c->h_u64 + 128);
@@ -879,7 +882,7 @@ int wrb_wavelet3d_device(wrb_codec* c, double* d_x, int nx, int ny, int nz, int 
     CK(cudaSetDevice(c->device));
     const size_t ntot = (size_t)nx * ny * nz;
     int rc;
-    if ((rc = ensure_transform_buffers(c, nx, ny, nz))) return rc;
+    if ((rc = ensure_transform_buffers(c, nx, ny, nz, false, true, true, lvl < 0))) return rc;
     CK(c->field.ensure(ntot * 8));
     cudaStream_t s = c->stream;
     if (lvl == 0) return 0;
@@ -889,7 +892,8 @@ int wrb_wavelet3d_device(wrb_codec* c, double* d_x, int nx, int ny, int nz, int 
         CK(cudaMemcpyAsync(c->field.p, d_x, ntot * 8, cudaMemcpyDeviceToDevice, s));
         wavelet_forward(c->field.p, 0, d_x, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, nx, ny, nz, lvl, st, s);
     } else {
-        wavelet_inverse(d_x, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, c->field.p, 0, nx, ny, nz, -lvl, s);
+        wavelet_inverse(d_x, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, c->field.p, 0, nx, ny, nz, -lvl, s,
+                        nullptr, 0, 0, 0, 0, nullptr, nullptr, nullptr, (double*)c->zring.p, c->zring.cap);
         CK(cudaMemcpyAsync(d_x, c->field.p, ntot * 8, cudaMemcpyDeviceToDevice, s));
     }
     CK(cudaStreamSynchronize(s));

@@ -406,7 +406,7 @@ static inline int ceil_shift(int n, int k) { return (int)(((long long)n + (1ll <
 void wavelet_inverse(double* coef, double* tmp, double* lllA, double* lllB, void* out, int out_is_f32,
                      int nx, int ny, int nz, int levels, cudaStream_t s, const uint8_t* sym,
                      unsigned long long layer_stride, unsigned long long chunk_len, unsigned long long pitch, int nlay,
-                     const double* deps, const double* minval, HostSink* sink)
+                     const double* deps, const double* minval, HostSink* sink, double* zb, size_t zb_bytes)
 {
     DequantSrc dq{};
     dq.sym = sym; dq.layer_stride = layer_stride; dq.chunk_len = chunk_len; dq.pitch = pitch; dq.nlay = nlay;
@@ -429,16 +429,27 @@ void wavelet_inverse(double* coef, double* tmp, double* lllA, double* lllB, void
         fused = fused_inverse_supported(ceil_shift(nx, k), ceil_shift(ny, k), ceil_shift(nz, k));
     if (fused) {
         const double* prev = nullptr;
+        // two-pass level (z stream, then TMA-staged y/x tiles) when its scratch is there; else the one-kernel level
+        const bool two_pass = zb != nullptr && zb_bytes >= (size_t)nx * ny * 16 + 256 && inverse_two_pass_enabled();
+        auto level = [&](const double* lllp, void* dst, int dst_f32, long long dsy, long long dsz, int n0, int n1, int n2,
+                         int p0, int p1) {
+            if (two_pass)
+                inverse_level_two_pass(coef, ay, az, sym, layer_stride, nlay, deps, minval, lllp, dst, dst_f32, dsy, dsz, n0, n1,
+                                       n2, zb, zb_bytes, s, p0, p1);
+            else
+                fused_inverse_level(coef, ay, az, sym, layer_stride, nlay, deps, minval, lllp, dst, dst_f32, dsy, dsz, n0, n1, n2,
+                                    s, p0, p1);
+        };
         for (int k = levels - 1; k >= 0; k--) {
             const int n0 = ceil_shift(nx, k), n1 = ceil_shift(ny, k), n2 = ceil_shift(nz, k);
             if (k == 0 && sink != nullptr && n2 / 2 >= 64) {
                 // Four z-pieces; piece i leaves for the host on the copy stream while piece i+1 is computed (the copy of a
-                // 512^3 float field takes ~10 ms, the level ~1.4 ms: only the first piece's compute stays exposed).
+                // 512^3 float field takes ~10 ms, the level ~1 ms: only the first piece's compute stays exposed).
                 const int q2 = n2 / 2;
                 const size_t esz = out_is_f32 ? 4 : 8;
                 for (int i = 0; i < 4; i++) {
                     const int p0 = (int)((long long)q2 * i / 4), p1 = (int)((long long)q2 * (i + 1) / 4);
-                    fused_inverse_level(coef, ay, az, sym, layer_stride, nlay, deps, minval, prev, out, out_is_f32, ay, az, n0, n1, n2, s, p0, p1);
+                    level(prev, out, out_is_f32, ay, az, n0, n1, n2, p0, p1);
                     cudaEventRecord(sink->ev[i], s);
                     cudaStreamWaitEvent(sink->copy, sink->ev[i], 0);
                     const size_t off = (size_t)(2 * p0) * (size_t)az * esz, len = (size_t)(2 * (p1 - p0)) * (size_t)az * esz;
@@ -446,10 +457,10 @@ void wavelet_inverse(double* coef, double* tmp, double* lllA, double* lllB, void
                 }
                 sink->used = 1;
             } else if (k == 0) {
-                fused_inverse_level(coef, ay, az, sym, layer_stride, nlay, deps, minval, prev, out, out_is_f32, ay, az, n0, n1, n2, s);
+                level(prev, out, out_is_f32, ay, az, n0, n1, n2, -1, -1);
             } else {
                 double* nxt = (k & 1) ? lllA : lllB;
-                fused_inverse_level(coef, ay, az, sym, layer_stride, nlay, deps, minval, prev, nxt, 0, n0, (long long)n0 * n1, n0, n1, n2, s);
+                level(prev, nxt, 0, n0, (long long)n0 * n1, n0, n1, n2, -1, -1);
                 prev = nxt;
             }
         }

@@ -33,7 +33,9 @@ struct FusedFwdArgs {
     double* coef;    long long ay, az;          // coefficient array (array strides)
     double* lll;     long long lsy, lsz;        // compact low-low-low scratch, or null on the last level
     int n0, n1, n2;                             // box extents (even); n2 is the GLOBAL z extent
-    int zoff;                                   // slab mode: global z of plane 0 of src (0 otherwise)
+    int zoff;                                   // slab mode: global z of plane 0 of src incl. halo (0 otherwise)
+    const void* halo_lo; const void* halo_hi;   // slab mode, level 1: the 4 planes below / 3 above live here and src
+    int nown;                                   // holds only the nown own planes (null: src holds halo + own + halo)
     int pair_lo, nl;                            // owned global pairs [pair_lo, pair_lo + nl) (0, n2/2 otherwise)
     int zpairs;                                 // output pairs per z-segment
     int hi_off;                                 // plane offset of the z-high band relative to the z-low band (nl, or the
@@ -123,7 +125,13 @@ __global__ void __launch_bounds__(FTHREADS, 2) fwd_level_fused_kernel(FusedFwdAr
 
     TIN nxt[FSLOTS];
     auto load_plane = [&](int z) {
-        const TIN* __restrict__ plane = src + (long long)(mirror_idx(z, a.n2) - a.zoff) * a.ssz;
+        const int lp = mirror_idx(z, a.n2) - a.zoff;                 // plane counted from the first lower-halo plane
+        const TIN* __restrict__ plane = src + (long long)lp * a.ssz;
+        if (a.halo_lo != nullptr) {                                   // uniform per CTA
+            if (lp < 4) plane = (const TIN*)a.halo_lo + (long long)lp * a.ssz;
+            else if (lp < 4 + a.nown) plane = src + (long long)(lp - 4) * a.ssz;
+            else plane = (const TIN*)a.halo_hi + (long long)(lp - 4 - a.nown) * a.ssz;
+        }
 #pragma unroll
         for (int k = 0; k < FSLOTS; k++) nxt[k] = plane[goff[k]];
     };
@@ -211,14 +219,16 @@ bool fused_forward_supported(int n0, int n1, int n2)
 void fused_forward_level(const void* src, int src_is_f32, long long ssy, long long ssz, double* coef, long long ay,
                          long long az, double* lll, int n0, int n1, int n2, unsigned long long* in_min,
                          unsigned long long* in_max, unsigned long long* out_min, unsigned long long* out_max,
-                         cudaStream_t s, int zoff, int pair_lo, int nl, int hi_off)
+                         cudaStream_t s, int zoff, int pair_lo, int nl, int hi_off, const void* halo_lo, const void* halo_hi)
 {
     FusedFwdArgs a{};
+    a.halo_lo = halo_lo; a.halo_hi = halo_hi;
     a.src = src; a.ssy = ssy; a.ssz = ssz; a.coef = coef; a.ay = ay; a.az = az;
     a.lll = lll; a.lsy = n0 / 2; a.lsz = (long long)(n0 / 2) * (n1 / 2);
     a.n0 = n0; a.n1 = n1; a.n2 = n2;
     a.zoff = zoff; a.pair_lo = pair_lo; a.nl = (nl < 0) ? n2 / 2 : nl;
     a.hi_off = (hi_off < 0) ? a.nl : hi_off;
+    a.nown = 2 * a.nl;
     a.in_min = in_min; a.in_max = in_max; a.out_min = out_min; a.out_max = out_max;
     const int m0 = n0 / 2, m1 = n1 / 2, m2 = a.nl;
     const int gx = (m0 + FPX - 1) / FPX, gy = (m1 + FPY - 1) / FPY;

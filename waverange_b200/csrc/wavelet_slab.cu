@@ -171,7 +171,8 @@ int wavelet_slab_supported(int nx, int ny, int nz, int z0, int nzl, int levels)
 // (nzl + 7) * nx * ny doubles.  halo(user, buf, elem_bytes, plane_elems, nplanes_own, lo, hi) fills the lo planes
 // before and hi planes after the own planes (which start at plane `lo` of buf) from the z-neighbours.
 int wavelet_forward_slab(const void* src, int src_is_f32, double* coef, double* tmp, double* lllA, double* lllB, int nx,
-                         int ny, int nz, int z0, int nzl, int levels, DevState* st, const SlabHooks& hk, cudaStream_t s)
+                         int ny, int nz, int z0, int nzl, int levels, DevState* st, const SlabHooks& hk, cudaStream_t s,
+                         void* halo1)
 {
     const long long ay = nx, az = (long long)nx * ny;
     int n0 = nx, n1 = ny, n2l = nzl, n2g = nz, zg = z0;
@@ -188,24 +189,39 @@ int wavelet_forward_slab(const void* src, int src_is_f32, double* coef, double* 
         const int esz = cur_f32 ? 4 : 8;
         if (fused_forward_supported(n0, n1, n2g) && n2l >= 2) {
             // one pass: raw level input (+ halo planes from the neighbours) -> octants
-            if (cur_base == nullptr) {                                         // level 1: the caller's slab has no halo room
-                cur_base = tmp;
-                cudaMemcpyAsync((char*)tmp + (size_t)kHaloLo * csz * esz, cur, (size_t)n2l * csz * esz, cudaMemcpyDeviceToDevice, s);
+            const size_t pb = (size_t)csz * esz;
+            const void* hlo = nullptr; const void* hhi = nullptr;
+            if (cur_base == nullptr && halo1 != nullptr) {
+                // level 1: the caller's slab is read in place; the neighbours' planes arrive in a buffer of their own
+                // (4 below, then 3 above) -- no copy of the slab just to gain halo room
+                hlo = halo1; hhi = (char*)halo1 + (size_t)kHaloLo * pb;
+                if (hk.nranks > 1) {
+                    int rc = hk.halo(hk.user, cur, (const char*)cur + (size_t)(n2l - kHaloLo) * pb, halo1, (char*)halo1 + (size_t)kHaloLo * pb,
+                                     (unsigned long long)kHaloHi * pb, (unsigned long long)kHaloLo * pb);
+                    if (rc) return rc;
+                }
+                fused_forward_level(cur, cur_f32 ? 1 : 0, csy, csz, coef, ay, az, lll, n0, n1, n2g, &st->fmin_key, &st->fmax_key,
+                                    &st->rmin_key[0], &st->rmax_key[0], s, zg - kHaloLo, zg / 2, n2l / 2, -1, hlo, hhi);
+            } else {
+                if (cur_base == nullptr) {                                     // level 1 without a halo buffer: copy into tmp
+                    cur_base = tmp;
+                    cudaMemcpyAsync((char*)tmp + (size_t)kHaloLo * pb, cur, (size_t)n2l * pb, cudaMemcpyDeviceToDevice, s);
+                }
+                if (hk.nranks > 1) {
+                    int rc = halo_exchange_contiguous(hk, cur_base, pb, n2l, kHaloLo, kHaloHi);
+                    if (rc) return rc;
+                }
+                fused_forward_level(cur_base, cur_f32 ? 1 : 0, csy, csz, coef, ay, az, lll, n0, n1, n2g,
+                                    (k == 1) ? &st->fmin_key : nullptr, (k == 1) ? &st->fmax_key : nullptr, &st->rmin_key[0],
+                                    &st->rmax_key[0], s, zg - kHaloLo, zg / 2, n2l / 2);
             }
-            if (hk.nranks > 1) {
-                int rc = hk.halo(hk.user, cur_base, esz, csz, n2l, kHaloLo, kHaloHi);
-                if (rc) return rc;
-            }
-            fused_forward_level(cur_base, cur_f32 ? 1 : 0, csy, csz, coef, ay, az, lll, n0, n1, n2g,
-                                (k == 1) ? &st->fmin_key : nullptr, (k == 1) ? &st->fmax_key : nullptr, &st->rmin_key[0],
-                                &st->rmax_key[0], s, zg - kHaloLo, zg / 2, n2l / 2);
         } else {
             // x: cur -> coef (local box used as scratch), y: coef -> tmp (compact, own planes after the lower halo)
             const long long tsy = n0, tsz = (long long)n0 * n1;
             wavelet_xy_passes(cur, cur_f32 ? 1 : 0, csy, csz, coef, ay, az, tmp + kHaloLo * tsz, tsy, tsz, n0, n1, n2l,
                               (k == 1) ? &st->fmin_key : nullptr, (k == 1) ? &st->fmax_key : nullptr, s);
             if (hk.nranks > 1) {
-                int rc = hk.halo(hk.user, tmp, 8, tsz, n2l, kHaloLo, kHaloHi);
+                int rc = halo_exchange_contiguous(hk, tmp, (size_t)tsz * 8, n2l, kHaloLo, kHaloHi);
                 if (rc) return rc;
             }
             FwdSlabArgs a{};
@@ -259,9 +275,9 @@ int wavelet_inverse_slab(double* coef, double* tmp, double* lllA, double* lllB, 
             else build_bands_kernel<<<grid, block, 0, s>>>(coef, ay, az, lll, lsy, lsz, q0, q1, n0, n1, nl, lowx, highx, bsy, bsz);
             note_launch(1);
             if (hk.nranks > 1) {
-                int rc = hk.halo(hk.user, lowx, 8, bsz, nl, kHaloInv, kHaloInv);
+                int rc = halo_exchange_contiguous(hk, lowx, (size_t)bsz * 8, nl, kHaloInv, kHaloInv);
                 if (rc) return rc;
-                rc = hk.halo(hk.user, highx, 8, bsz, nl, kHaloInv, kHaloInv);
+                rc = halo_exchange_contiguous(hk, highx, (size_t)bsz * 8, nl, kHaloInv, kHaloInv);
                 if (rc) return rc;
             }
             double* nxt = (k & 1) ? lllA : lllB;
@@ -285,9 +301,9 @@ int wavelet_inverse_slab(double* coef, double* tmp, double* lllA, double* lllB, 
             note_launch(1);
         }
         if (hk.nranks > 1) {
-            int rc = hk.halo(hk.user, lowx, 8, bsz, nl, kHaloInv, kHaloInv);
+            int rc = halo_exchange_contiguous(hk, lowx, (size_t)bsz * 8, nl, kHaloInv, kHaloInv);
             if (rc) return rc;
-            rc = hk.halo(hk.user, highx, 8, bsz, nl, kHaloInv, kHaloInv);
+            rc = halo_exchange_contiguous(hk, highx, (size_t)bsz * 8, nl, kHaloInv, kHaloInv);
             if (rc) return rc;
         }
         InvSlabArgs a{};

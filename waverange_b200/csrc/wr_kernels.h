@@ -21,7 +21,8 @@ struct HostSink { void* host; cudaStream_t copy; cudaEvent_t ev[4]; int used; };
 void wavelet_inverse(double* coef, double* tmp, double* lllA, double* lllB, void* out, int out_is_f32,
                      int nx, int ny, int nz, int levels, cudaStream_t s, const uint8_t* sym = nullptr,
                      unsigned long long layer_stride = 0, unsigned long long chunk_len = 0, unsigned long long pitch = 0,
-                     int nlay = 0, const double* deps = nullptr, const double* minval = nullptr, HostSink* sink = nullptr);
+                     int nlay = 0, const double* deps = nullptr, const double* minval = nullptr, HostSink* sink = nullptr,
+                     double* zb = nullptr, size_t zb_bytes = 0);      // scratch of the two-pass levels (wavelet_inv2.cu)
 
 void wavelet_xy_passes(const void* cur, int cur_is_f32, long long csy, long long csz, double* scratch, long long ay,
                        long long az, double* dst, long long dsy, long long dsz, int n0, int n1, int n2,
@@ -30,19 +31,32 @@ void wavelet_yx_inverse_passes(const double* src, double* scratch, long long ay,
                                void* out, int out_is_f32, long long osy, long long osz, cudaStream_t s);
 
 // ---- wavelet_slab.cu ----------------------------------------------------------------------
-// Collectives of the z-slab partition are injected by the host (NCCL via torch.distributed in
-// production, gloo or an in-process emulation in tests):
-//   halo  : fill `lo` planes before and `hi` planes after the `nown` own planes of buf (own planes start at
-//           plane `lo`) with the adjacent own planes of the z-neighbours; nothing at the domain ends
+// Collectives of the z-slab partition: NCCL issued from the library (slab_comm.cu, wrb_set_comm), or injected by the
+// host as callbacks (wrb_set_slab: gloo in the CPU tests, an in-process emulation of several ranks on one GPU):
+//   halo  : neighbour exchange along z.  Send `down_bytes` from send_down to rank-1 and receive as many into recv_hi
+//           from rank+1; send `up_bytes` from send_up to rank+1 and receive as many into recv_lo from rank-1.  Nothing is
+//           sent or received at the domain ends.  (Forward lifting: up = my last 4 planes, down = my first 3.)
 //   reduce: in-place global MIN over `count` signed 64-bit integers (the codec packs min keys and
-//           complemented max keys into one buffer so a single all_reduce(MIN) serves both)
+//           complemented max keys into one buffer so a single all-reduce(MIN) serves both)
 // Both are enqueued on / ordered with the codec's stream and return 0 on success.
-typedef int (*HaloFn)(void* user, void* d_buf, int elem_bytes, long long plane_elems, int nown, int lo, int hi);
+typedef int (*HaloFn)(void* user, const void* send_down, const void* send_up, void* recv_lo, void* recv_hi,
+                      unsigned long long down_bytes, unsigned long long up_bytes);
 typedef int (*ReduceFn)(void* user, long long* d_buf, int count);
 struct SlabHooks { int rank = 0, nranks = 1; HaloFn halo = nullptr; ReduceFn reduce = nullptr; void* user = nullptr; };
+// halo exchange of a buffer that holds `lo` halo planes, `nown` own planes and `hi` halo planes back to back
+inline int halo_exchange_contiguous(const SlabHooks& hk, void* buf, size_t plane_bytes, int nown, int lo, int hi)
+{
+    char* b = (char*)buf;
+    return hk.halo(hk.user, b + (size_t)lo * plane_bytes, b + (size_t)nown * plane_bytes, b,
+                   b + (size_t)(lo + nown) * plane_bytes, (unsigned long long)hi * plane_bytes,
+                   (unsigned long long)lo * plane_bytes);
+}
 int wavelet_slab_supported(int nx, int ny, int nz, int z0, int nzl, int levels);
+// halo1: room for 7 planes of the level-1 input (nx*ny elements each, the field's own type): its z-neighbour planes
+// arrive there, the slab itself is read in place
 int wavelet_forward_slab(const void* src, int src_is_f32, double* coef, double* tmp, double* lllA, double* lllB, int nx,
-                         int ny, int nz, int z0, int nzl, int levels, DevState* st, const SlabHooks& hk, cudaStream_t s);
+                         int ny, int nz, int z0, int nzl, int levels, DevState* st, const SlabHooks& hk, cudaStream_t s,
+                         void* halo1 = nullptr);
 // sym != null (flat symbol planes of the rank-local array, layer l at sym + l*lstride): the band buffers are built
 // straight from the symbols -- no dequantise pass, coef untouched; needs wavelet_inverse_slab_fused_ok()
 int wavelet_inverse_slab(double* coef, double* tmp, double* lllA, double* lllB, double* ext, void* out, int out_is_f32,
@@ -56,7 +70,8 @@ bool fused_forward_supported(int n0, int n1, int n2);
 void fused_forward_level(const void* src, int src_is_f32, long long ssy, long long ssz, double* coef, long long ay,
                          long long az, double* lll, int n0, int n1, int n2, unsigned long long* in_min,
                          unsigned long long* in_max, unsigned long long* out_min, unsigned long long* out_max,
-                         cudaStream_t s, int zoff = 0, int pair_lo = 0, int nl = -1, int hi_off = -1);
+                         cudaStream_t s, int zoff = 0, int pair_lo = 0, int nl = -1, int hi_off = -1,
+                         const void* halo_lo = nullptr, const void* halo_hi = nullptr);   // slab mode: halo planes apart from src
 
 // ---- wavelet_inv_fused.cu -----------------------------------------------------------------
 bool fused_inverse_supported(int n0, int n1, int n2);
@@ -69,6 +84,15 @@ void fused_inverse_level(const double* coef, long long ay, long long az, const u
 void fused_inverse_level_bands(const double* lowb, const double* highb, long long bsy, long long bsz, int halo, int pair_lo,
                                int nown, void* dst, int dst_is_f32, long long dsy, long long dsz, int n0, int n1, int n2g,
                                cudaStream_t s);
+
+// ---- wavelet_inv2.cu ----------------------------------------------------------------------
+// two-pass level (streaming z pass + TMA-staged y/x tile pass); same shapes as fused_inverse_supported()
+bool inverse_two_pass_enabled();
+size_t inverse_two_pass_scratch_bytes(int nx, int ny, int nz);
+void inverse_level_two_pass(const double* coef, long long ay, long long az, const uint8_t* sym, unsigned long long lstride,
+                            int nlay, const double* deps, const double* minval, const double* lll, void* dst,
+                            int dst_is_f32, long long dsy, long long dsz, int n0, int n1, int n2, double* zb, size_t zb_bytes,
+                            cudaStream_t s, int seg_lo = -1, int seg_hi = -1);
 
 // ---- quant.cu -----------------------------------------------------------------------------
 // Geometry of the chunked symbol container of one layer.

@@ -92,17 +92,21 @@ class DistHooks:
         self.error = None
         self.halo_bytes = 0
 
-    def halo_planes(self, t, nown, lo, hi):
-        """t: [lo + nown + hi, plane_bytes] view of the halo'd buffer.  The rank above needs my last `lo`
-        planes, the rank below my first `hi` planes; nothing happens at the domain ends."""
+    def halo_exchange(self, send_down, send_up, recv_lo, recv_hi):
+        """uint8 tensors (or None for an empty transfer): my first planes go down to rank-1 and arrive there as its
+        upper halo, my last planes go up to rank+1 as its lower halo; nothing happens at the domain ends."""
         dist = self.dist
         ops = []
         if self.rank + 1 < self.world:
-            ops.append(dist.P2POp(dist.isend, t[nown:nown + lo], self.rank + 1, self.group))
-            ops.append(dist.P2POp(dist.irecv, t[lo + nown:lo + nown + hi], self.rank + 1, self.group))
+            if send_up is not None:
+                ops.append(dist.P2POp(dist.isend, send_up, self.rank + 1, self.group))
+            if recv_hi is not None:
+                ops.append(dist.P2POp(dist.irecv, recv_hi, self.rank + 1, self.group))
         if self.rank > 0:
-            ops.append(dist.P2POp(dist.isend, t[lo:lo + hi], self.rank - 1, self.group))
-            ops.append(dist.P2POp(dist.irecv, t[0:lo], self.rank - 1, self.group))
+            if send_down is not None:
+                ops.append(dist.P2POp(dist.isend, send_down, self.rank - 1, self.group))
+            if recv_lo is not None:
+                ops.append(dist.P2POp(dist.irecv, recv_lo, self.rank - 1, self.group))
         if ops:
             for r in dist.batch_isend_irecv(ops):
                 r.wait()
@@ -123,11 +127,10 @@ class DistHooks:
         self.dist.all_gather(parts, t, group=self.group)
         return self.torch.stack(parts)
 
-    def _halo(self, user, buf, elem_bytes, plane_elems, nown, lo, hi):
+    def _halo(self, user, send_down, send_up, recv_lo, recv_hi, down_bytes, up_bytes):
         try:
-            pb = elem_bytes * plane_elems
-            t = _tensor_from_ptr(self.torch, buf, (lo + nown + hi) * pb, self.cuda).view(lo + nown + hi, pb)
-            self.halo_planes(t, nown, lo, hi)
+            t = lambda ptr, n: _tensor_from_ptr(self.torch, ptr, n, self.cuda) if n else None
+            self.halo_exchange(t(send_down, down_bytes), t(send_up, up_bytes), t(recv_lo, up_bytes), t(recv_hi, down_bytes))
             return 0
         except Exception as e:          # never let an exception cross the C boundary
             self.error = e
@@ -156,16 +159,15 @@ class LocalGroup:
     def _make(self, rank):
         torch, world = self.torch, self.world
 
-        def halo(user, buf, elem_bytes, plane_elems, nown, lo, hi):
-            pb = elem_bytes * plane_elems
-            t = _tensor_from_ptr(torch, buf, (lo + nown + hi) * pb, True).view(lo + nown + hi, pb)
+        def halo(user, send_down, send_up, recv_lo, recv_hi, down_bytes, up_bytes):
+            t = lambda ptr, n: _tensor_from_ptr(torch, ptr, n, True) if n else None
             torch.cuda.synchronize()
-            self.slots[rank] = t
+            self.slots[rank] = (t(send_down, down_bytes), t(send_up, up_bytes))
             self.barrier.wait()
-            if rank + 1 < world:
-                t[lo + nown:lo + nown + hi].copy_(self.slots[rank + 1][lo:lo + hi])
-            if rank > 0:
-                t[0:lo].copy_(self.slots[rank - 1][nown:nown + lo])
+            if rank + 1 < world and down_bytes:
+                t(recv_hi, down_bytes).copy_(self.slots[rank + 1][0])
+            if rank > 0 and up_bytes:
+                t(recv_lo, up_bytes).copy_(self.slots[rank - 1][1])
             torch.cuda.synchronize()
             self.barrier.wait()
             return 0
