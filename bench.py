@@ -200,7 +200,8 @@ def workload_config(n, world):
     else:
         shape = "%dx%dx%d" % (n, n, n * world)
         fields = ("one %dx%dx%d field, z-slab partitioned over %d GPUs (%d planes each): NCCL halo exchange per level "
-                  "(4 planes below / 3 above), all-reduce of the extrema per layer" % (n, n, n * world, world, n))
+                  "(4 planes below / 3 above), all-reduce of the extrema per layer, symbol exchange over NVLink into the "
+                  "global wavelet-space order (every chunk stream = the single-GPU run's)" % (n, n, n * world, world, n))
     tag = " (BASELINE.json configs[1])" if (n == N_FIELD and world == 1) else \
           (" (configs[1]'s field extended along z, weak scaling; configs[3]'s partition)" if n == N_FIELD else " (profiling size)")
     return {"workload": "%s float32 turbulence-like field, tol 1e-4%s" % (shape, tag),
@@ -288,11 +289,11 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.current_stream()
     codec = api.Codec(device=local_rank, stream=stream.cuda_stream)
     codec.set_timing(True)
-    hooks = None
     if slab_mode:
+        # every collective is issued by the library (NCCL from C++); torch.distributed only carries the 128-byte NCCL id.
+        # The ranks code the GLOBAL symbol order: each chunk stream is the one a single GPU (and the reference) produces.
         from waverange_b200 import slab
-        hooks = slab.DistHooks(torch, dist, cuda=True)
-        codec.set_slab(rank, world, hooks.halo_cb, hooks.reduce_cb)
+        slab.set_comm_from_dist(codec, torch, dist, dev)
 
     def encode_dev(src_ptr, dst_ptr):
         if slab_mode:
@@ -381,6 +382,28 @@ def run_ours(args, rank, world, local_rank):
     if e2e_ms:
         assert np.array_equal(np_rec.ravel()[:4096], recon[:4096].cpu().numpy())
 
+    # ---- N > 1: the chunk streams of all ranks against a single-GPU encode of the same (whole) field on rank 0 --------
+    streams_equal = None
+    if slab_mode and not args.no_check:
+        from waverange_b200 import slab
+        crcs = slab.stream_crcs(h, blob[:h.ntot_enc].cpu().numpy())
+        allc = [None] * world
+        dist.gather_object((crcs, list(h.deps_vec), list(h.minval_vec), int(h.nlay)), allc if rank == 0 else None, dst=0)
+        if rank == 0:
+            whole = synth_field(torch, n, 1234, dev, torch.float32, nz_total=nz_total, z0=0, nzl=nz_total)
+            c1 = api.Codec(device=local_rank, stream=stream.cuda_stream)
+            cap1 = whole.numel() * 3 + (1 << 20)
+            blob1 = torch.empty(cap1 + 64, dtype=torch.uint8, device=dev)
+            h1 = c1.encode_device(whole.data_ptr(), api.F32, nx, ny, nz_total, TOL, blob1.data_ptr(), cap1)
+            want = slab.stream_crcs(h1, blob1[:h1.ntot_enc].cpu().numpy())
+            got = [[x for r in range(world) for x in allc[r][0][l]] for l in range(int(h1.nlay))] if all(a[3] == h1.nlay for a in allc) else None
+            streams_equal = {"chunk_streams_equal_single_gpu": bool(got == want),
+                             "header_doubles_equal_single_gpu": bool(all(a[1] == list(h1.deps_vec) and a[2] == list(h1.minval_vec) for a in allc)),
+                             "chunk_streams": sum(len(x) for x in want), "single_gpu_bytes": int(h1.ntot_enc)}
+            c1.close()
+            del whole, blob1
+        dist.barrier()
+
     # ---- max over ranks ------------------------------------------------------------------------
     vals = torch.tensor([step_ms, statistics.mean(enc_ms), statistics.mean(dec_ms), e2e_step], device=dev, dtype=torch.float64)
     if world > 1:
@@ -458,6 +481,9 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "host_wall_ms_per_step": wall_ms,
     }
+    if streams_equal is not None:
+        line["global_order_check"] = streams_equal
+        line["nccl_rank0"] = codec.comm_counters()
     if cpu is not None:
         line["cpu_baseline"] = cpu
         line["ratio_check"] = ratio_check
@@ -625,6 +651,7 @@ def main():
     ap.add_argument("--size", type=int, default=N_FIELD, help="field edge (default 512 = BASELINE configs[1]; other sizes are for profiling only)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (profiling only)")
     ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (C1, C3, C5 beside the headline)")
+    ap.add_argument("--no-check", action="store_true", help="N > 1: skip the comparison of the chunk streams with a single-GPU encode")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

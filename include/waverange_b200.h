@@ -128,6 +128,31 @@ typedef int (*wrb_halo_fn)(void* user, const void* send_down, const void* send_u
                            unsigned long long down_bytes, unsigned long long up_bytes);
 typedef int (*wrb_reduce_fn)(void* user, long long* d_buf, int count);
 int wrb_set_slab(wrb_codec* c, int rank, int nranks, wrb_halo_fn halo, wrb_reduce_fn reduce, void* user);
+/* NCCL transport inside the library (libnccl.so.2 is loaded at run time; nothing to link).  Rank 0 obtains an id,
+ * the 128 bytes reach the other ranks by any means (MPI_Bcast, a file, torch.distributed ...), and every rank -- one
+ * process per GPU, its device current -- calls wrb_set_comm: ncclCommInitRank, halo exchange = grouped ncclSend /
+ * ncclRecv, reductions = ncclAllReduce, all on the codec's stream.  It also switches on the GLOBAL symbol order:
+ * before coding, the ranks exchange the 1-byte symbols so that rank r codes the chunks [r*nchunks/n, (r+1)*nchunks/n)
+ * of the symbol sequence of the WHOLE field in the reference's order (wrappers.cpp:384-412 on the array that
+ * waveletcdf97_3d.c:128-135,256-263 de-interleaves) -- every chunk stream is then byte for byte the one a single
+ * GPU, and the reference's range_encode on that sub-array, produce.  The exchange reads the peers' symbol planes
+ * directly over NVLink (CUDA IPC mappings, set up once per geometry through an ncclAllGather of the handles).
+ * Each rank's data_enc is a self-contained WRCK container of its run of chunks; hdr->nlay / deps_vec / minval_vec
+ * are identical on all ranks.  Requires equal slabs in rank order (z0 == rank * nzl). */
+int wrb_comm_unique_id(unsigned char id[128]);
+int wrb_set_comm(wrb_codec* c, int rank, int nranks, const unsigned char id[128]);
+/* Several ranks emulated in ONE process on one device (tests): with the callbacks of wrb_set_slab, the codecs of all
+ * ranks in rank order; switches on the global symbol order (the peers' windows are then plain pointers). */
+int wrb_set_slab_peers(wrb_codec* c, wrb_codec* const* peers, int n);
+/* 0: every rank codes its own coefficients in rank-local order (no symbol exchange); 1: the global order */
+int wrb_set_slab_order(wrb_codec* c, int global);
+/* NCCL transport counters since wrb_set_comm: halo bytes received, neighbour exchanges, all-reduces */
+int wrb_comm_counters(const wrb_codec* c, unsigned long long out[3]);
+/* The partition's index map (host arithmetic, for tests and tools): global wavelet-space plane of local plane p of
+ * `rank` for an (x, y) position that leaves the low box at level `reg` (levels + 1: the coarsest box); and the chunks
+ * [c0, c1) of the global sequence that `rank` codes. */
+int wrb_slab_order_plane(int nx, int ny, int nz, int nranks, int levels, int rank, int p, int reg);
+int wrb_slab_chunk_range(int nx, int ny, int nz, int nranks, unsigned long chunk_len, int rank, unsigned long* c0, unsigned long* c1);
 int wrb_encode_slab_device(wrb_codec* c, const void* d_field_slab, int dtype, int nx, int ny, int nz, int z0, int nzl,
                            int wtflag, double tolrel, wrb_header* hdr, unsigned char* d_data_enc, unsigned long cap);
 int wrb_decode_slab_device(wrb_codec* c, void* d_field_slab_out, int dtype, int nx, int ny, int nz, int z0, int nzl,

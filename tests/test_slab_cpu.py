@@ -89,18 +89,6 @@ def _worker(rank, world, port, q):
     got = buf.view(np.uint64)
     kmin, kmax = got[:3] ^ flip, ~(got[3:] ^ flip)
     ok &= np.array_equal(kmin, dkey_np(allv.min(axis=0))) and np.array_equal(kmax, dkey_np(allv.max(axis=0)))
-    # ---- symbol exchange of the global-order mode: all_gather of the rank-local planes, gather of the rank's run ----
-    nz, ny, nx = 64, 16, 24
-    nzl = nz // world
-    G = np.random.default_rng(9).integers(0, 256, size=(nz, ny, nx), dtype=np.uint8)      # same on both ranks
-    ys, xs = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
-    gz = slab.local_to_global_z(nx, ny, nz, rank * nzl, nzl)
-    mine = torch.from_numpy(G[gz, ys[None], xs[None]].reshape(-1).copy())
-    go = slab.GlobalOrder(torch, nx, ny, nz, rank, world, torch.device("cpu"), chunk=997)
-    allsym = hk.all_gather_u8(mine)
-    ok &= tuple(allsym.shape) == (world, mine.numel())
-    run = go.gather_run(allsym).numpy()
-    ok &= np.array_equal(run, G.reshape(-1)[go.j0[rank]:go.j0[rank + 1]])
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
@@ -119,38 +107,42 @@ def test_halo_exchange_and_key_reduction_gloo_world2():
     assert res == {0: True, 1: True}
 
 
-@pytest.mark.parametrize("world", [1, 2, 4])
-@pytest.mark.parametrize("shape", [(128, 32, 48), (64, 40, 16)])
-def test_global_order_maps(world, shape):
-    """GlobalOrder (compact region tables) against local_to_global_z: the run a rank gathers is its slice of the
-    global wavelet-space sequence, and scattering the runs back gives every rank its local planes"""
-    import torch
-    from waverange_b200 import slab
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+@pytest.mark.parametrize("shape", [(128, 32, 48), (256, 40, 16), (512, 18, 22)])
+def test_library_index_map_matches_the_restatement(world, shape, product_lib):
+    """The closed-form index map of the library (csrc/slab_order.cu, through wrb_slab_order_plane) against the
+    independent restatement local_to_global_z(), which follows the in-box de-interleave of the reference
+    (waveletcdf97_3d.c:128-135,256-263) level by level; and the chunk ranges of the ranks."""
+    from waverange_b200 import api, slab
     nz, ny, nx = shape
-    if (nz // world) % 32 != 0:
+    if (nz // world) % 32 != 0 or nz % world:
         pytest.skip("partition rule")
     nzl = nz // world
-    rng = np.random.default_rng(world + nx)
-    G = rng.integers(0, 256, size=(nz, ny, nx), dtype=np.uint8)          # symbols in global wavelet-space order
-    ys, xs = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
-    local = []
+    reg = np.array([[slab.region_of(nx, ny, x, y) for x in range(nx)] for y in range(ny)])
     for r in range(world):
         gz = slab.local_to_global_z(nx, ny, nz, r * nzl, nzl)
-        local.append(G[gz, ys[None], xs[None]].reshape(-1))
-    allsym = torch.from_numpy(np.stack(local))
-    gos = [slab.GlobalOrder(torch, nx, ny, nz, r, world, torch.device("cpu"), chunk=997) for r in range(world)]
-    runs = []
-    for r, go in enumerate(gos):
-        run = go.gather_run(allsym).numpy()
-        assert np.array_equal(run, G.reshape(-1)[go.j0[r]:go.j0[r + 1]])
-        runs.append(run)
-    assert sum(len(x) for x in runs) == G.size and gos[0].j0[-1] == G.size
-    pitch = max(len(x) for x in runs)
-    allruns = torch.zeros((world, pitch), dtype=torch.uint8)
-    for r, x in enumerate(runs):
-        allruns[r, :len(x)] = torch.from_numpy(x)
-    for r, go in enumerate(gos):
-        assert np.array_equal(go.scatter_local(allruns, pitch).numpy(), local[r])
+        for k in range(1, 6):
+            ys, xs = np.nonzero(reg == k)
+            if ys.size == 0:
+                continue
+            for p in range(nzl):
+                w = api.slab_order_plane(nx, ny, nz, world, 4, r, p, k)
+                assert (gz[p, ys, xs] == w).all(), (r, p, k)
+    nch, cb = slab.chunk_ranges(nx * ny * nz, world, 997)
+    for r in range(world):
+        assert api.slab_chunk_range(nx, ny, nz, world, 997, r) == (cb[r], cb[r + 1])
+
+
+def test_join_pieces_gives_an_ordinary_container():
+    """slab.join_pieces: the ranks' chunk streams, in rank order, as one container the parser (and the decoder) reads"""
+    from waverange_b200 import api, slab
+    rng = np.random.default_rng(1)
+    streams = [[bytes(rng.integers(0, 256, n, dtype=np.uint8)) for n in ns] for ns in ((9, 600), (17,), (5, 5, 80))]
+    h = api.Header()
+    h.nlay = 1
+    hj, blob = slab.join_pieces(h, [[s] for s in streams], 6 * 59999 - 3)
+    cl, got = api.parse_container(np.frombuffer(blob, dtype=np.uint8))
+    assert cl == 59999 and got == [x for s in streams for x in s] and hj.ntot_enc == len(blob) == hj.len_enc_vec[0]
 
 
 def test_wrck_container_helper_matches_the_parser():

@@ -104,61 +104,75 @@ def test_slab_rejects_bad_partition(codec, torch_cuda):
         codec.encode_slab_device(x.data_ptr(), F64, 8, 8, 96, 0, 48, 1e-3, out.data_ptr(), 1 << 20)
 
 
-@pytest.mark.parametrize("world", [1, 2, 4])
-@pytest.mark.parametrize("shape,tol", [((128, 64, 96), 1e-5), ((128, 48, 40), 1e-9)])
-def test_slab_global_symbol_order(torch_cuda, oracle, world, shape, tol):
-    """with the symbol exchange (slab.encode_global) the ranks code whole chunks of the GLOBAL
-    sequence: every chunk stream equals the oracle's range_encode of that chunk (= the single-GPU run's), the joined
-    pieces are an ordinary container that the single-GPU decoder reads, and decode_global gives the reference's
-    reconstruction"""
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("shape,tol,dtype", [((128, 64, 96), 1e-5, F64), ((128, 48, 40), 1e-9, F64), ((256, 40, 72), 1e-4, F32),
+                                             ((128, 33, 50), 1e-6, F64)])
+def test_slab_global_symbol_order(torch_cuda, oracle, world, shape, tol, dtype):
+    """SURVEY.md section 8e(3), inside the library (csrc/slab_order.cu): the ranks exchange the symbols and code whole
+    chunks of the GLOBAL sequence.  Every chunk stream equals the oracle's range_encode of that chunk (= the single-GPU
+    run's), the joined pieces are an ordinary container that the single-GPU decoder reads, and the slab decoder (run
+    decode + exchange back + inverse) gives the reference's reconstruction.  Two rounds on the same handles: the
+    exchange windows and the peers' pointers are reused."""
     torch = torch_cuda
     from waverange_b200 import api, slab
     nz, ny, nx = shape
     f = oracle.probe_field(shape, seed=77 + world, nm=16)
+    if dtype == F32:
+        f = f.astype(np.float32).astype(np.float64)
     want = oracle.encode(f, tol, chunk_len=slab.CHUNK)
     hw = want["header"]
     parts = slab.partition(nz, world)
     grp = slab.LocalGroup(torch, world)
+    codecs = [api.Codec(device=0) for _ in range(world)]
 
     def rank_fn(r, halo_cb, reduce_cb):
         z0, nzl = parts[r]
-        c = api.Codec(device=0)
+        c = codecs[r]
         c.set_slab(r, world, halo_cb, reduce_cb)
-        hooks = grp.rank_hooks(r)
-        go = slab.GlobalOrder(torch, nx, ny, nz, r, world, torch.device("cuda", 0))
-        d_f = torch.from_numpy(np.ascontiguousarray(f[z0:z0 + nzl])).cuda()
-        h, pieces = slab.encode_global(torch, c, hooks, go, d_f.data_ptr(), F64, tol)
-        rec = torch.zeros(nzl * ny * nx, dtype=torch.float64, device="cuda")
-        slab.decode_global(torch, c, hooks, go, h, pieces, rec.data_ptr(), F64)
-        out = dict(h=h, pieces=[(list(l), s.cpu().numpy().tobytes()) for l, s in pieces], rec=rec.cpu().numpy().reshape(nzl, ny, nx))
-        c.close()
+        c.set_slab_peers(codecs)
+        loc = np.ascontiguousarray(f[z0:z0 + nzl])
+        d_f = torch.from_numpy(loc.astype(np.float32) if dtype == F32 else loc).cuda()
+        _, cap = api.setup_wr(nx, ny, nzl)
+        out = None
+        for rnd in range(2):
+            blob = torch.zeros(cap + 64, dtype=torch.uint8, device="cuda")
+            h = c.encode_slab_device(d_f.data_ptr(), dtype, nx, ny, nz, z0, nzl, tol, blob.data_ptr(), cap)
+            rec = torch.zeros(nzl * ny * nx, dtype=torch.float32 if dtype == F32 else torch.float64, device="cuda")
+            c.decode_slab_device(rec.data_ptr(), dtype, nx, ny, nz, z0, nzl, h, blob.data_ptr())
+            cur = dict(h=h, streams=slab.piece_streams(h, blob[:h.ntot_enc].cpu().numpy()), rec=rec.cpu().numpy().reshape(nzl, ny, nx))
+            if out is not None:
+                assert cur["streams"] == out["streams"] and bits_equal(cur["rec"], out["rec"])
+            out = cur
         return out
 
     res = grp.run(rank_fn)
+    for c in codecs:
+        c.close()
     h = res[0]["h"]
-    assert h.nlay == hw.nlay and list(h.deps_vec)[:h.nlay] == list(hw.deps)[:h.nlay]
+    for r in res:
+        assert r["h"].nlay == hw.nlay and bits_equal(np.array(list(r["h"].deps_vec)), np.array(list(hw.deps)))
+        assert bits_equal(np.array(list(r["h"].minval_vec)), np.array(list(hw.minval)))
     # the chunk streams of all ranks, in rank order, are the oracle's chunk streams
-    blob = b""
     woff = 0
     for l in range(h.nlay):
-        lens = [n for r in res for n in r["pieces"][l][0]]
-        streams = b"".join(r["pieces"][l][1] for r in res)
-        assert lens == [int(x) for x in want["chunk_lens"][l]]
-        n = sum(lens)
-        assert streams == want["data"][woff:woff + n].tobytes(), "layer %d" % l
+        streams = [s for r in res for s in r["streams"][l]]
+        assert [len(s) for s in streams] == [int(x) for x in want["chunk_lens"][l]]
+        n = sum(len(s) for s in streams)
+        assert b"".join(streams) == want["data"][woff:woff + n].tobytes(), "layer %d" % l
         woff += n
-        layer = slab.wrck_container(slab.CHUNK if f.size > slab.CHUNK else f.size, f.size, lens, streams)
-        h.len_enc_vec[l] = len(layer)
-        blob += layer
-    h.ntot_enc = len(blob)
-    # ... and the joined pieces are a container the plain single-GPU decoder reads
+    # ... the joined pieces are a container the plain single-GPU decoder reads
+    hj, blob = slab.join_pieces(h, [r["streams"] for r in res], f.size)
     c = api.Codec(device=0)
     d_blob = torch.zeros(len(blob) + 64, dtype=torch.uint8, device="cuda")
     d_blob[:len(blob)] = torch.from_numpy(np.frombuffer(blob, dtype=np.uint8).copy()).cuda()
     rec1 = torch.zeros(f.size, dtype=torch.float64, device="cuda")
-    c.decode_device(rec1.data_ptr(), F64, nx, ny, nz, h, d_blob.data_ptr())
+    c.decode_device(rec1.data_ptr(), F64, nx, ny, nz, hj, d_blob.data_ptr())
     c.close()
     whole = oracle.encode(f, tol)
     want_rec = oracle.decode(shape, whole["header"], whole["data"])
     assert bits_equal(rec1.cpu().numpy().reshape(shape), want_rec)
-    assert bits_equal(np.concatenate([r["rec"] for r in res], axis=0), want_rec)
+    got = np.concatenate([r["rec"] for r in res], axis=0)
+    assert bits_equal(got, want_rec.astype(np.float32) if dtype == F32 else want_rec)
+    # compression ratio: the pieces together within 1 % of the reference's single-stream layers (plus the tables of
+    # chunks that a small field cannot amortise)
+    assert sum(r["h"].ntot_enc for r in res) <= 1.01 * whole["header"].ntot_enc + 100 * len([s for r in res for l in r["streams"] for s in l])

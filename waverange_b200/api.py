@@ -73,7 +73,8 @@ _lib = None
 # every symbol include/waverange_b200.h and include/waverange.h declare
 EXPORTS = ["wrb_create", "wrb_destroy", "wrb_last_error", "wrb_set_stream", "wrb_set_chunk_blocks", "wrb_set_seek_points",
            "wrb_set_local_cutoff", "wrb_launch_count", "wrb_trim", "wrb_current_device", "wrb_layer_guess_misses", "wrb_setup", "wrb_encode_device", "wrb_decode_device",
-           "wrb_encode_host", "wrb_decode_host", "wrb_decode_symbols_device", "wrb_decode_slab_symbols_device", "wrb_set_slab", "wrb_encode_slab_device", "wrb_decode_slab_device", "wrb_quantise_slab_device", "wrb_wavelet3d_device", "wrb_quantise_device",
+           "wrb_encode_host", "wrb_decode_host", "wrb_decode_symbols_device", "wrb_decode_slab_symbols_device", "wrb_set_slab", "wrb_comm_unique_id", "wrb_set_comm",
+           "wrb_set_slab_peers", "wrb_set_slab_order", "wrb_comm_counters", "wrb_slab_order_plane", "wrb_slab_chunk_range", "wrb_encode_slab_device", "wrb_decode_slab_device", "wrb_quantise_slab_device", "wrb_wavelet3d_device", "wrb_quantise_device",
            "wrb_range_encode_device", "wrb_range_decode_device", "wrb_ind_p2w_3d", "wrb_set_timing",
            "wrb_last_stage_ms",
            "wrb_wrh_begin", "wrb_wrh_append", "wrb_wrh_read", "wrb_file_encode", "wrb_file_decode", "wrb_file_last_error",
@@ -114,6 +115,13 @@ def lib():
     L.wrb_encode_host.argtypes = [vp, vp, i, i, i, i, i, d, H, vp, ul]
     L.wrb_decode_host.argtypes = [vp, vp, i, i, i, i, H, vp]
     L.wrb_set_slab.argtypes = [vp, i, i, HALO_FN, REDUCE_FN, vp]
+    L.wrb_comm_unique_id.argtypes = [C.c_char_p]
+    L.wrb_set_comm.argtypes = [vp, i, i, C.c_char_p]
+    L.wrb_set_slab_peers.argtypes = [vp, C.POINTER(vp), i]
+    L.wrb_set_slab_order.argtypes = [vp, i]
+    L.wrb_comm_counters.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+    L.wrb_slab_order_plane.argtypes = [i] * 8
+    L.wrb_slab_chunk_range.argtypes = [i, i, i, i, ul, i, C.POINTER(ul), C.POINTER(ul)]
     L.wrb_encode_slab_device.argtypes = [vp, vp, i, i, i, i, i, i, i, d, H, vp, ul]
     L.wrb_decode_slab_device.argtypes = [vp, vp, i, i, i, i, i, i, H, vp]
     L.wrb_decode_symbols_device.argtypes = [vp, vp, i, i, i, i, H, vp]
@@ -165,6 +173,26 @@ def setup_wr(nx, ny, nz):
 
 def _np_ptr(a, t):
     return a.ctypes.data_as(C.POINTER(t))
+
+
+def comm_unique_id():
+    """128 bytes from ncclGetUniqueId (rank 0); hand them to every rank's Codec.set_comm"""
+    buf = C.create_string_buffer(128)
+    rc = lib().wrb_comm_unique_id(buf)
+    if rc != 0:
+        raise WaveRangeError("wrb_comm_unique_id failed (%d): NCCL not loadable?" % rc)
+    return buf.raw
+
+
+def slab_order_plane(nx, ny, nz, nranks, levels, rank, p, reg):
+    return lib().wrb_slab_order_plane(nx, ny, nz, nranks, levels, rank, p, reg)
+
+
+def slab_chunk_range(nx, ny, nz, nranks, chunk_len, rank):
+    c0, c1 = C.c_ulong(), C.c_ulong()
+    if lib().wrb_slab_chunk_range(nx, ny, nz, nranks, chunk_len, rank, C.byref(c0), C.byref(c1)) != 0:
+        raise WaveRangeError("bad partition")
+    return c0.value, c1.value
 
 
 # ---- generic .wrh / .wrb files (include/waverange_files.h) -------------------------------------
@@ -405,6 +433,24 @@ class Codec:
     def set_slab(self, rank, nranks, halo_cb, reduce_cb):
         """halo_cb / reduce_cb: HALO_FN / REDUCE_FN instances (kept alive by the caller)"""
         self._ck(self.L.wrb_set_slab(self.h, rank, nranks, halo_cb, reduce_cb, None))
+
+    def set_comm(self, rank, nranks, unique_id):
+        """NCCL transport inside the library + the global symbol order (include/waverange_b200.h wrb_set_comm)"""
+        assert len(unique_id) == 128
+        self._ck(self.L.wrb_set_comm(self.h, rank, nranks, unique_id))
+
+    def set_slab_peers(self, codecs):
+        """ranks emulated in one process: the Codec objects of all ranks in rank order"""
+        arr = (C.c_void_p * max(1, len(codecs)))(*[c.h.value for c in codecs])
+        self._ck(self.L.wrb_set_slab_peers(self.h, arr, len(codecs)))
+
+    def set_slab_order(self, global_order):
+        self._ck(self.L.wrb_set_slab_order(self.h, int(bool(global_order))))
+
+    def comm_counters(self):
+        a = (C.c_ulonglong * 3)()
+        self._ck(self.L.wrb_comm_counters(self.h, a))
+        return dict(halo_bytes=a[0], halo_calls=a[1], reduce_calls=a[2])
 
     def encode_slab_device(self, d_field, dtype, nx, ny, nz, z0, nzl, tol, d_out, cap, wtflag=1):
         h = Header()

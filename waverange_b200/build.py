@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwaverange_b200.so")
-SOURCES = ["codec.cu", "wavelet.cu", "wavelet_fused.cu", "wavelet_inv_fused.cu", "wavelet_inv2.cu", "wavelet_slab.cu", "quant.cu", "rangecoder.cu", "compat.cpp", "wrfile.cpp", "mssgfile.cpp"]
-HEADERS = ["wr_common.cuh", "wr_kernels.h", "wavelet_pairs.cuh", "../../include/waverange_b200.h", "../../include/waverange.h",
+SOURCES = ["codec.cu", "wavelet.cu", "wavelet_fused.cu", "wavelet_inv_fused.cu", "wavelet_inv2.cu", "wavelet_slab.cu", "slab_comm.cu", "slab_order.cu", "quant.cu", "rangecoder.cu", "compat.cpp", "wrfile.cpp", "mssgfile.cpp"]
+HEADERS = ["wr_common.cuh", "wr_kernels.h", "slab_comm.h", "wavelet_pairs.cuh", "../../include/waverange_b200.h", "../../include/waverange.h",
            "../../include/waverange_files.h", "../../include/waverange_mssg.h", "cli/wrenc.cpp", "cli/wrdec.cpp",
            "cli/wrmssgenc.cpp", "cli/wrmssgdec.cpp"]
 BIN = os.path.join(HERE, "bin")

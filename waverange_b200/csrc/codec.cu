@@ -15,8 +15,10 @@
 #include <new>
 #include <thread>
 #include <vector>
+#include <algorithm>
 #include "wr_common.cuh"
 #include "wr_kernels.h"
+#include "slab_comm.h"
 #include "../../include/waverange_b200.h"
 
 namespace wrb {
@@ -65,6 +67,18 @@ struct wrb_codec {
     cudaEvent_t piece_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     HostSource* src_pipe = nullptr;   // set by wrb_encode_host for the duration of one call: the field arrives in z-pieces
     unsigned long long guess_misses = 0;      // encodes that had to be repeated with all 8 layers (layer_guess)
+    // ---- z-slab partition: transport and the global symbol order (slab_comm.cu, slab_order.cu) ----
+    SlabComm* comm = nullptr;                 // NCCL transport created by wrb_set_comm (else: callbacks of wrb_set_slab)
+    int order_global = 0;                     // code the GLOBAL wavelet-space symbol order (needs the peers' windows)
+    DevBuf xsym, xrun, halo1, ipcbuf;         // exchange windows (local symbol planes / my decoded run), level-1 halo planes
+    size_t xsym_stride = 0, xrun_stride = 0;  // bytes between layers inside the windows
+    int win_layers = 0;                       // layers the windows hold
+    unsigned long long win_key[4] = {0, 0, 0, 0};   // geometry the peers' pointers belong to
+    bool peers_ok = false;
+    PeerPtrs peer_xsym{}, peer_xrun{};
+    void* ipc_open[2][kMaxRanks] = {};        // mappings of the peers' windows (cudaIpcOpenMemHandle)
+    wrb_codec* local_peers[kMaxRanks] = {};   // ranks emulated in one process (wrb_set_slab_peers)
+    int n_local_peers = 0;
 };
 
 #define CK(call)                                                                                   \
@@ -209,16 +223,28 @@ int wrb_trim(wrb_codec* c)
     if (!c) return WRB_E_ARG;
     cudaSetDevice(c->device);
     DevBuf* all[] = {&c->coef, &c->tmp, &c->lllA, &c->lllB, &c->sym, &c->hist, &c->slots, &c->lens,
-                     &c->dstoff, &c->seek, &c->blob, &c->field, &c->offs, &c->layoff, &c->misc, &c->ext, &c->lcut, &c->zring};
+                     &c->dstoff, &c->seek, &c->blob, &c->field, &c->offs, &c->layoff, &c->misc, &c->ext, &c->lcut, &c->zring, &c->halo1};
     for (DevBuf* b : all) b->release();
     c->lc_mx = c->lc_my = c->lc_mz = 0;                  // the local-cutoff grid went with lcut: off until set again
     return 0;
+}
+
+static void close_peer_windows(wrb_codec* c)
+{
+    for (int w = 0; w < 2; w++)
+        for (int r = 0; r < kMaxRanks; r++)
+            if (c->ipc_open[w][r]) { cudaIpcCloseMemHandle(c->ipc_open[w][r]); c->ipc_open[w][r] = nullptr; }
+    c->peers_ok = false;
 }
 
 void wrb_destroy(wrb_codec* c)
 {
     if (!c) return;
     wrb_trim(c);
+    cudaSetDevice(c->device);
+    close_peer_windows(c);
+    c->xsym.release(); c->xrun.release(); c->ipcbuf.release();
+    if (c->comm) { slab_comm_destroy(c->comm); c->comm = nullptr; }
     c->state.release();
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_u64) cudaFreeHost(c->h_u64);
@@ -368,18 +394,33 @@ static bool all_levels_fused(int nx, int ny, int nz, int levels)
     return true;
 }
 
-// scratch of the transform.  need_coef / need_tmp: see all_levels_fused(); the z-slab mode always takes both
-// (its level-1 input is copied into `tmp` with halo room, its inverse may fall back to the line passes)
+// z-slab mode: does every level of the forward / inverse transform run through the one-pass kernels?  (same predicates
+// as wavelet_forward_slab / wavelet_inverse_slab)  Then the slab needs no full-size scratch: the level-1 halo planes have
+// a buffer of their own, and the inverse builds its band buffers straight from the symbols.
+static bool slab_forward_all_fused(int nx, int ny, int nz, int nzl, int levels)
+{
+    int n0 = nx, n1 = ny, n2g = nz, n2l = nzl;
+    for (int k = 0; k < levels; k++) {
+        if (!fused_forward_supported(n0, n1, n2g) || n2l < 2) return false;
+        n0 = half_up(n0); n1 = half_up(n1); n2g /= 2; n2l /= 2;
+    }
+    return levels > 0;
+}
+
+// scratch of the transform.  need_coef / need_tmp: see all_levels_fused().  slab != null: z-slab mode (nz is the local
+// plane count): halo room in the low-pass scratch, the level-1 halo planes, the band buffers of the inverse.
+struct SlabGeom;
 static int ensure_transform_buffers(wrb_codec* c, int nx, int ny, int nz, bool slab = false, bool need_coef = true,
-                                    bool need_tmp = true, bool need_zring = false)
+                                    bool need_tmp = true, bool need_zring = false, bool need_ext = true)
 {
     if (need_zring && inverse_two_pass_enabled()) CK(c->zring.ensure(inverse_two_pass_scratch_bytes(nx, ny, nz)));
     const size_t ntot = (size_t)nx * ny * nz;
     const size_t m1 = (size_t)half_up(nx) * half_up(ny) * half_up(nz);
     const size_t m2 = (size_t)half_up(half_up(nx)) * half_up(half_up(ny)) * half_up(half_up(nz));
-    if (need_coef || slab) CK(c->coef.ensure(ntot * 8));
-    if (need_tmp || slab) CK(c->tmp.ensure((ntot + (slab ? 7ull * nx * ny : 0ull)) * 8));
-    if (slab) CK(c->ext.ensure(((size_t)nz + 8) * nx * ny * 8));
+    if (need_coef) CK(c->coef.ensure(ntot * 8));
+    if (need_tmp) CK(c->tmp.ensure((ntot + (slab ? 7ull * nx * ny : 0ull)) * 8));
+    if (slab && need_ext) CK(c->ext.ensure(((size_t)nz + 8) * nx * ny * 8));
+    if (slab) CK(c->halo1.ensure(7ull * nx * ny * 8 + 64));
     const size_t h1 = slab ? 7ull * half_up(nx) * half_up(ny) : 0, h2 = slab ? 7ull * half_up(half_up(nx)) * half_up(half_up(ny)) : 0;
     CK(c->lllA.ensure((m1 + h1) * 8 + 64));      // slab mode: room for 4 + 3 halo planes
     CK(c->lllB.ensure((m2 + h2) * 8 + 64));
@@ -450,8 +491,10 @@ static int layer_guess(double tolrel)
     return n;
 }
 
+// sym_out / sym_stride: where the layers' symbols go (default: the codec's chunk-major buffer c->sym)
 static int run_transform_and_quantise(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag,
-                                      double tolrel, const ChunkGeom& g, const SlabGeom* sg = nullptr, int nlayers = kNLayMax)
+                                      double tolrel, const ChunkGeom& g, const SlabGeom* sg = nullptr, int nlayers = kNLayMax,
+                                      uint8_t* sym_out = nullptr, unsigned long long sym_stride = 0)
 {
     DevState* st = (DevState*)c->state.p;
     cudaStream_t s = c->stream;
@@ -466,8 +509,8 @@ static int run_transform_and_quantise(wrb_codec* c, const void* d_field, int dty
     const LocalCutoff lc{wtflag ? 0 : 1, nx, ny, nz, c->lc_mx, c->lc_my, c->lc_mz, (const double*)c->lcut.p, c->lc_min};
     if (sg != nullptr && wtflag) {
         int rc = wavelet_forward_slab(d_field, dtype == WRB_F32, (double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p,
-                                      (double*)c->lllB.p, nx, ny, sg->nz_global, sg->z0, nz, kWavLvl, st, c->hooks, s);
-        if (rc) return fail(c, WRB_E_CUDA, "halo exchange callback failed");
+                                      (double*)c->lllB.p, nx, ny, sg->nz_global, sg->z0, nz, kWavLvl, st, c->hooks, s, c->halo1.p);
+        if (rc) return fail(c, WRB_E_CUDA, c->comm ? slab_comm_error(c->comm) : "halo exchange callback failed");
     } else {
         wavelet_forward(d_field, dtype == WRB_F32, (double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p,
                         (double*)c->lllB.p, nx, ny, nz, wtflag ? kWavLvl : 0, st, s, c->src_pipe);
@@ -475,7 +518,8 @@ static int run_transform_and_quantise(wrb_codec* c, const void* d_field, int dty
     if (dist && reduce_extrema(c, &st->fmin_key, &st->fmax_key)) return fail(c, WRB_E_CUDA, "reduce callback failed");
     state_prepare(st, tolrel, s);
     if (c->timing) cudaEventRecord(c->ev[1], s);
-    const unsigned long long lstride = (unsigned long long)g.nchunks * g.pitch;
+    const unsigned long long lstride = sym_out ? sym_stride : (unsigned long long)g.nchunks * g.pitch;
+    uint8_t* const symp = sym_out ? sym_out : (uint8_t*)c->sym.p;
     const unsigned long long hstride = (unsigned long long)g.nblocks * 256;
     CK(cudaMemsetAsync(c->hist.p, 0, (size_t)nlayers * hstride * 4, s));      // the quantiser adds partial histograms
     for (int l = 0; l < nlayers; l++) {
@@ -483,10 +527,10 @@ static int run_transform_and_quantise(wrb_codec* c, const void* d_field, int dty
         if (dist && reduce_extrema(c, &st->rmin_key[l], &st->rmax_key[l])) return fail(c, WRB_E_CUDA, "reduce callback failed");
         layer_params(st, l, s);
         if (local)
-            quantise_layer_masked((const double*)c->coef.p, g, l, st, (uint8_t*)c->sym.p + l * lstride,
+            quantise_layer_masked((const double*)c->coef.p, g, l, st, symp + l * lstride,
                                   (uint32_t*)c->hist.p + l * hstride, lc, s);
         else
-            quantise_layer((const double*)c->coef.p, g, l, st, (uint8_t*)c->sym.p + l * lstride,
+            quantise_layer((const double*)c->coef.p, g, l, st, symp + l * lstride,
                            (uint32_t*)c->hist.p + l * hstride, s);
     }
     if (c->timing) cudaEventRecord(c->ev[2], s);
@@ -497,6 +541,133 @@ static int run_transform_and_quantise(wrb_codec* c, const void* d_field, int dty
 extern "C" {
 
 }  // extern "C"
+
+// ---- z-slab partition: the global symbol order --------------------------------------------------------------------
+// a collective with no payload: every rank has executed everything enqueued before it on its stream when it completes
+static int slab_barrier(wrb_codec* c)
+{
+    long long* buf = (long long*)((char*)c->misc.p + 96);
+    CK(cudaMemsetAsync(buf, 0, 16, c->stream));
+    if (c->hooks.reduce(c->hooks.user, buf, 2)) return fail(c, WRB_E_CUDA, c->comm ? slab_comm_error(c->comm) : "reduce callback failed");
+    return 0;
+}
+
+static bool global_order_on(const wrb_codec* c, const SlabGeom* sg)
+{
+    return sg != nullptr && c->order_global && c->hooks.nranks > 1 && c->chunk_blocks > 0;
+}
+
+// The exchange windows of this rank -- its local symbol planes (xsym) and its decoded run of the global sequence (xrun),
+// `nlayers` layers each -- and the peers' pointers to theirs: CUDA IPC handles all-gathered over NCCL, or the codecs of
+// the other emulated ranks of this process.  Collective: every rank calls it with the same geometry.
+static int slab_windows(wrb_codec* c, const OrderGeom& og, int nlayers)
+{
+    const int R = og.nranks, rank = c->hooks.rank;
+    const size_t ntl = (size_t)og.nx * og.ny * og.nzl;
+    const size_t xs = ((ntl + 15) & ~(size_t)15) + 16;
+    size_t maxrun = 0;
+    for (int r = 0; r < R; r++) maxrun = std::max(maxrun, (size_t)(og.j0[r + 1] - og.j0[r]));
+    const size_t rs = ((maxrun + 15) & ~(size_t)15) + 64;
+    const unsigned long long key[4] = {og.ntot, (unsigned long long)R | ((unsigned long long)og.levels << 8) | ((unsigned long long)og.nx << 16),
+                                       og.chunk_len, (unsigned long long)og.ny};
+    const bool same = c->peers_ok && memcmp(key, c->win_key, sizeof(key)) == 0 && nlayers <= c->win_layers;
+    if (same) return 0;
+    if (R > kMaxRanks) return fail(c, WRB_E_ARG, "too many ranks");
+    CK(cudaStreamSynchronize(c->stream));
+    close_peer_windows(c);
+    const int nl = std::max(nlayers, c->win_layers);
+    CK(c->xsym.ensure((size_t)nl * xs + 64));
+    CK(c->xrun.ensure((size_t)nl * rs + 64));
+    c->xsym_stride = xs; c->xrun_stride = rs; c->win_layers = nl;
+    memcpy(c->win_key, key, sizeof(key));
+    CK(c->misc.ensure(256));
+    if (c->comm != nullptr) {
+        cudaIpcMemHandle_t mine[2];
+        CK(cudaIpcGetMemHandle(&mine[0], c->xsym.p));
+        CK(cudaIpcGetMemHandle(&mine[1], c->xrun.p));
+        const size_t hb = sizeof(mine);                                  // 128 bytes
+        CK(c->ipcbuf.ensure((size_t)(R + 1) * hb));
+        CK(cudaMemcpyAsync(c->ipcbuf.p, mine, hb, cudaMemcpyHostToDevice, c->stream));
+        if (slab_comm_allgather(c->comm, c->ipcbuf.p, (char*)c->ipcbuf.p + hb, hb)) return fail(c, WRB_E_CUDA, slab_comm_error(c->comm));
+        std::vector<cudaIpcMemHandle_t> all(2 * (size_t)R);
+        CK(cudaMemcpyAsync(all.data(), (char*)c->ipcbuf.p + hb, (size_t)R * hb, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int r = 0; r < R; r++) {
+            if (r == rank) { c->peer_xsym.p[r] = (const uint8_t*)c->xsym.p; c->peer_xrun.p[r] = (const uint8_t*)c->xrun.p; continue; }
+            for (int w = 0; w < 2; w++) {
+                void* p = nullptr;
+                CK(cudaIpcOpenMemHandle(&p, all[2 * r + w], cudaIpcMemLazyEnablePeerAccess));
+                c->ipc_open[w][r] = p;
+                (w == 0 ? c->peer_xsym : c->peer_xrun).p[r] = (const uint8_t*)p;
+            }
+        }
+    } else if (c->n_local_peers == R) {
+        int rc = slab_barrier(c);                                        // every emulated rank has allocated its windows
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(c->stream));
+        for (int r = 0; r < R; r++) {
+            const wrb_codec* o = c->local_peers[r];
+            if (!o || !o->xsym.p || !o->xrun.p || o->xsym_stride != xs || o->xrun_stride != rs) return fail(c, WRB_E_ARG, "peer codec has no matching exchange window");
+            c->peer_xsym.p[r] = (const uint8_t*)o->xsym.p;
+            c->peer_xrun.p[r] = (const uint8_t*)o->xrun.p;
+        }
+        rc = slab_barrier(c);                                            // ... and nobody reallocates before everyone has read
+        if (rc) return rc;
+    } else {
+        return fail(c, WRB_E_ARG, "the global symbol order needs wrb_set_comm (NCCL) or wrb_set_slab_peers (one process)");
+    }
+    c->peers_ok = true;
+    return 0;
+}
+
+static int encode_slab_global(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nzl, int wtflag, double tolrel,
+                              wrb_header* hdr, unsigned char* d_data_enc, unsigned long cap, const SlabGeom* sg, int nlayers)
+{
+    const int R = c->hooks.nranks, rank = c->hooks.rank;
+    if (sg->z0 != rank * nzl || (long long)nzl * R != sg->nz_global) return fail(c, WRB_E_ARG, "the global symbol order needs equal slabs in rank order");
+    const OrderGeom og = make_order_geom(nx, ny, sg->nz_global, R, wtflag ? kWavLvl : 0, chunk_len_of(c));
+    if (og.nchunks < (unsigned long long)R) return fail(c, WRB_E_ARG, "fewer chunks than ranks");
+    const unsigned long long ntl = (unsigned long long)nx * ny * nzl;
+    const unsigned long long runlen = og.j0[rank + 1] - og.j0[rank];
+    const ChunkGeom gq = make_geom(ntl, 0, 0);                          // the quantiser's view: the local array, flat, one "chunk"
+    const ChunkGeom gr = make_geom(runlen, og.chunk_len, c->seek_points < 0 ? 7u : (unsigned)c->seek_points);   // my run of the global sequence
+    int rc;
+    const bool fused_fwd = !wtflag || slab_forward_all_fused(nx, ny, sg->nz_global, nzl, kWavLvl);
+    if ((rc = ensure_transform_buffers(c, nx, ny, nzl, true, true, !fused_fwd, false, false))) return rc;
+    if ((rc = ensure_coder_buffers(c, gr, nlayers, true))) return rc;
+    CK(c->hist.ensure((size_t)nlayers * std::max(gq.nblocks, gr.nblocks) * 256 * 4));      // the quantiser's (unused) local histograms too
+    const OrderGeom ogw = og;
+    if ((rc = slab_windows(c, ogw, nlayers))) return rc;
+    DevState* st = (DevState*)c->state.p;
+    cudaStream_t s = c->stream;
+    if ((rc = run_transform_and_quantise(c, d_field, dtype, nx, ny, nzl, wtflag, tolrel, gq, sg, nlayers, (uint8_t*)c->xsym.p, c->xsym_stride))) return rc;
+    // every rank's symbol planes are complete; then my run comes straight out of the peers' windows (NVLink), lands in
+    // the coder's chunk-major layout and is histogrammed per coder block on the way
+    if ((rc = slab_barrier(c))) return rc;
+    const unsigned long long lstride = (unsigned long long)gr.nchunks * gr.pitch;
+    const unsigned long long hstride = (unsigned long long)gr.nblocks * 256;
+    gather_global_run(og, rank, c->peer_xsym, c->xsym_stride, nlayers, st->active, gr, (uint8_t*)c->sym.p, lstride,
+                      (uint32_t*)c->hist.p, hstride, s);
+    if (c->timing) cudaEventRecord(c->ev[2], s);                        // "quantise" includes the exchange in this mode
+    const unsigned long long sp = chunk_slot_pitch(gr);
+    range_encode_chunks((const uint8_t*)c->sym.p, lstride, (const uint32_t*)c->hist.p, hstride, gr, nlayers, st->active,
+                        (uint8_t*)c->slots.p, sp, (unsigned long long*)c->lens.p, (uint32_t*)c->seek.p, s);
+    if (c->timing) cudaEventRecord(c->ev[3], s);
+    assemble_container((const uint8_t*)c->slots.p, sp, (const unsigned long long*)c->lens.p, (const uint32_t*)c->seek.p, gr,
+                       1, c->seek_points < 0, st, d_data_enc, cap, (unsigned long long*)c->dstoff.p, s);
+    if (c->timing) cudaEventRecord(c->ev[4], s);
+    CK(cudaMemcpyAsync(c->h_state, st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (c->timing) for (int i = 0; i < 4; i++) cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]);
+    if (!c->h_state->trivial && !c->h_state->done && nlayers < kNLayMax) {     // same decision on every rank (global extrema)
+        c->guess_misses++;
+        return encode_slab_global(c, d_field, dtype, nx, ny, nzl, wtflag, tolrel, hdr, d_data_enc, cap, sg, kNLayMax);
+    }
+    header_from_state(*c->h_state, wtflag, hdr);
+    if (c->h_state->error) return fail(c, WRB_E_OVERFLOW, "encoded data does not fit in data_enc");
+    return 0;
+}
 
 static int encode_impl(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag, double tolrel,
                        wrb_header* hdr, unsigned char* d_data_enc, unsigned long cap, const SlabGeom* sg, int nlayers = 0)
@@ -510,12 +681,15 @@ static int encode_impl(wrb_codec* c, const void* d_field, int dtype, int nx, int
     if (!c || !d_field || !hdr || !d_data_enc || nx < 1 || ny < 1 || nz < 1 || (dtype != WRB_F64 && dtype != WRB_F32))
         return c ? fail(c, WRB_E_ARG, "bad argument") : WRB_E_ARG;
     CK(cudaSetDevice(c->device));
+    if (global_order_on(c, sg) && c->lc_mx == 0)
+        return encode_slab_global(c, d_field, dtype, nx, ny, nz, wtflag, tolrel, hdr, d_data_enc, cap, sg, nlayers);
     const unsigned long long ntot = (unsigned long long)nx * ny * nz;
     const ChunkGeom g = make_geom(ntot, chunk_len_of(c), c->seek_points < 0 ? 7u : (unsigned)c->seek_points);
     const int chunked = c->chunk_blocks > 0;
     int rc;
     const bool fused_all = sg == nullptr && all_levels_fused(nx, ny, nz, wtflag ? kWavLvl : 0);
-    if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr, true, !fused_all))) return rc;
+    const bool slab_fused_fwd = sg != nullptr && (!wtflag || slab_forward_all_fused(nx, ny, sg->nz_global, nz, kWavLvl));
+    if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr, true, sg != nullptr ? !slab_fused_fwd : !fused_all, false, false))) return rc;
     if ((rc = ensure_coder_buffers(c, g, nlayers, true))) return rc;      // symbols, histograms and coder scratch of the layers launched
     DevState* st = (DevState*)c->state.p;
     cudaStream_t s = c->stream;
@@ -554,6 +728,70 @@ int wrb_set_slab(wrb_codec* c, int rank, int nranks, wrb_halo_fn halo, wrb_reduc
 {
     if (!c || nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && (!halo || !reduce))) return c ? fail(c, WRB_E_ARG, "bad slab setup") : WRB_E_ARG;
     c->hooks.rank = rank; c->hooks.nranks = nranks; c->hooks.halo = halo; c->hooks.reduce = reduce; c->hooks.user = user;
+    return 0;
+}
+
+int wrb_comm_unique_id(unsigned char id[128])
+{
+    if (!id) return WRB_E_ARG;
+    std::string err;
+    if (slab_comm_unique_id(id, &err)) { fprintf(stderr, "waverange_b200: %s\n", err.c_str()); return WRB_E_CUDA; }
+    return 0;
+}
+
+int wrb_set_comm(wrb_codec* c, int rank, int nranks, const unsigned char id[128])
+{
+    if (!c || !id || nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) return c ? fail(c, WRB_E_ARG, "bad communicator setup") : WRB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    if (c->comm) { close_peer_windows(c); slab_comm_destroy(c->comm); c->comm = nullptr; }
+    std::string err;
+    c->comm = slab_comm_create(rank, nranks, id, &c->stream, &err);
+    if (!c->comm) return fail(c, WRB_E_CUDA, err.c_str());
+    c->hooks.rank = rank; c->hooks.nranks = nranks; c->hooks.halo = slab_comm_halo; c->hooks.reduce = slab_comm_reduce; c->hooks.user = c->comm;
+    c->order_global = 1;
+    c->n_local_peers = 0;
+    c->peers_ok = false;
+    return 0;
+}
+
+int wrb_set_slab_peers(wrb_codec* c, wrb_codec* const* peers, int n)
+{
+    if (!c || n < 0 || n > kMaxRanks || (n > 0 && !peers)) return c ? fail(c, WRB_E_ARG, "bad peer list") : WRB_E_ARG;
+    for (int r = 0; r < n; r++) c->local_peers[r] = peers[r];
+    c->n_local_peers = n;
+    c->peers_ok = false;
+    c->order_global = n > 0 ? 1 : c->order_global;
+    return 0;
+}
+
+int wrb_set_slab_order(wrb_codec* c, int global)
+{
+    if (!c) return WRB_E_ARG;
+    c->order_global = global ? 1 : 0;
+    return 0;
+}
+
+int wrb_comm_counters(const wrb_codec* c, unsigned long long out[3])
+{
+    if (!c || !out) return WRB_E_ARG;
+    slab_comm_counters(c->comm, out);
+    return 0;
+}
+
+// host restatement of the partition's index map, for tests: global wavelet-space plane of local plane p of `rank` for an
+// (x, y) position of region reg, and the chunk range a rank codes
+int wrb_slab_order_plane(int nx, int ny, int nz, int nranks, int levels, int rank, int p, int reg)
+{
+    if (nranks < 1 || nranks > kMaxRanks || nz % nranks != 0) return -1;
+    const OrderGeom og = make_order_geom(nx, ny, nz, nranks, levels, 59999);
+    return order_global_plane(og, rank, p, reg);
+}
+
+int wrb_slab_chunk_range(int nx, int ny, int nz, int nranks, unsigned long chunk_len, int rank, unsigned long* c0, unsigned long* c1)
+{
+    if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks || !c0 || !c1) return WRB_E_ARG;
+    const OrderGeom og = make_order_geom(nx, ny, nz, nranks, 4, chunk_len);
+    *c0 = (unsigned long)og.cb[rank]; *c1 = (unsigned long)og.cb[rank + 1];
     return 0;
 }
 
@@ -676,6 +914,16 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
         if (c->timing) for (int i = 0; i < 4; i++) cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]);
         return 0;
     }
+    // z-slab mode in the global symbol order: the blob holds this rank's run of whole chunks of the GLOBAL sequence
+    const bool global = global_order_on(c, sg);
+    OrderGeom og{};
+    unsigned long long nsym_expected = ntot;
+    if (global) {
+        const int R = c->hooks.nranks, rank = c->hooks.rank;
+        if (sg->z0 != rank * nz || (long long)nz * R != sg->nz_global) return fail(c, WRB_E_ARG, "the global symbol order needs equal slabs in rank order");
+        og = make_order_geom(nx, ny, sg->nz_global, R, (int)hdr->wlev, chunk_len_of(c));
+        nsym_expected = og.j0[rank + 1] - og.j0[rank];
+    }
     unsigned long long* lay = c->h_u64;                       // layer offsets [nlay+1]
     lay[0] = 0;
     for (int l = 0; l < nlay; l++) lay[l + 1] = lay[l] + hdr->len_enc_vec[l];
@@ -703,7 +951,8 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
             for (int k = 0; k < 8; k++) { cl |= (unsigned long long)pk[8 + k] << (8 * k); nsym |= (unsigned long long)pk[16 + k] << (8 * k); }
             for (int k = 0; k < 4; k++) { ver |= (unsigned long long)pk[4 + k] << (8 * k); nch |= (unsigned long long)pk[24 + k] << (8 * k); nsk |= (unsigned long long)pk[28 + k] << (8 * k); }
             // version 3: 10-byte seek entries on nested grids; a version-2 container without seek points has the same layout
-            if (!(ver == 3 || (ver == 2 && nsk == 0)) || nsym != ntot || cl == 0 || cl > ntot || nch != (ntot + cl - 1) / cl || nsk > 15)
+            if (!(ver == 3 || (ver == 2 && nsk == 0)) || nsym != nsym_expected || cl == 0 || cl > nsym_expected ||
+                nch != (nsym_expected + cl - 1) / cl || nsk > 15)
                 return fail(c, WRB_E_FORMAT, "chunk container header does not match the field size");
             if (l > 0 && (cl != chunk_len || nsk != nseek)) return fail(c, WRB_E_FORMAT, "layers disagree on the chunk geometry");
             // header + tables + the shortest possible streams must fit into the layer: this also bounds every
@@ -714,23 +963,44 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
             return fail(c, WRB_E_FORMAT, "layer is neither a WRCK container nor a reference stream");
         }
     }
-    ChunkGeom g = make_geom(ntot, chunk_len, (unsigned)nseek);
+    ChunkGeom g = make_geom(nsym_expected, chunk_len, (unsigned)nseek);
     if (g.nseek != nseek) return fail(c, WRB_E_FORMAT, "seek table does not match the chunk geometry");
+    if (global && (!chunked || chunk_len != (og.chunk_len < nsym_expected ? og.chunk_len : nsym_expected)))
+        return fail(c, WRB_E_FORMAT, "not a run of the global chunk sequence");
     g.pitch = g.chunk_len;        // decoded symbols are kept flat (array order): the inverse transform indexes them directly
     int rc;
     const bool fused_all = sg == nullptr && all_levels_fused(nx, ny, nz, (int)hdr->wlev) && nz >= (1 << hdr->wlev) &&
                            getenv("WRB_NO_FUSED_DEQUANT") == nullptr;
-    if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr, !fused_all, !fused_all, sg == nullptr && hdr->wlev > 0))) return rc;
+    const bool slab_fused_inv = sg != nullptr && hdr->wlev > 0 && wavelet_inverse_slab_fused_ok(nx, ny, sg->nz_global, nz, (int)hdr->wlev);
+    const bool need_full = sg != nullptr ? !slab_fused_inv : !fused_all;
+    if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr, need_full, need_full, sg == nullptr && hdr->wlev > 0))) return rc;
     if ((rc = ensure_coder_buffers(c, g, nlay, false, false))) return rc;
+    ChunkGeom gl = make_geom(ntot, 0, 0);                     // the local array, flat (global mode: after the exchange)
+    gl.pitch = gl.chunk_len;
+    if (global) {
+        CK(c->sym.ensure((size_t)nlay * ((ntot + 15) & ~15ull) + 64));
+        if ((rc = slab_windows(c, og, nlay))) return rc;
+        if ((rc = slab_barrier(c))) return rc;                 // the peers have finished reading my run of the previous call
+    }
     int* d_err = (int*)c->misc.p;
     CK(cudaMemsetAsync(d_err, 0, sizeof(int), s));
     CK(cudaMemcpyAsync(c->layoff.p, lay, (nlay + 1) * 8, cudaMemcpyHostToDevice, s));
     parse_container(d_data_enc, g, chunked, nlay, (const unsigned long long*)c->layoff.p, (unsigned long long*)c->offs.p, d_err, s);
     if (c->timing) cudaEventRecord(c->ev[1], s);
     // layer planes of the decoded symbols start 16-byte aligned (the z pass of the inverse reads them as words)
-    const unsigned long long lstride = ((unsigned long long)g.nchunks * g.pitch + 15ull) & ~15ull;
-    range_decode_chunks(d_data_enc, (const unsigned long long*)c->offs.p, (const unsigned long long*)c->layoff.p, g, nlay,
-                        (uint8_t*)c->sym.p, lstride, (unsigned long long)hdr->ntot_enc, d_err, s);
+    unsigned long long lstride = ((unsigned long long)g.nchunks * g.pitch + 15ull) & ~15ull;
+    if (global) {
+        // my run is decoded into the exchange window; then every rank gathers its local planes from the peers' runs
+        range_decode_chunks(d_data_enc, (const unsigned long long*)c->offs.p, (const unsigned long long*)c->layoff.p, g, nlay,
+                            (uint8_t*)c->xrun.p, c->xrun_stride, (unsigned long long)hdr->ntot_enc, d_err, s);
+        if ((rc = slab_barrier(c))) return rc;
+        lstride = (ntot + 15ull) & ~15ull;
+        scatter_local_planes(og, c->hooks.rank, c->peer_xrun, c->xrun_stride, nlay, (uint8_t*)c->sym.p, lstride, s);
+        g = gl;
+    } else {
+        range_decode_chunks(d_data_enc, (const unsigned long long*)c->offs.p, (const unsigned long long*)c->layoff.p, g, nlay,
+                            (uint8_t*)c->sym.p, lstride, (unsigned long long)hdr->ntot_enc, d_err, s);
+    }
     if (c->timing) cudaEventRecord(c->ev[2], s);
     // The inverse z pass rebuilds the coefficients from the symbols itself; a separate dequantise pass is only
     // needed without a transform, for extent-1 z, and in slab mode (its band buffers are built from coef).
