@@ -101,7 +101,7 @@ int order_global_plane(const OrderGeom& og, int rank, int p, int reg)
     return order_plane(o, rank, p, reg);
 }
 
-// four bytes at an arbitrary address through two aligned word loads (the buffers have >= 8 bytes of slack)
+// four / sixteen bytes at an arbitrary address through aligned word loads (the buffers have >= 16 bytes of slack)
 __device__ __forceinline__ uint32_t load4_unaligned(const uint8_t* src)
 {
     const unsigned long long a = (unsigned long long)src;
@@ -110,20 +110,54 @@ __device__ __forceinline__ uint32_t load4_unaligned(const uint8_t* src)
     const uint32_t w0 = wp[0], w1 = wp[1];
     return __funnelshift_r(w0, w1, sh);
 }
+// Sixteen bytes at an arbitrary address for every lane of a warp, when consecutive lanes mostly read consecutive 16-byte
+// items of one contiguous source run.  Loads that cross NVLink are not kept in L1, so five overlapping word loads per
+// lane (the obvious way) move every sector five times; here a lane loads ONE aligned 16-byte vector, takes the next one
+// from its neighbour by shuffle (or loads it itself where the run ends) and shifts the pair in registers.
+// All 32 lanes must call it; `on` = this lane wants data.
+__device__ __forceinline__ uint4 warp_load16_unaligned(const uint8_t* src, bool on)
+{
+    const unsigned long long a = on ? (unsigned long long)src : 0ull;
+    const uint4* vp = reinterpret_cast<const uint4*>(a & ~15ull);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (on) v = *vp;
+    // the neighbour's vector is my next one iff its aligned address is mine + 16
+    const unsigned long long an = __shfl_down_sync(0xffffffffu, a & ~15ull, 1);
+    uint4 n;
+    n.x = __shfl_down_sync(0xffffffffu, v.x, 1); n.y = __shfl_down_sync(0xffffffffu, v.y, 1);
+    n.z = __shfl_down_sync(0xffffffffu, v.z, 1); n.w = __shfl_down_sync(0xffffffffu, v.w, 1);
+    const unsigned int s = (unsigned int)(a & 15ull);
+    const bool own = on && s != 0 && ((threadIdx.x & 31) == 31 || an != (a & ~15ull) + 16ull);
+    if (own) n = vp[1];
+    // bytes [s, s + 16) of (v, n)
+    const unsigned int ws = s >> 2, bs = (s & 3u) * 8u;
+    const uint32_t W[8] = {v.x, v.y, v.z, v.w, n.x, n.y, n.z, n.w};
+    uint32_t o[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        uint32_t x = W[k];
+        x = (ws == 1) ? W[k + 1] : x;
+        x = (ws == 2) ? W[k + 2] : x;
+        x = (ws == 3) ? W[(k + 3) & 7] : x;
+        o[k] = x;
+    }
+    return make_uint4(__funnelshift_r(o[0], o[1], bs), __funnelshift_r(o[1], o[2], bs), __funnelshift_r(o[2], o[3], bs),
+                      __funnelshift_r(o[3], o[4], bs));
+}
 
 // ---- encode side -----------------------------------------------------------------------------------------------
-// grid (coder blocks of my run, layers): one CTA per coder block (<= 60000 symbols), as the quantiser has it
-__global__ void __launch_bounds__(256) gather_run_kernel(OrderDev o, int rank, PeerPtrs peer, unsigned long long peer_stride,
+// Generic version (any shape; used for rows shorter than 256 symbols).  Pure copy kernel, grid (coder blocks of my run,
+// layers), no shared memory: what limits it is the latency of loads
+// that cross NVLink (~2-3 us), so it wants as many bytes in flight as the SM can hold -- 2048 threads x 20 bytes.  (A
+// first version read 4 bytes per thread and iteration and histogrammed on the way: 180 GB/s.)  The coder blocks'
+// histograms are taken afterwards from the local copy (hist_blocks_kernel).
+__global__ void __launch_bounds__(256) gather_run_small_kernel(OrderDev o, int rank, PeerPtrs peer, unsigned long long peer_stride,
                                                          const int* __restrict__ active, ChunkGeom g,
-                                                         uint8_t* __restrict__ sym, unsigned long long lstride,
-                                                         uint32_t* __restrict__ hist, unsigned long long hstride)
+                                                         uint8_t* __restrict__ sym, unsigned long long lstride)
 {
     const int layer = blockIdx.y;
     if (active != nullptr && !active[layer]) return;
-    __shared__ uint32_t s_hist[256];
     const int tid = threadIdx.x;
-    s_hist[tid] = 0;
-    __syncthreads();
     const unsigned int b = blockIdx.x;
     const unsigned int c = b / g.blocks_per_chunk, kb = b % g.blocks_per_chunk;
     const unsigned long long cstart = (unsigned long long)c * g.chunk_len;
@@ -137,44 +171,194 @@ __global__ void __launch_bounds__(256) gather_run_kernel(OrderDev o, int rank, P
     const unsigned int yb = rem / (unsigned int)o.nx, xb = rem - yb * (unsigned int)o.nx;
     uint8_t* __restrict__ out = sym + (unsigned long long)layer * lstride + (unsigned long long)c * g.pitch + boff;
     const unsigned long long loff = (unsigned long long)layer * peer_stride;
-    for (unsigned int q = 4u * tid; q < bs; q += 4u * 256u) {
+    // position (x, y, w) of symbol q of the block
+    auto locate = [&](unsigned int q, int& x, int& y, int& w) {
         const unsigned int t = xb + q;
         const unsigned int dy = t / (unsigned int)o.nx;
-        const int x = (int)(t - dy * (unsigned int)o.nx);
+        x = (int)(t - dy * (unsigned int)o.nx);
         const unsigned int yy = yb + dy;
         const unsigned int dw = yy / (unsigned int)o.ny;
-        const int y = (int)(yy - dw * (unsigned int)o.ny);
-        const int w = (int)(wb + dw);
-        const int reg = order_region(o, x, y);
-        if (q + 4 <= bs && x + 3 < o.nx && order_region(o, x + 3, y) == reg) {      // the quad stays in one row and region
-            int owner, p;
-            order_source(o, w, reg, owner, p);
-            const uint8_t* src = peer.p[owner] + loff + ((unsigned long long)p * o.ny + y) * o.nx + x;
-            const uint32_t v = load4_unaligned(src);
-            *reinterpret_cast<uint32_t*>(out + q) = v;
-            atomicAdd(&s_hist[v & 0xFFu], 1u);
-            atomicAdd(&s_hist[(v >> 8) & 0xFFu], 1u);
-            atomicAdd(&s_hist[(v >> 16) & 0xFFu], 1u);
-            atomicAdd(&s_hist[v >> 24], 1u);
-        } else {
-            for (unsigned int e = 0; e < 4 && q + e < bs; e++) {
-                const unsigned int t1 = xb + q + e;
-                const unsigned int dy1 = t1 / (unsigned int)o.nx;
-                const int x1 = (int)(t1 - dy1 * (unsigned int)o.nx);
-                const unsigned int yy1 = yb + dy1;
-                const unsigned int dw1 = yy1 / (unsigned int)o.ny;
-                const int y1 = (int)(yy1 - dw1 * (unsigned int)o.ny);
-                const int w1 = (int)(wb + dw1);
-                int owner, p;
-                order_source(o, w1, order_region(o, x1, y1), owner, p);
-                const uint8_t v = peer.p[owner][loff + ((unsigned long long)p * o.ny + y1) * o.nx + x1];
-                out[q + e] = v;
-                atomicAdd(&s_hist[v], 1u);
+        y = (int)(yy - dw * (unsigned int)o.ny);
+        w = (int)(wb + dw);
+    };
+    auto source = [&](int x, int y, int w, int reg) -> const uint8_t* {
+        int owner, p;
+        order_source(o, w, reg, owner, p);
+        return peer.p[owner] + loff + ((unsigned long long)p * o.ny + y) * o.nx + x;
+    };
+    for (unsigned int q0 = 0; q0 < bs; q0 += 16u * 256u) {            // warp-uniform trip count: the lanes shuffle
+        const unsigned int q = q0 + 16u * tid;
+        int x = 0, y = 0, w = 0, reg = 0;
+        bool fast = false;
+        const uint8_t* src = nullptr;
+        if (q < bs) {
+            locate(q, x, y, w);
+            reg = order_region(o, x, y);
+            fast = q + 16 <= bs && x + 15 < o.nx && order_region(o, x + 15, y) == reg;   // 16 symbols of one row and region
+            if (fast) src = source(x, y, w, reg);
+        }
+        const uint4 v = warp_load16_unaligned(src, fast);
+        if (fast) { *reinterpret_cast<uint4*>(out + q) = v; continue; }
+        if (q >= bs) continue;
+        for (unsigned int q4 = q; q4 < q + 16 && q4 < bs; q4 += 4) {                  // row end / region border / tail
+            locate(q4, x, y, w);
+            const int r4 = order_region(o, x, y);
+            if (q4 + 4 <= bs && x + 3 < o.nx && order_region(o, x + 3, y) == r4) {
+                *reinterpret_cast<uint32_t*>(out + q4) = load4_unaligned(source(x, y, w, r4));
+            } else {
+                for (unsigned int e = q4; e < q4 + 4 && e < bs; e++) {
+                    locate(e, x, y, w);
+                    out[e] = *source(x, y, w, order_region(o, x, y));
+                }
             }
         }
     }
+}
+
+// Fast version for rows of >= 256 symbols (every real field).  The generic kernel above spends ~80 instructions per
+// byte on index arithmetic (two divisions, the region and source searches, per item and again per byte where an item
+// straddles a region border: 1.2 ms for a 512 x 512 x 512 slab's three layers).  Here the CTA first writes, per row its
+// coder block touches (<= 60000 / 256 + 2), the row's segments -- runs of one region, i.e. of one (owner, local plane) --
+// with their source pointers into shared memory; the copy loop then finds an item's row by one multiply-shift, its
+// segment by comparisons and its source by one shared load.
+constexpr int kGRowsMax = 240;
+struct FastDiv { uint32_t mul, sh; };
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, FastDiv d) { return __umulhi(n, d.mul) >> d.sh; }   // exact for n <= 2^31, divisor >= 2
+
+__global__ void __launch_bounds__(256) gather_run_kernel(OrderDev o, FastDiv dnx, int rank, PeerPtrs peer, unsigned long long peer_stride,
+                                                         const int* __restrict__ active, ChunkGeom g,
+                                                         uint8_t* __restrict__ sym, unsigned long long lstride)
+{
+    const int layer = blockIdx.y;
+    if (active != nullptr && !active[layer]) return;
+    __shared__ const uint8_t* s_ptr[kGRowsMax * 5];   // source of x = 0 of every (row, segment): add x
+    __shared__ uint8_t s_ky[kGRowsMax];               // segments of the row (= region of its y alone)
+    const int tid = threadIdx.x;
+    const unsigned int b = blockIdx.x;
+    const unsigned int c = b / g.blocks_per_chunk, kb = b % g.blocks_per_chunk;
+    const unsigned long long cstart = (unsigned long long)c * g.chunk_len;
+    const unsigned long long clen = (g.ntot - cstart < g.chunk_len) ? g.ntot - cstart : g.chunk_len;
+    const unsigned long long boff = (unsigned long long)kb * kBlock;
+    const unsigned int bs = (clen - boff < kBlock) ? (unsigned int)(clen - boff) : kBlock;
+    const unsigned long long jb = o.j0[rank] + cstart + boff;
+    const unsigned long long wb = jb / o.plane;
+    const unsigned int rem = (unsigned int)(jb - wb * o.plane);
+    const unsigned int yb = rem / (unsigned int)o.nx, xb = rem - yb * (unsigned int)o.nx;
+    uint8_t* __restrict__ out = sym + (unsigned long long)layer * lstride + (unsigned long long)c * g.pitch + boff;
+    const unsigned long long loff = (unsigned long long)layer * peer_stride;
+    const int L = o.levels;
+    const unsigned int nrows = bs ? (xb + bs - 1) / (unsigned int)o.nx + 1 : 0;
+    // ---- the rows' segments: segment s of a row with ky segments covers x in [B_s, B_s+1), B_0 = 0, B_j = mx[ky - j], B_ky = nx,
+    //      and has region ky for s == 0, ky - s otherwise ----
+    for (unsigned int t = tid; t < nrows * 5u; t += 256u) {
+        const unsigned int r = t / 5u, sgm = t - r * 5u;
+        const unsigned int yy = yb + r;
+        const unsigned int dw = yy / (unsigned int)o.ny;
+        const int y = (int)(yy - dw * (unsigned int)o.ny);
+        const int w = (int)(wb + dw);
+        int ky = L + 1;
+        for (int k = L; k >= 1; k--) if (y >= o.my[k]) ky = k;
+        if (sgm == 0) s_ky[r] = (uint8_t)ky;
+        if ((int)sgm < ky) {
+            int owner, p;
+            order_source(o, w, ky - (int)sgm, owner, p);
+            s_ptr[t] = peer.p[owner] + loff + ((unsigned long long)p * o.ny + y) * o.nx;
+        }
+    }
     __syncthreads();
-    hist[(unsigned long long)layer * hstride + (unsigned long long)b * 256 + tid] = s_hist[tid];
+    const int m1 = o.mx[1], m2 = o.mx[2], m3 = o.mx[3], m4 = o.mx[4];
+    // segment of x in a row with ky segments, and the end of that segment
+    auto segment = [&](int x, int ky, int& xe) -> int {
+        // boundaries B_j = mx[ky - j], j = 1 .. ky-1: count those <= x
+        int s = 0;
+        xe = o.nx;
+        if (ky > 4) { if (x >= m4) s++; else { xe = m4; return s; } }      // ky = 5: B_1 = mx[4]
+        if (ky > 3) { if (x >= m3) s++; else { xe = m3; return s; } }
+        if (ky > 2) { if (x >= m2) s++; else { xe = m2; return s; } }
+        if (ky > 1) { if (x >= m1) s++; else { xe = m1; return s; } }
+        return s;
+    };
+    for (unsigned int q0 = 0; q0 < bs; q0 += 16u * 256u) {            // warp-uniform trip count: the lanes shuffle
+        const unsigned int q = q0 + 16u * tid;
+        bool fast = false;
+        const uint8_t* src = nullptr;
+        unsigned int r = 0;
+        int x = 0, xe = 0, ky = 1, sgm = 0;
+        if (q < bs) {
+            const unsigned int t = xb + q;
+            r = fdiv(t, dnx);
+            x = (int)(t - r * (unsigned int)o.nx);
+            ky = s_ky[r];
+            sgm = segment(x, ky, xe);
+            fast = q + 16 <= bs && x + 16 <= xe;
+            src = s_ptr[r * 5 + sgm] + x;
+        }
+        const uint4 v = warp_load16_unaligned(src, fast);
+        if (fast) { *reinterpret_cast<uint4*>(out + q) = v; continue; }
+        if (q >= bs) continue;
+        for (unsigned int e = q; e < q + 16 && e < bs; e++) {          // the item crosses a segment or row end (or is the tail)
+            if (x >= xe) {
+                if (x >= o.nx) { x = 0; r++; ky = s_ky[r]; }
+                sgm = segment(x, ky, xe);
+                src = s_ptr[r * 5 + sgm] + x;
+            }
+            out[e] = *src;
+            src++; x++;
+        }
+    }
+}
+
+// 256-bin histogram of every coder block of the (local, chunk-major) symbols: one CTA per block, private one-byte
+// counters per thread as in the quantiser (quant.cu) -- no atomics, so a layer that is almost one symbol costs the same
+constexpr int kHThreads = 256;
+constexpr int kHHistBytes = 256 * kHThreads;             // 64 KiB
+__global__ void __launch_bounds__(kHThreads) hist_blocks_kernel(const uint8_t* __restrict__ sym, unsigned long long lstride,
+                                                                const int* __restrict__ active, ChunkGeom g,
+                                                                uint32_t* __restrict__ hist, unsigned long long hstride)
+{
+    const int layer = blockIdx.y;
+    if (active != nullptr && !active[layer]) return;
+    extern __shared__ __align__(16) uint32_t s_cnt[];     // [256 bins][64 words]: thread t's counter of bin q is byte t>>6 of word q*64 + (t&63)
+    const int tid = threadIdx.x;
+    {
+        uint4* z = reinterpret_cast<uint4*>(s_cnt);
+        for (int i = tid; i < kHHistBytes / 16; i += kHThreads) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    uint8_t* const cnt = reinterpret_cast<uint8_t*>(s_cnt);
+    const unsigned int mine = (tid & 63) * 4 + (tid >> 6);
+    const unsigned int b = blockIdx.x;
+    const unsigned int c = b / g.blocks_per_chunk, kb = b % g.blocks_per_chunk;
+    const unsigned long long cstart = (unsigned long long)c * g.chunk_len;
+    const unsigned long long clen = (g.ntot - cstart < g.chunk_len) ? g.ntot - cstart : g.chunk_len;
+    const unsigned long long boff = (unsigned long long)kb * kBlock;
+    const unsigned int bs = (clen - boff < kBlock) ? (unsigned int)(clen - boff) : kBlock;
+    const uint8_t* __restrict__ in = sym + (unsigned long long)layer * lstride + (unsigned long long)c * g.pitch + boff;
+    for (unsigned int q = 16u * tid; q < bs; q += 16u * kHThreads) {                  // <= 15 vectors = 240 symbols per thread
+        const uint4 v4 = *reinterpret_cast<const uint4*>(in + q);                    // chunks start 16-byte aligned, pitch slack covers the tail
+        const uint32_t vv[4] = {v4.x, v4.y, v4.z, v4.w};
+        const unsigned int n = bs - q;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t v = vv[k];
+            if (n > 4u * k) cnt[__byte_perm(v, mine, 0x6504)] += 1;                  // offset = bin * 256 + mine
+            if (n > 4u * k + 1) cnt[__byte_perm(v >> 8, mine, 0x6504)] += 1;
+            if (n > 4u * k + 2) cnt[__byte_perm(v >> 16, mine, 0x6504)] += 1;
+            if (n > 4u * k + 3) cnt[__byte_perm(v >> 24, mine, 0x6504)] += 1;
+        }
+    }
+    __syncthreads();
+    const uint4* row = reinterpret_cast<const uint4*>(s_cnt + tid * 64);
+    unsigned int tot = 0;
+#pragma unroll
+    for (int wd = 0; wd < 16; wd++) {
+        const uint4 xx = row[(wd + tid) & 15];
+        tot = __dp4a(xx.x, 0x01010101u, tot);
+        tot = __dp4a(xx.y, 0x01010101u, tot);
+        tot = __dp4a(xx.z, 0x01010101u, tot);
+        tot = __dp4a(xx.w, 0x01010101u, tot);
+    }
+    hist[(unsigned long long)layer * hstride + (unsigned long long)b * 256 + tid] = tot;
 }
 
 void gather_global_run(const OrderGeom& og, int rank, const PeerPtrs& peer, unsigned long long peer_stride, int nlayers,
@@ -183,42 +367,77 @@ void gather_global_run(const OrderGeom& og, int rank, const PeerPtrs& peer, unsi
 {
     if (g.nblocks == 0 || nlayers <= 0) return;
     const OrderDev o = make_dev(og);
+    static DeviceOnce once;
+    once.run([] { cudaFuncSetAttribute(hist_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHHistBytes); });
     dim3 grid(g.nblocks, nlayers, 1);
-    gather_run_kernel<<<grid, 256, 0, s>>>(o, rank, peer, peer_stride, active, g, sym, sym_layer_stride, hist, hist_layer_stride);
-    note_launch(1);
+    if (og.nx >= 256 && og.levels <= 4) {
+        uint32_t l2 = 0;
+        while ((1u << l2) < (uint32_t)og.nx) l2++;                       // ceil(log2 nx)
+        FastDiv d{(uint32_t)(((1ull << (31 + l2)) + (unsigned long long)og.nx - 1) / (unsigned long long)og.nx), l2 - 1};
+        gather_run_kernel<<<grid, 256, 0, s>>>(o, d, rank, peer, peer_stride, active, g, sym, sym_layer_stride);
+    } else {
+        gather_run_small_kernel<<<grid, 256, 0, s>>>(o, rank, peer, peer_stride, active, g, sym, sym_layer_stride);
+    }
+    hist_blocks_kernel<<<grid, kHThreads, kHHistBytes, s>>>(sym, sym_layer_stride, active, g, hist, hist_layer_stride);
+    note_launch(2);
 }
 
 // ---- decode side -----------------------------------------------------------------------------------------------
-// grid (ny, nzl, layers): one CTA per row (y, local plane p) of one layer
-__global__ void __launch_bounds__(128) scatter_local_kernel(OrderDev o, int rank, PeerPtrs peer, unsigned long long peer_stride,
+// grid (ceil(ny / kSRows), nzl, layers): one CTA per group of kSRows rows of one local plane of one layer; a thread moves
+// 16 symbols per iteration (same reasoning as gather_run_kernel: the loads cross NVLink)
+constexpr int kSRows = 16;
+
+__global__ void __launch_bounds__(256) scatter_local_kernel(OrderDev o, int rank, PeerPtrs peer, unsigned long long peer_stride,
                                                             uint8_t* __restrict__ out, unsigned long long out_stride)
 {
-    const int y = blockIdx.x, p = blockIdx.y, layer = blockIdx.z;
+    const int p = blockIdx.y, layer = blockIdx.z;
     const unsigned long long loff = (unsigned long long)layer * peer_stride;
-    uint8_t* __restrict__ row = out + (unsigned long long)layer * out_stride + ((unsigned long long)p * o.ny + y) * o.nx;
-    const bool vec = (o.nx & 3) == 0 && (((unsigned long long)row) & 3ull) == 0;
-    auto source = [&](unsigned long long j) -> const uint8_t* {
+    // global plane of this local plane for every region (1 .. levels + 1)
+    int wreg[8];
+#pragma unroll
+    for (int k = 1; k < 8; k++) wreg[k] = (k <= o.levels + 1) ? order_plane(o, rank, p, k) : 0;
+    auto wof = [&](int reg) -> int {                                  // register select instead of a local-memory array
+        int w = wreg[1];
+#pragma unroll
+        for (int k = 2; k < 8; k++) w = (reg == k) ? wreg[k] : w;
+        return w;
+    };
+    auto source = [&](unsigned long long j, unsigned long long& left) -> const uint8_t* {
         int d = 0;
         while (d + 1 < o.nranks && j >= o.j0[d + 1]) d++;
+        left = o.j0[d + 1] - j;                                       // symbols of this rank's run from j on
         return peer.p[d] + loff + (j - o.j0[d]);
     };
-    for (int x = 4 * threadIdx.x; x < o.nx; x += 4 * 128) {
-        const int reg = order_region(o, x, y);
-        const int x3 = (x + 3 < o.nx) ? x + 3 : o.nx - 1;
-        bool fast = vec && x + 3 < o.nx && order_region(o, x3, y) == reg;
-        if (fast) {
-            const int w = order_plane(o, rank, p, reg);
-            const unsigned long long j = ((unsigned long long)w * o.ny + y) * o.nx + x;
-            int d = 0;
-            while (d + 1 < o.nranks && j >= o.j0[d + 1]) d++;
-            if (j + 3 < o.j0[d + 1]) {                               // the quad lies in one rank's run
-                *reinterpret_cast<uint32_t*>(row + x) = load4_unaligned(peer.p[d] + loff + (j - o.j0[d]));
-                continue;
+    const int ipr = (o.nx + 15) >> 4;                                 // 16-symbol items per row
+    const int y0 = blockIdx.x * kSRows;
+    const int nrows = min(kSRows, o.ny - y0);
+    for (int it0 = 0; it0 < nrows * ipr; it0 += 256) {                // warp-uniform trip count: the lanes shuffle
+        const int it = it0 + threadIdx.x;
+        const bool live = it < nrows * ipr;
+        const int ry = live ? it / ipr : 0, x = live ? 16 * (it - ry * ipr) : 0;
+        const int y = y0 + ry;
+        uint8_t* __restrict__ row = out + (unsigned long long)layer * out_stride + ((unsigned long long)p * o.ny + y) * o.nx;
+        unsigned long long left = 0;
+        bool fast = false;
+        const uint8_t* src = nullptr;
+        if (live) {
+            const int reg = order_region(o, x, y);
+            if (x + 15 < o.nx && ((((unsigned long long)row) + x) & 15ull) == 0 && order_region(o, x + 15, y) == reg) {
+                src = source(((unsigned long long)wof(reg) * o.ny + y) * o.nx + x, left);
+                fast = left >= 16;
             }
         }
-        for (int e = 0; e < 4 && x + e < o.nx; e++) {
-            const int w = order_plane(o, rank, p, order_region(o, x + e, y));
-            row[x + e] = *source(((unsigned long long)w * o.ny + y) * o.nx + (x + e));
+        const uint4 v = warp_load16_unaligned(src, fast);
+        if (fast) { *reinterpret_cast<uint4*>(row + x) = v; continue; }
+        if (!live) continue;
+        for (int x4 = x; x4 < x + 16 && x4 < o.nx; x4 += 4) {
+            const int r4 = order_region(o, x4, y);
+            if (x4 + 3 < o.nx && ((((unsigned long long)row) + x4) & 3ull) == 0 && order_region(o, x4 + 3, y) == r4) {
+                const uint8_t* s4 = source(((unsigned long long)wof(r4) * o.ny + y) * o.nx + x4, left);
+                if (left >= 4) { *reinterpret_cast<uint32_t*>(row + x4) = load4_unaligned(s4); continue; }
+            }
+            for (int e = x4; e < x4 + 4 && e < o.nx; e++)
+                row[e] = *source(((unsigned long long)wof(order_region(o, e, y)) * o.ny + y) * o.nx + e, left);
         }
     }
 }
@@ -228,8 +447,8 @@ void scatter_local_planes(const OrderGeom& og, int rank, const PeerPtrs& peer, u
 {
     if (nlay <= 0) return;
     const OrderDev o = make_dev(og);
-    dim3 grid(og.ny, og.nzl, nlay);
-    scatter_local_kernel<<<grid, 128, 0, s>>>(o, rank, peer, peer_stride, out, out_stride);
+    dim3 grid((og.ny + kSRows - 1) / kSRows, og.nzl, nlay);
+    scatter_local_kernel<<<grid, 256, 0, s>>>(o, rank, peer, peer_stride, out, out_stride);
     note_launch(1);
 }
 
