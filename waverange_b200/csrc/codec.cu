@@ -420,7 +420,7 @@ static int ensure_transform_buffers(wrb_codec* c, int nx, int ny, int nz, bool s
     if (need_coef) CK(c->coef.ensure(ntot * 8));
     if (need_tmp) CK(c->tmp.ensure((ntot + (slab ? 7ull * nx * ny : 0ull)) * 8));
     if (slab && need_ext) CK(c->ext.ensure(((size_t)nz + 8) * nx * ny * 8));
-    if (slab) CK(c->halo1.ensure(7ull * nx * ny * 8 + 64));
+    if (slab) CK(c->halo1.ensure(14ull * nx * ny * 8 + 64));     // level-1 halo planes (forward) / boundary + halo planes (inverse)
     const size_t h1 = slab ? 7ull * half_up(nx) * half_up(ny) : 0, h2 = slab ? 7ull * half_up(half_up(nx)) * half_up(half_up(ny)) : 0;
     CK(c->lllA.ensure((m1 + h1) * 8 + 64));      // slab mode: room for 4 + 3 halo planes
     CK(c->lllB.ensure((m2 + h2) * 8 + 64));
@@ -889,7 +889,7 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
         ChunkGeom g = make_geom(ntot, 0, 0);
         g.pitch = g.chunk_len;
         int rc;
-        if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr, true, true, sg == nullptr && hdr->wlev > 0))) return rc;
+        if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr, true, true, hdr->wlev > 0))) return rc;
         const unsigned long long lstride = ntot;
         if (c->timing) for (int i = 0; i < 4; i++) cudaEventRecord(c->ev[i], s);
         const bool slab_fused = sg != nullptr && hdr->wlev > 0 && wavelet_inverse_slab_fused_ok(nx, ny, sg->nz_global, nz, (int)hdr->wlev);
@@ -898,7 +898,8 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
         if (sg != nullptr && hdr->wlev > 0) {
             if (wavelet_inverse_slab((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, (double*)c->ext.p,
                                      d_out, dtype == WRB_F32, nx, ny, sg->nz_global, sg->z0, nz, (int)hdr->wlev, c->hooks, s,
-                                     slab_fused ? d_sym_flat : nullptr, lstride, nlay, hdr->deps_vec, hdr->minval_vec))
+                                     slab_fused ? d_sym_flat : nullptr, lstride, nlay, hdr->deps_vec, hdr->minval_vec,
+                                     (double*)c->zring.p, c->zring.cap, (double*)c->halo1.p))
                 return fail(c, WRB_E_CUDA, "halo exchange callback failed");
         } else if (fuse) {
             wavelet_inverse((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, d_out, dtype == WRB_F32,
@@ -973,7 +974,9 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
                            getenv("WRB_NO_FUSED_DEQUANT") == nullptr;
     const bool slab_fused_inv = sg != nullptr && hdr->wlev > 0 && wavelet_inverse_slab_fused_ok(nx, ny, sg->nz_global, nz, (int)hdr->wlev);
     const bool need_full = sg != nullptr ? !slab_fused_inv : !fused_all;
-    if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr, need_full, need_full, sg == nullptr && hdr->wlev > 0))) return rc;
+    const bool slab_two_pass = sg != nullptr && hdr->wlev > 0 && wavelet_inverse_slab_two_pass_ok(nx, ny, sg->nz_global, nz, (int)hdr->wlev);
+    if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr, need_full, need_full, (sg == nullptr && hdr->wlev > 0) || slab_two_pass,
+                                       !slab_two_pass))) return rc;
     if ((rc = ensure_coder_buffers(c, g, nlay, false, false))) return rc;
     ChunkGeom gl = make_geom(ntot, 0, 0);                     // the local array, flat (global mode: after the exchange)
     gl.pitch = gl.chunk_len;
@@ -1011,8 +1014,9 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
     if (sg != nullptr && hdr->wlev > 0) {
         if (wavelet_inverse_slab((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, (double*)c->ext.p,
                                  d_out, dtype == WRB_F32, nx, ny, sg->nz_global, sg->z0, nz, (int)hdr->wlev, c->hooks, s,
-                                 slab_fused ? (const uint8_t*)c->sym.p : nullptr, lstride, nlay, hdr->deps_vec, hdr->minval_vec))
-            return fail(c, WRB_E_CUDA, "halo exchange callback failed");
+                                 slab_fused ? (const uint8_t*)c->sym.p : nullptr, lstride, nlay, hdr->deps_vec, hdr->minval_vec,
+                                 (double*)c->zring.p, c->zring.cap, (double*)c->halo1.p))
+            return fail(c, WRB_E_CUDA, c->comm ? slab_comm_error(c->comm) : "halo exchange callback failed");
     } else {
         if (fuse_deq)
             wavelet_inverse((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, d_out, dtype == WRB_F32,

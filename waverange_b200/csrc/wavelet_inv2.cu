@@ -44,6 +44,11 @@ struct InvZArgs2 {
     int n0, n1, n2;                             // box extents (even)
     int pair0, npairs;                          // the slab: output pairs [pair0, pair0 + npairs)
     int zpairs;                                 // output pairs per z-segment (blockIdx.z)
+    // z-slab mode (SLAB): n2 is the GLOBAL extent of the level's box; this rank owns the pairs [own0, own0 + nown) and
+    // its symbol / coefficient / lll planes are rank-local (z-low pair p at local plane p - own0, z-high pair p at
+    // nown + p - own0).  The neighbours' boundary coefficients arrive as doubles in `halo`, seven planes of n0 x n1:
+    // low[own0-1] | high[own0-2], high[own0-1] | low[own0+nown], low[own0+nown+1] | high[own0+nown], high[own0+nown+1]
+    const double* halo; int own0, nown;
 };
 
 __device__ __forceinline__ int mirror_s2(int i, int Q)
@@ -61,7 +66,7 @@ __device__ __forceinline__ int mirror_d2(int i, int Q)
 
 // VX consecutive x positions per thread (4: aligned word loads of the symbols, 16-byte loads / stores of doubles;
 // 1: any shape and alignment).  NLAY > 0: coefficients rebuilt from NLAY symbol planes; 0: read from coef.
-template <int NLAY, int VX>
+template <int NLAY, int VX, bool SLAB>
 __global__ void __launch_bounds__(128) inv_z_kernel(InvZArgs2 a)
 {
     constexpr bool FROM_SYM = NLAY > 0;
@@ -86,33 +91,49 @@ __global__ void __launch_bounds__(128) inv_z_kernel(InvZArgs2 a)
     // raw inputs of one z step, loaded one step ahead of their use
     unsigned int qlo[NRAW], qhi[NRAW];            // VX symbols per word (VX == 1: one symbol)
     double clo[VX], chi[VX];
+    bool lo_halo = false, hi_halo = false;        // SLAB: this step's low / high coefficients came from the halo planes (doubles)
+    auto load4d = [&](const double* __restrict__ p, double (&dst)[VX]) {
+        if (VX == 4) {
+            const double2 a0 = *reinterpret_cast<const double2*>(p), a1 = *(reinterpret_cast<const double2*>(p) + 1);
+            dst[0] = a0.x; dst[1] = a0.y; dst[VX > 2 ? 2 : 0] = a1.x; dst[VX > 3 ? 3 : 0] = a1.y;
+        } else dst[0] = p[0];
+    };
     auto load_step = [&](int m) {
-        const long long pl = mirror_s2(m, q2), ph = (long long)q2 + mirror_d2(m, q2);
+        long long pl = mirror_s2(m, q2), ph = (long long)q2 + mirror_d2(m, q2);
+        bool lh = false, hh = false;
+        if (SLAB) {
+            const int gl = (int)pl, gh = (int)(ph - q2);
+            const long long hpos = x0 + (long long)y * a.n0;
+            if (gl < a.own0) { lh = true; load4d(a.halo + hpos, clo); }                                     // low[own0-1] (also stands in for own0-2: feeds no output)
+            else if (gl >= a.own0 + a.nown) { lh = true; load4d(a.halo + hpos + (long long)(3 + min(gl - a.own0 - a.nown, 1)) * zplane, clo); }
+            else pl = gl - a.own0;
+            if (gh < a.own0) { hh = true; load4d(a.halo + hpos + (long long)(1 + max(gh - (a.own0 - 2), 0)) * zplane, chi); }
+            else if (gh >= a.own0 + a.nown) { hh = true; load4d(a.halo + hpos + (long long)(5 + min(gh - a.own0 - a.nown, 1)) * zplane, chi); }
+            else ph = (long long)a.nown + gh - a.own0;
+        }
+        lo_halo = lh; hi_halo = hh;
         if (FROM_SYM) {
 #pragma unroll
             for (int l = 0; l < NRAW; l++) {
                 const uint8_t* __restrict__ sl = a.sym + (unsigned long long)l * a.lstride + pos;
                 if (VX == 4) {
-                    qhi[l] = __ldcs(reinterpret_cast<const unsigned int*>(sl + ph * a.az));
-                    if (!inl) qlo[l] = __ldcs(reinterpret_cast<const unsigned int*>(sl + pl * a.az));
+                    if (!hh) qhi[l] = __ldcs(reinterpret_cast<const unsigned int*>(sl + ph * a.az));
+                    if (!inl && !lh) qlo[l] = __ldcs(reinterpret_cast<const unsigned int*>(sl + pl * a.az));
                 } else {
-                    qhi[l] = sl[ph * a.az];
-                    if (!inl) qlo[l] = sl[pl * a.az];
+                    if (!hh) qhi[l] = sl[ph * a.az];
+                    if (!inl && !lh) qlo[l] = sl[pl * a.az];
                 }
             }
-        } else {
+        } else if (!hh) {
             const double* __restrict__ ch = a.coef + pos + ph * a.az;
             if (VX == 4) {
                 const double2 h0 = __ldcs(reinterpret_cast<const double2*>(ch)), h1 = __ldcs(reinterpret_cast<const double2*>(ch) + 1);
                 chi[0] = h0.x; chi[1] = h0.y; chi[VX > 2 ? 2 : 0] = h1.x; chi[VX > 3 ? 3 : 0] = h1.y;
             } else chi[0] = ch[0];
         }
+        if (lh) return;
         if (inl) {
-            const double* __restrict__ cl = a.lll + lpos + pl * a.lsz;
-            if (VX == 4) {
-                const double2 l0 = *reinterpret_cast<const double2*>(cl), l1 = *(reinterpret_cast<const double2*>(cl) + 1);
-                clo[0] = l0.x; clo[1] = l0.y; clo[VX > 2 ? 2 : 0] = l1.x; clo[VX > 3 ? 3 : 0] = l1.y;
-            } else clo[0] = cl[0];
+            load4d(a.lll + lpos + pl * a.lsz, clo);
         } else if (!FROM_SYM) {
             const double* __restrict__ cl = a.coef + pos + pl * a.az;
             if (VX == 4) {
@@ -140,8 +161,10 @@ __global__ void __launch_bounds__(128) inv_z_kernel(InvZArgs2 a)
         double lv[VX], hv[VX];
 #pragma unroll
         for (int v = 0; v < VX; v++) {
-            if (FROM_SYM) { hv[v] = deq(qhi, v); lv[v] = inl ? clo[v] : deq(qlo, v); }
-            else { hv[v] = chi[v]; lv[v] = clo[v]; }
+            if (FROM_SYM) {
+                hv[v] = (SLAB && hi_halo) ? chi[v] : deq(qhi, v);
+                lv[v] = (inl || (SLAB && lo_halo)) ? clo[v] : deq(qlo, v);
+            } else { hv[v] = chi[v]; lv[v] = clo[v]; }
         }
         if (m <= e1) load_step(m + 1);
         const bool out = (m - 2 >= e0);
@@ -476,8 +499,9 @@ bool inverse_two_pass_enabled()
 void inverse_level_two_pass(const double* coef, long long ay, long long az, const uint8_t* sym, unsigned long long lstride,
                             int nlay, const double* deps, const double* minval, const double* lll, void* dst,
                             int dst_is_f32, long long dsy, long long dsz, int n0, int n1, int n2, double* zb, size_t zb_bytes,
-                            cudaStream_t s, int seg_lo, int seg_hi)
+                            cudaStream_t s, int seg_lo, int seg_hi, const double* halo, int n2_global, int own0)
 {
+    // z-slab mode (halo != null): n2 counts the rank's own planes, n2_global the level's box; output pairs are local
     const int q2 = n2 / 2;
     if (seg_lo < 0) seg_lo = 0;
     if (seg_hi < 0 || seg_hi > q2) seg_hi = q2;
@@ -486,13 +510,15 @@ void inverse_level_two_pass(const double* coef, long long ay, long long az, cons
     za.coef = coef; za.ay = ay; za.az = az; za.sym = sym; za.lstride = lstride;
     for (int l = 0; l < nlay && l < kNLayMax && sym != nullptr; l++) { za.deps[l] = deps[l]; za.minval[l] = minval[l]; }
     za.lll = lll; za.lsy = n0 / 2; za.lsz = (long long)(n0 / 2) * (n1 / 2);
-    za.zb = zb; za.n0 = n0; za.n1 = n1; za.n2 = n2;
+    za.zb = zb; za.n0 = n0; za.n1 = n1; za.n2 = halo ? n2_global : n2;
+    za.halo = halo; za.own0 = own0; za.nown = q2;
     // four positions per thread need 16-byte aligned rows of doubles, 4-byte aligned rows of symbols, and quads that
     // do not straddle the low / high boundary in x
     bool vec = (n0 % 8 == 0) && (ay % 4 == 0) && (az % 4 == 0) && (reinterpret_cast<size_t>(zb) % 16 == 0);
     if (sym != nullptr) vec = vec && (lstride % 4 == 0) && (reinterpret_cast<size_t>(sym) % 4 == 0);
     else vec = vec && (reinterpret_cast<size_t>(coef) % 16 == 0) && (ay % 2 == 0) && (az % 2 == 0);
     if (lll != nullptr) vec = vec && (reinterpret_cast<size_t>(lll) % 16 == 0) && ((n0 / 2) % 2 == 0);
+    if (halo != nullptr) vec = vec && (reinterpret_cast<size_t>(halo) % 16 == 0);
     if (getenv("WRB_INV_NOVEC") != nullptr) vec = false;
     const int vx = vec ? 4 : 1;
     const int xthreads = (n0 + vx - 1) / vx;
@@ -518,15 +544,18 @@ void inverse_level_two_pass(const double* coef, long long ay, long long az, cons
     for (int p0 = seg_lo; p0 < seg_hi; p0 += sp) {
         const int np = (p0 + sp <= seg_hi) ? sp : seg_hi - p0;
         // ---- z pass: pairs [p0, p0 + np) -> slab planes 0 .. 2 np ----
-        za.pair0 = p0; za.npairs = np;
+        za.pair0 = own0 + p0; za.npairs = np;
         int zp = np;              // z-segments inside the slab only when the (x, y) positions alone cannot fill the GPU
         while (zp > 8 && (long long)xthreads * n1 * ((np + zp - 1) / zp) < 148ll * 1536) zp = (zp + 1) / 2;
         za.zpairs = zp;
         dim3 zgrid((xthreads + bx - 1) / bx, (n1 + by - 1) / by, (np + zp - 1) / zp);
 #define WRB_Z_LAUNCH(NL)                                                                            \
         do {                                                                                        \
-            if (vec) inv_z_kernel<NL, 4><<<zgrid, zblock, 0, s>>>(za);                              \
-            else inv_z_kernel<NL, 1><<<zgrid, zblock, 0, s>>>(za);                                  \
+            if (za.halo != nullptr) {                                                               \
+                if (vec) inv_z_kernel<NL, 4, true><<<zgrid, zblock, 0, s>>>(za);                    \
+                else inv_z_kernel<NL, 1, true><<<zgrid, zblock, 0, s>>>(za);                        \
+            } else if (vec) inv_z_kernel<NL, 4, false><<<zgrid, zblock, 0, s>>>(za);                \
+            else inv_z_kernel<NL, 1, false><<<zgrid, zblock, 0, s>>>(za);                           \
         } while (0)
         switch (sym != nullptr ? nlay : 0) {
         case 0: WRB_Z_LAUNCH(0); break;

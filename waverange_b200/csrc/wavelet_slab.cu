@@ -241,6 +241,11 @@ int wavelet_forward_slab(const void* src, int src_is_f32, double* coef, double* 
 }
 
 // Inverse, slab mode.  ext must hold 2 * (nzl/2 + 4) * nx * ny doubles.
+int wavelet_inverse_slab_two_pass_ok(int nx, int ny, int nz, int nzl, int levels)
+{
+    return inverse_two_pass_enabled() && wavelet_inverse_slab_fused_ok(nx, ny, nz, nzl, levels) && (nzl >> levels) >= 2;
+}
+
 int wavelet_inverse_slab_fused_ok(int nx, int ny, int nz, int nzl, int levels)
 {
     if (levels < 1 || getenv("WRB_NO_FUSED_INVERSE") != nullptr || (long long)nx * ny >= (1ll << 31)) return 0;
@@ -251,12 +256,68 @@ int wavelet_inverse_slab_fused_ok(int nx, int ny, int nz, int nzl, int levels)
     return 1;
 }
 
+// the boundary coefficients of one level as doubles, for the neighbours: planes 0..3 go down to rank-1 (low[0], low[1],
+// high[0], high[1] of my own pairs), planes 4..6 go up to rank+1 (low[last], high[last-1], high[last])
+__global__ void __launch_bounds__(128) pack_boundary_kernel(BandDequant dq, long long ay, long long az,
+                                                            const double* __restrict__ lll, long long lsy, long long lsz,
+                                                            int q0, int q1, int n0, int nl, double* __restrict__ dst, long long plane)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, t = blockIdx.z;                   // t in [0, 7)
+    if (x >= n0) return;
+    const bool high = (t == 2 || t == 3 || t >= 5);
+    const int pr = (t == 0 || t == 2) ? 0 : (t == 1 || t == 3) ? 1 : (t == 5 ? nl - 2 : nl - 1);
+    double v;
+    if (!high && lll != nullptr && x < q0 && y < q1) {
+        v = lll[x + (long long)y * lsy + (long long)pr * lsz];
+    } else {
+        const uint8_t* __restrict__ q = dq.sym + (x + (long long)y * ay + (long long)(high ? nl + pr : pr) * az);
+        v = 0.0;
+        for (int l = 0; l < dq.nlay; l++) {
+            const double tt = (double)q[(unsigned long long)l * dq.lstride] * dq.deps[l] + dq.minval[l];
+            v = (l == 0) ? tt : v + tt;
+        }
+    }
+    dst[x + (long long)y * n0 + (long long)t * plane] = v;
+}
+
 int wavelet_inverse_slab(double* coef, double* tmp, double* lllA, double* lllB, double* ext, void* out, int out_is_f32,
                          int nx, int ny, int nz, int z0, int nzl, int levels, const SlabHooks& hk, cudaStream_t s,
-                         const uint8_t* sym, unsigned long long lstride, int nlay, const double* deps, const double* minval)
+                         const uint8_t* sym, unsigned long long lstride, int nlay, const double* deps, const double* minval,
+                         double* zb, size_t zb_bytes, double* hb)
 {
     const long long ay = nx, az = (long long)nx * ny;
     const double* lll = nullptr; long long lsy = 0, lsz = 0;
+    if (sym != nullptr && zb != nullptr && hb != nullptr && zb_bytes >= (size_t)nx * ny * 16 + 256 &&
+        wavelet_inverse_slab_two_pass_ok(nx, ny, nz, nzl, levels)) {
+        // per level: the boundary coefficients of the rank's own pairs go to the neighbours as doubles (one exchange of
+        // 4 + 3 planes), then the two-pass level of wavelet_inv2.cu: streaming z kernel on the own symbol planes (halo
+        // pairs from the received planes), TMA-staged y / x tile kernel.  No band buffers, no dequantise pass.
+        BandDequant dq{};
+        dq.sym = sym; dq.lstride = lstride; dq.nlay = nlay;
+        for (int l = 0; l < nlay && l < kNLayMax; l++) { dq.deps[l] = deps[l]; dq.minval[l] = minval[l]; }
+        for (int k = levels - 1; k >= 0; k--) {
+            const int n0 = (nx + (1 << k) - 1) >> k, n1 = (ny + (1 << k) - 1) >> k;
+            const int n2l = nzl >> k, n2g = nz >> k, zg = z0 >> k;
+            const int q0 = n0 / 2, q1 = n1 / 2, nl = n2l / 2;
+            const long long plane = (long long)n0 * n1;
+            double* sendb = hb;                       // planes 0..6
+            double* halo = hb + 7 * plane;            // planes 7..13: [3 from below | 4 from above]
+            if (hk.nranks > 1) {
+                dim3 block(128, 1, 1), grid((n0 + 127) / 128, n1, 7);
+                pack_boundary_kernel<<<grid, block, 0, s>>>(dq, ay, az, lll, lsy, lsz, q0, q1, n0, nl, sendb, plane);
+                note_launch(1);
+                int rc = hk.halo(hk.user, sendb, sendb + 4 * plane, halo, halo + 3 * plane, 4ull * plane * 8, 3ull * plane * 8);
+                if (rc) return rc;
+            }
+            double* nxt = (k & 1) ? lllA : lllB;
+            inverse_level_two_pass(nullptr, ay, az, sym, lstride, nlay, deps, minval, lll, (k == 0) ? out : (void*)nxt,
+                                   (k == 0) ? out_is_f32 : 0, (k == 0) ? ay : (long long)n0, (k == 0) ? az : (long long)n0 * n1,
+                                   n0, n1, n2l, zb, zb_bytes, s, -1, -1, halo, n2g, zg / 2);
+            lll = nxt; lsy = n0; lsz = (long long)n0 * n1;
+        }
+        return 0;
+    }
     if (wavelet_inverse_slab_fused_ok(nx, ny, nz, nzl, levels)) {
         // per level: band buffers (own pairs + halo room) from the symbols or the coefficient array, two halo
         // exchanges, then ONE kernel for the z, y and x inverse lifting (wavelet_inv_fused.cu, band mode)

@@ -62,8 +62,10 @@ int wavelet_forward_slab(const void* src, int src_is_f32, double* coef, double* 
 int wavelet_inverse_slab(double* coef, double* tmp, double* lllA, double* lllB, double* ext, void* out, int out_is_f32,
                          int nx, int ny, int nz, int z0, int nzl, int levels, const SlabHooks& hk, cudaStream_t s,
                          const uint8_t* sym = nullptr, unsigned long long lstride = 0, int nlay = 0,
-                         const double* deps = nullptr, const double* minval = nullptr);
+                         const double* deps = nullptr, const double* minval = nullptr, double* zb = nullptr, size_t zb_bytes = 0,
+                         double* hb = nullptr);      // zb / hb (14 planes of nx*ny doubles): scratch of the two-pass levels
 int wavelet_inverse_slab_fused_ok(int nx, int ny, int nz, int nzl, int levels);
+int wavelet_inverse_slab_two_pass_ok(int nx, int ny, int nz, int nzl, int levels);   // no band buffers (`ext`) needed then
 
 // ---- wavelet_fused.cu ---------------------------------------------------------------------
 bool fused_forward_supported(int n0, int n1, int n2);
@@ -92,7 +94,8 @@ size_t inverse_two_pass_scratch_bytes(int nx, int ny, int nz);
 void inverse_level_two_pass(const double* coef, long long ay, long long az, const uint8_t* sym, unsigned long long lstride,
                             int nlay, const double* deps, const double* minval, const double* lll, void* dst,
                             int dst_is_f32, long long dsy, long long dsz, int n0, int n1, int n2, double* zb, size_t zb_bytes,
-                            cudaStream_t s, int seg_lo = -1, int seg_hi = -1);
+                            cudaStream_t s, int seg_lo = -1, int seg_hi = -1, const double* halo = nullptr, int n2_global = 0,
+                            int own0 = 0);          // z-slab mode: see InvZArgs2 (wavelet_inv2.cu)
 
 // ---- quant.cu -----------------------------------------------------------------------------
 // Geometry of the chunked symbol container of one layer.
