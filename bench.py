@@ -88,12 +88,11 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def synth_field(torch, n, seed, device, dtype, nm=48, expo=-5.0 / 6.0, nz_total=None, z0=0, nzl=None):
+def synth_field(torch, n, seed, device, dtype, nm=48, expo=-5.0 / 6.0, nz_total=None, z0=0, nzl=None, kmax=24):
     """Turbulence-like field: sum of nm plane waves with random integer wavevectors, random phases,
     amplitude |k|^expo, evaluated in f64 on the device slab by slab through
     separable complex tables, then rounded to `dtype`.  Deterministic for a given seed."""
     rng = np.random.default_rng(seed)
-    kmax = 24
     k = rng.integers(1, kmax + 1, size=(nm, 3)).astype(np.float64)
     k *= rng.choice([-1.0, 1.0], size=(nm, 3))
     ph = rng.uniform(0, 2 * np.pi, nm)
@@ -381,6 +380,27 @@ def run_ours(args, rank, world, local_rank):
     e2e_step = statistics.mean(e2e_ms) if e2e_ms else float('nan')
     if e2e_ms:
         assert np.array_equal(np_rec.ravel()[:4096], recon[:4096].cpu().numpy())
+    # what the host link gives each rank when all ranks copy at once (explains the e2e scaling: the ranks share the host's
+    # memory system and PCIe root ports, the codec itself scales with the device-timed value)
+    copy_gbs = None
+    if e2e_ms and slab_mode:
+        d_tmp = torch.empty_like(field)
+        t_copy = []
+        for direction in (0, 1):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                if direction == 0:
+                    d_tmp.copy_(h_field, non_blocking=True)
+                else:
+                    h_rec.copy_(d_tmp, non_blocking=True)
+            torch.cuda.synchronize()
+            t_copy.append((time.perf_counter() - t0) / 3)
+        tc = torch.tensor(t_copy, device=dev, dtype=torch.float64)
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        copy_gbs = {"h2d_per_rank_min": nbytes / tc[0].item() / 1e9, "d2h_per_rank_min": nbytes / tc[1].item() / 1e9,
+                    "note": "pinned 0.5 GB per rank, all ranks copying at the same time"}
+        del d_tmp
 
     # ---- N > 1: the chunk streams of all ranks against a single-GPU encode of the same (whole) field on rank 0 --------
     streams_equal = None
@@ -476,7 +496,8 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": world * (nbytes + int(h.ntot_enc)),
                 "d2h_bytes_per_step": world * (nbytes + int(h.ntot_enc)), "ms_per_step": e2e_step,
                 "api": "wrb_encode_host + wrb_decode_host (f32 pinned host buffers)" if world == 1 else
-                       "pinned H2D + wrb_encode_slab_device + D2H, H2D + wrb_decode_slab_device + D2H per rank"},
+                       "pinned H2D + wrb_encode_slab_device + D2H, H2D + wrb_decode_slab_device + D2H per rank",
+                "host_link": copy_gbs},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "host_wall_ms_per_step": wall_ms,

@@ -122,7 +122,8 @@ int wrb_decode_device(wrb_codec* c, void* d_field_out, int dtype, int nx, int ny
  *   halo  : neighbour exchange along z.  Send down_bytes from send_down to rank-1 and receive as many into
  *           recv_hi from rank+1; send up_bytes from send_up to rank+1 and receive as many into recv_lo from
  *           rank-1; nothing at the domain ends.  All pointers are device pointers.
- *   reduce: in-place global MIN over `count` signed 64-bit integers on the device (one all-reduce).
+ *   reduce: in-place global MIN over `count` signed 64-bit integers on the device (one all-reduce); a negative
+ *           count asks for the global SUM over -count values.
  * Both must be ordered with the codec's stream. */
 typedef int (*wrb_halo_fn)(void* user, const void* send_down, const void* send_up, void* recv_lo, void* recv_hi,
                            unsigned long long down_bytes, unsigned long long up_bytes);

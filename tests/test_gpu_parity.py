@@ -93,6 +93,25 @@ def test_range_coder_chunks_vs_oracle(codec, torch_cuda, oracle, n, chunk, kind)
     assert np.array_equal(back.cpu().numpy(), sym)
 
 
+@pytest.mark.parametrize("form", ["full", "compact"])
+def test_encoder_table_forms_are_bit_identical(codec, torch_cuda, oracle, monkeypatch, form):
+    """the encoder's two table forms (32 KB full entries / 16.5 KB cumulative counts only, chosen by grid size): both
+    must give the oracle's bytes; skewed, uniform and single-symbol data"""
+    monkeypatch.setenv("WRB_ENC_TABLES", form)
+    rng = np.random.default_rng(3)
+    n = 59999 * 5 + 123
+    for sym in (rng.integers(0, 256, n, dtype=np.uint8), np.clip(np.rint(128 + 0.7 * rng.standard_normal(n)), 0, 255).astype(np.uint8),
+                np.full(n, 255, np.uint8), np.where(rng.random(n) < 0.001, 0, 255).astype(np.uint8)):
+        d_sym = dev(torch_cuda, sym)
+        out = torch_cuda.zeros(2 * n + 65536, dtype=torch_cuda.uint8, device="cuda")
+        lens, total = codec.range_encode_device(d_sym.data_ptr(), n, L1, out.data_ptr(), out.numel())
+        blob = out[:total].cpu().numpy()
+        off = 0
+        for c, ln in enumerate(lens):
+            assert np.array_equal(blob[off:off + ln], oracle.range_encode(sym[c * L1:(c + 1) * L1])), "chunk %d" % c
+            off += ln
+
+
 def test_chunk_streams_accepted_by_reference_decoder(codec, torch_cuda, ref):
     """every chunk is a byte-valid stream for the reference's own range_decode()"""
     n = 200000

@@ -428,9 +428,10 @@ static int ensure_transform_buffers(wrb_codec* c, int nx, int ny, int nz, bool s
     return 0;
 }
 
-static int ensure_coder_buffers(wrb_codec* c, const ChunkGeom& g, int nlayers, bool need_slots, bool need_hist = true)
+static int ensure_coder_buffers(wrb_codec* c, const ChunkGeom& g, int nlayers, bool need_slots, bool need_hist = true,
+                                bool need_sym = true)
 {
-    CK(c->sym.ensure((size_t)nlayers * (((size_t)g.nchunks * g.pitch + 15) & ~(size_t)15) + 64));
+    if (need_sym) CK(c->sym.ensure((size_t)nlayers * (((size_t)g.nchunks * g.pitch + 15) & ~(size_t)15) + 64));
     if (need_hist) CK(c->hist.ensure((size_t)nlayers * g.nblocks * 256 * 4));
     if (need_slots) {
         CK(c->slots.ensure((size_t)nlayers * g.nchunks * chunk_slot_pitch(g)));
@@ -565,8 +566,8 @@ static int slab_windows(wrb_codec* c, const OrderGeom& og, int nlayers)
     const int R = og.nranks, rank = c->hooks.rank;
     const size_t ntl = (size_t)og.nx * og.ny * og.nzl;
     const size_t xs = ((ntl + 15) & ~(size_t)15) + 16;
-    size_t maxrun = 0;
-    for (int r = 0; r < R; r++) maxrun = std::max(maxrun, (size_t)(og.j0[r + 1] - og.j0[r]));
+    size_t maxrun = 0;                                                   // chunk-major padded: every chunk 16-byte aligned
+    for (int r = 0; r < R; r++) maxrun = std::max(maxrun, (size_t)(og.cb[r + 1] - og.cb[r]) * (((size_t)og.chunk_len + 15) & ~(size_t)15));
     const size_t rs = ((maxrun + 15) & ~(size_t)15) + 64;
     const unsigned long long key[4] = {og.ntot, (unsigned long long)R | ((unsigned long long)og.levels << 8) | ((unsigned long long)og.nx << 16),
                                        og.chunk_len, (unsigned long long)og.ny};
@@ -634,7 +635,7 @@ static int encode_slab_global(wrb_codec* c, const void* d_field, int dtype, int 
     int rc;
     const bool fused_fwd = !wtflag || slab_forward_all_fused(nx, ny, sg->nz_global, nzl, kWavLvl);
     if ((rc = ensure_transform_buffers(c, nx, ny, nzl, true, true, !fused_fwd, false, false))) return rc;
-    if ((rc = ensure_coder_buffers(c, gr, nlayers, true))) return rc;
+    if ((rc = ensure_coder_buffers(c, gr, nlayers, true, true, false))) return rc;         // the run lives in the exchange window
     CK(c->hist.ensure((size_t)nlayers * std::max(gq.nblocks, gr.nblocks) * 256 * 4));      // the quantiser's (unused) local histograms too
     const OrderGeom ogw = og;
     if ((rc = slab_windows(c, ogw, nlayers))) return rc;
@@ -644,17 +645,27 @@ static int encode_slab_global(wrb_codec* c, const void* d_field, int dtype, int 
     // every rank's symbol planes are complete; then my run comes straight out of the peers' windows (NVLink), lands in
     // the coder's chunk-major layout and is histogrammed per coder block on the way
     if ((rc = slab_barrier(c))) return rc;
-    const unsigned long long lstride = (unsigned long long)gr.nchunks * gr.pitch;
+    // (the two windows serve both directions: `xsym` holds the rank's local symbol planes -- written by the quantiser
+    //  here, by the exchange when decoding -- and `xrun` its run of the global sequence -- gathered here in the coder's
+    //  chunk-major layout, written by the range decoder when decoding; no further symbol buffer exists in this mode)
+    const unsigned long long lstride = c->xrun_stride;
     const unsigned long long hstride = (unsigned long long)gr.nblocks * 256;
-    gather_global_run(og, rank, c->peer_xsym, c->xsym_stride, nlayers, st->active, gr, (uint8_t*)c->sym.p, lstride,
+    uint8_t* const runp = (uint8_t*)c->xrun.p;
+    gather_global_run(og, rank, c->peer_xsym, c->xsym_stride, nlayers, st->active, gr, runp, lstride,
                       (uint32_t*)c->hist.p, hstride, s);
     if (c->timing) cudaEventRecord(c->ev[2], s);                        // "quantise" includes the exchange in this mode
     const unsigned long long sp = chunk_slot_pitch(gr);
-    range_encode_chunks((const uint8_t*)c->sym.p, lstride, (const uint32_t*)c->hist.p, hstride, gr, nlayers, st->active,
+    range_encode_chunks(runp, lstride, (const uint32_t*)c->hist.p, hstride, gr, nlayers, st->active,
                         (uint8_t*)c->slots.p, sp, (unsigned long long*)c->lens.p, (uint32_t*)c->seek.p, s);
     if (c->timing) cudaEventRecord(c->ev[3], s);
+    // the seek-point budget is decided on the coded bytes of ALL ranks (one SUM all-reduce of two values): every rank
+    // keeps the number of decoder entry points a single GPU would keep for the whole field -- a rank whose run is the
+    // highly compressible fine-scale band would otherwise keep none and decode eight times slower than the others
+    unsigned long long* gtot = (unsigned long long*)((char*)c->misc.p + 128);
+    sum_chunk_lens((const unsigned long long*)c->lens.p, gr, st, gtot, s);
+    if (c->hooks.reduce(c->hooks.user, (long long*)gtot, -2)) return fail(c, WRB_E_CUDA, c->comm ? slab_comm_error(c->comm) : "reduce callback failed");
     assemble_container((const uint8_t*)c->slots.p, sp, (const unsigned long long*)c->lens.p, (const uint32_t*)c->seek.p, gr,
-                       1, c->seek_points < 0, st, d_data_enc, cap, (unsigned long long*)c->dstoff.p, s);
+                       1, c->seek_points < 0, st, d_data_enc, cap, (unsigned long long*)c->dstoff.p, s, gtot);
     if (c->timing) cudaEventRecord(c->ev[4], s);
     CK(cudaMemcpyAsync(c->h_state, st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -977,12 +988,13 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
     const bool slab_two_pass = sg != nullptr && hdr->wlev > 0 && wavelet_inverse_slab_two_pass_ok(nx, ny, sg->nz_global, nz, (int)hdr->wlev);
     if ((rc = ensure_transform_buffers(c, nx, ny, nz, sg != nullptr, need_full, need_full, (sg == nullptr && hdr->wlev > 0) || slab_two_pass,
                                        !slab_two_pass))) return rc;
-    if ((rc = ensure_coder_buffers(c, g, nlay, false, false))) return rc;
+    if ((rc = ensure_coder_buffers(c, g, nlay, false, false, !global))) return rc;
     ChunkGeom gl = make_geom(ntot, 0, 0);                     // the local array, flat (global mode: after the exchange)
     gl.pitch = gl.chunk_len;
+    const uint8_t* symp = (const uint8_t*)c->sym.p;           // where the inverse finds the symbol planes
     if (global) {
-        CK(c->sym.ensure((size_t)nlay * ((ntot + 15) & ~15ull) + 64));
         if ((rc = slab_windows(c, og, nlay))) return rc;
+        symp = (const uint8_t*)c->xsym.p;
         if ((rc = slab_barrier(c))) return rc;                 // the peers have finished reading my run of the previous call
     }
     int* d_err = (int*)c->misc.p;
@@ -997,8 +1009,8 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
         range_decode_chunks(d_data_enc, (const unsigned long long*)c->offs.p, (const unsigned long long*)c->layoff.p, g, nlay,
                             (uint8_t*)c->xrun.p, c->xrun_stride, (unsigned long long)hdr->ntot_enc, d_err, s);
         if ((rc = slab_barrier(c))) return rc;
-        lstride = (ntot + 15ull) & ~15ull;
-        scatter_local_planes(og, c->hooks.rank, c->peer_xrun, c->xrun_stride, nlay, (uint8_t*)c->sym.p, lstride, s);
+        lstride = c->xsym_stride;
+        scatter_local_planes(og, c->hooks.rank, c->peer_xrun, c->xrun_stride, nlay, (uint8_t*)c->xsym.p, lstride, s);
         g = gl;
     } else {
         range_decode_chunks(d_data_enc, (const unsigned long long*)c->offs.p, (const unsigned long long*)c->layoff.p, g, nlay,
@@ -1009,12 +1021,12 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
     // needed without a transform, for extent-1 z, and in slab mode (its band buffers are built from coef).
     const bool slab_fused = sg != nullptr && hdr->wlev > 0 && wavelet_inverse_slab_fused_ok(nx, ny, sg->nz_global, nz, (int)hdr->wlev);
     const bool fuse_deq = slab_fused || (sg == nullptr && hdr->wlev > 0 && nz >= (1 << hdr->wlev) && getenv("WRB_NO_FUSED_DEQUANT") == nullptr);
-    if (!fuse_deq) dequantise((const uint8_t*)c->sym.p, lstride, g, nlay, hdr->deps_vec, hdr->minval_vec, (double*)c->coef.p, s);
+    if (!fuse_deq) dequantise(symp, lstride, g, nlay, hdr->deps_vec, hdr->minval_vec, (double*)c->coef.p, s);
     if (c->timing) cudaEventRecord(c->ev[3], s);
     if (sg != nullptr && hdr->wlev > 0) {
         if (wavelet_inverse_slab((double*)c->coef.p, (double*)c->tmp.p, (double*)c->lllA.p, (double*)c->lllB.p, (double*)c->ext.p,
                                  d_out, dtype == WRB_F32, nx, ny, sg->nz_global, sg->z0, nz, (int)hdr->wlev, c->hooks, s,
-                                 slab_fused ? (const uint8_t*)c->sym.p : nullptr, lstride, nlay, hdr->deps_vec, hdr->minval_vec,
+                                 slab_fused ? symp : nullptr, lstride, nlay, hdr->deps_vec, hdr->minval_vec,
                                  (double*)c->zring.p, c->zring.cap, (double*)c->halo1.p))
             return fail(c, WRB_E_CUDA, c->comm ? slab_comm_error(c->comm) : "halo exchange callback failed");
     } else {

@@ -37,9 +37,12 @@ constexpr uint32_t kTerm = 0x8000u;         // raw-entry flag: written by done_e
 
 unsigned long long chunk_slot_pitch(const ChunkGeom& g)
 {
-    // worst case 2 B/symbol + 513 B per coder block + framing (wrappers.cpp:79 uses 2*BLOCKSIZE+1000),
-    // two bytes of scratch per output byte (raw 9-bit entries)
-    unsigned long long p = 2 * (2 * g.chunk_len + 1024ull * (g.blocks_per_chunk + 1));
+    // Raw 16-bit entries, one per output byte.  Upper bound of a block's output: a symbol of count c in a block of bs
+    // symbols costs log2(range / (r * c)) bits with r = floor(range / bs) >= 2^23 / 60000 > 139, i.e. at most
+    // log2(bs / c) + log2(1 + 1/139) < log2(bs / c) + 0.0104 bits, and sum log2(bs / c) <= 8 bs for 256 symbols: a block
+    // is at most bs * 8.0104 / 8 bytes + its 512-byte count table + markers and flush.  (The reference sizes its buffer
+    // 2 * BLOCKSIZE + 1000, wrappers.cpp:79; half of that is never reached.)
+    unsigned long long p = 2 * (g.chunk_len + g.chunk_len / 512 + 640ull * g.blocks_per_chunk + 64ull);
     return (p + 15ull) & ~15ull;
 }
 
@@ -141,7 +144,13 @@ __device__ __forceinline__ void enc_symbol(Enc& e, uint32_t ent, bool last, cons
     e.range = last ? rs - t : r * (ent & 0xFFFFu);
 }
 
-// grid (ceil(nchunks/32), layers), block 32: lane == chunk
+// grid (ceil(nchunks/32), layers), block 32: lane == chunk.
+// COMPACT: the per-lane tables hold 16-bit cumulative counts only, two per word ([symbol pair][lane]: conflict-free like
+// the full form) -- 16.5 KB per warp instead of 32 KB, so twice the warps fit an SM; an entry (cum, count) is then two
+// loads and a subtraction, ~6 instructions more per symbol, all off the recurrence.  The full form while every warp of
+// the grid is resident anyway (the 512^3 benchmark: one warp per scheduler, the recurrence is what counts), the compact
+// form for larger grids, where the resident warps per scheduler are what counts (1024^3 f64, 5 layers: 2797 warps).
+template <bool COMPACT>
 __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restrict__ sym,
                                                           unsigned long long sym_layer_stride,
                                                           const uint32_t* __restrict__ hist,
@@ -153,7 +162,7 @@ __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restr
 {
     const int layer = blockIdx.y;
     if (active != nullptr && !active[layer]) return;
-    __shared__ uint32_t tab[256 * 32];            // [symbol][lane] = cum << 16 | count
+    __shared__ uint32_t tab[(COMPACT ? 129 : 256) * 32];      // [symbol][lane] = cum << 16 | count; COMPACT: [symbol / 2][lane] = cum pair
     const unsigned int lane = threadIdx.x;
     const unsigned int chunk = blockIdx.x * 32 + lane;
     if (chunk >= g.nchunks) return;
@@ -170,6 +179,13 @@ __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restr
     e.raw[0] = 0;                                                          // lead byte
     e.pos = 1;
     const uint32_t* __restrict__ tl = tab + lane;
+    auto table_entry = [&](uint32_t c) -> uint32_t {              // cum << 16 | count of symbol c
+        if (!COMPACT) return tl[c * 32];
+        const uint32_t w0 = tl[(c >> 1) * 32], w1 = tl[((c + 1) >> 1) * 32];
+        const uint32_t lo = (c & 1u) ? (w0 >> 16) : (w0 & 0xFFFFu);                  // cum[c]
+        const uint32_t hi = (c & 1u) ? (w1 & 0xFFFFu) : (w0 >> 16);                  // cum[c + 1]
+        return (lo << 16) | (hi - lo);
+    };
     const uint32_t sub16 = g.sub_len >> 4;        // seek interval in 16-symbol groups (0: none)
     unsigned long long done = 0;
     for (;;) {                                                              // wrappers.cpp:85-128
@@ -179,14 +195,20 @@ __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restr
         for (int s = 0; s < 256; s += 4) {
             const uint4 c4 = *reinterpret_cast<const uint4*>(hrow + s);
             const uint32_t cc[4] = {c4.x, c4.y, c4.z, c4.w};
+            uint32_t pairw = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 enc_short(e, cc[k]);
-                tab[(s + k) * 32 + lane] = (cum << 16) | cc[k];
+                if (COMPACT) {
+                    if (k & 1) tab[((s + k) >> 1) * 32 + lane] = pairw | (cum << 16); else pairw = cum;
+                } else {
+                    tab[(s + k) * 32 + lane] = (cum << 16) | cc[k];
+                }
                 cum += cc[k];
                 if (cc[k]) lastsym = s + k;
             }
         }
+        if (COMPACT) tab[128 * 32 + lane] = cum;                             // cum[256] = block size (< 2^16)
         enc_renorm(e);                            // up to three shifts may be pending after a raw short
         const Magic mg = make_magic(bs);
         const uint4* __restrict__ p = reinterpret_cast<const uint4*>(in + done);
@@ -212,7 +234,7 @@ __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restr
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 cs[k] = (ww[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
-                ent[k] = tl[cs[k] * 32];
+                ent[k] = table_entry(cs[k]);
             }
 #pragma unroll
             for (int k = 0; k < 16; k++) enc_symbol<ONE>(e, ent[k], cs[k] == lastsym, mg);
@@ -226,7 +248,7 @@ __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restr
             }
             for (uint32_t k = 0; k < rem; k++) {
                 const uint32_t c = (ww[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
-                enc_symbol<ONE>(e, tl[c * 32], c == lastsym, mg);
+                enc_symbol<ONE>(e, table_entry(c), c == lastsym, mg);
             }
         }
         for (; g.nseek && nsk < g.nseek; nsk++) { sk[nsk * 3 + 0] = 0; sk[nsk * 3 + 1] = 0; sk[nsk * 3 + 2] = 0; }
@@ -247,8 +269,14 @@ void range_encode_chunks(const uint8_t* sym, unsigned long long sym_layer_stride
                          cudaStream_t s)
 {
     dim3 grid((g.nchunks + 31) / 32, nlayers, 1);
-    range_encode_kernel<<<grid, 32, 0, s>>>(sym, sym_layer_stride, hist, hist_layer_stride, g, active, slots, slot_pitch,
-                                            lens, seek);
+    const char* e = getenv("WRB_ENC_TABLES");                        // "full" / "compact": force a form (tests, A/B timing)
+    bool compact = (unsigned long long)grid.x * grid.y > 148ull * 6;    // the full form keeps 6-7 warps per SM resident (32 KB each)
+    if (e && *e == 'f') compact = false;
+    if (e && *e == 'c') compact = true;
+    if (compact)
+        range_encode_kernel<true><<<grid, 32, 0, s>>>(sym, sym_layer_stride, hist, hist_layer_stride, g, active, slots, slot_pitch, lens, seek);
+    else
+        range_encode_kernel<false><<<grid, 32, 0, s>>>(sym, sym_layer_stride, hist, hist_layer_stride, g, active, slots, slot_pitch, lens, seek);
     note_launch(1);
 }
 
@@ -281,10 +309,32 @@ __host__ __device__ inline unsigned long long container_header_bytes(const Chunk
 // the reference's layer streams whatever the data.
 constexpr double kSeekBudget = 0.0085;
 
+__global__ void __launch_bounds__(1024) sum_lens_kernel(const unsigned long long* __restrict__ lens, ChunkGeom g, const DevState* st,
+                                                        unsigned long long* __restrict__ out)
+{
+    __shared__ unsigned long long s_part[1024];
+    const int t = threadIdx.x;
+    const int nlay = st->nlay;
+    unsigned long long sum = 0;
+    for (int l = 0; l < nlay; l++)
+        for (unsigned int c = t; c < g.nchunks; c += 1024) sum += lens[(unsigned long long)l * g.nchunks + c];
+    s_part[t] = sum;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) { if (t < o) s_part[t] += s_part[t + o]; __syncthreads(); }
+    if (t == 0) { out[0] = s_part[0]; out[1] = (unsigned long long)g.nchunks * (unsigned long long)(nlay > 0 ? nlay : 0); }
+}
+
+void sum_chunk_lens(const unsigned long long* lens, const ChunkGeom& g, const DevState* st, unsigned long long* out, cudaStream_t s)
+{
+    sum_lens_kernel<<<1, 1024, 0, s>>>(lens, g, st, out);
+    note_launch(1);
+}
+
 __global__ void __launch_bounds__(1024) assemble_scan_kernel(const unsigned long long* __restrict__ lens, ChunkGeom g,
                                                              int chunked, int seek_auto, DevState* st,
                                                              uint8_t* __restrict__ blob, unsigned long long cap,
-                                                             unsigned long long* __restrict__ dst_off)
+                                                             unsigned long long* __restrict__ dst_off,
+                                                             const unsigned long long* __restrict__ gtot)
 {
     __shared__ unsigned long long s_part[1024];
     __shared__ unsigned long long s_base;
@@ -302,8 +352,8 @@ __global__ void __launch_bounds__(1024) assemble_scan_kernel(const unsigned long
         __syncthreads();
         for (int o = 512; o > 0; o >>= 1) { if (t < o) s_part[t] += s_part[t + o]; __syncthreads(); }
         if (t == 0) {
-            const unsigned long long chunks = (unsigned long long)g.nchunks * (unsigned long long)(nlay > 0 ? nlay : 1);
-            const double budget = kSeekBudget * (double)s_part[0];
+            const unsigned long long chunks = gtot ? gtot[1] : (unsigned long long)g.nchunks * (unsigned long long)(nlay > 0 ? nlay : 1);
+            const double budget = kSeekBudget * (double)(gtot ? gtot[0] : s_part[0]);
             unsigned int keep = g.nseek;
             while (keep > 0 && (double)(chunks * (4ull + (unsigned long long)kSeekBytes * keep)) > budget) keep = (keep - 1) / 2;
             s_keep = keep;
@@ -417,9 +467,9 @@ __global__ void __launch_bounds__(256) assemble_copy_kernel(const uint8_t* __res
 
 void assemble_container(const uint8_t* slots, unsigned long long slot_pitch, const unsigned long long* lens,
                         const uint32_t* seek, const ChunkGeom& g, int chunked, int seek_auto, DevState* st, uint8_t* blob,
-                        unsigned long long cap, unsigned long long* dst_off, cudaStream_t s)
+                        unsigned long long cap, unsigned long long* dst_off, cudaStream_t s, const unsigned long long* gtot)
 {
-    assemble_scan_kernel<<<1, 1024, 0, s>>>(lens, g, chunked, seek_auto, st, blob, cap, dst_off);
+    assemble_scan_kernel<<<1, 1024, 0, s>>>(lens, g, chunked, seek_auto, st, blob, cap, dst_off, gtot);
     dim3 grid(g.nchunks, kNLayMax, 1);
     assemble_copy_kernel<<<grid, 256, 0, s>>>(slots, slot_pitch, lens, dst_off, seek, g, chunked, st, blob);
     note_launch(2);

@@ -23,7 +23,7 @@ namespace wrb {
 // the few NCCL declarations used (nccl.h: ncclUniqueId :38, data types :278-290, reduction ops :260-266)
 struct NcclUniqueId { char internal[128]; };
 typedef void* NcclComm;
-enum { kNcclUint8 = 1, kNcclInt64 = 4, kNcclMin = 3 };
+enum { kNcclUint8 = 1, kNcclInt64 = 4, kNcclSum = 0, kNcclMin = 3 };
 
 struct NcclApi {
     void* lib = nullptr;
@@ -147,12 +147,13 @@ int slab_comm_halo(void* user, const void* send_down, const void* send_up, void*
     return 0;
 }
 
-// ReduceFn: in-place all-reduce(MIN) of `count` int64 values
+// ReduceFn: in-place all-reduce of |count| int64 values: MIN for count > 0, SUM for count < 0
 int slab_comm_reduce(void* user, long long* d_buf, int count)
 {
     SlabComm* sc = (SlabComm*)user;
     NcclApi* a = nccl_api();
-    int rc = a->AllReduce(d_buf, d_buf, (size_t)count, kNcclInt64, kNcclMin, sc->comm, *sc->stream);
+    int rc = a->AllReduce(d_buf, d_buf, (size_t)(count < 0 ? -count : count), kNcclInt64, count < 0 ? kNcclSum : kNcclMin, sc->comm,
+                          *sc->stream);
     if (rc) return nccl_fail(sc, rc, "ncclAllReduce");
     sc->reduce_calls++;
     return 0;

@@ -37,7 +37,8 @@ void wavelet_yx_inverse_passes(const double* src, double* scratch, long long ay,
 //           from rank+1; send `up_bytes` from send_up to rank+1 and receive as many into recv_lo from rank-1.  Nothing is
 //           sent or received at the domain ends.  (Forward lifting: up = my last 4 planes, down = my first 3.)
 //   reduce: in-place global MIN over `count` signed 64-bit integers (the codec packs min keys and
-//           complemented max keys into one buffer so a single all-reduce(MIN) serves both)
+//           complemented max keys into one buffer so a single all-reduce(MIN) serves both); count < 0: global SUM
+//           over -count values (the coded bytes of all ranks, for the container's seek-point budget)
 // Both are enqueued on / ordered with the codec's stream and return 0 on success.
 typedef int (*HaloFn)(void* user, const void* send_down, const void* send_up, void* recv_lo, void* recv_hi,
                       unsigned long long down_bytes, unsigned long long up_bytes);
@@ -142,9 +143,14 @@ void range_encode_chunks(const uint8_t* sym, unsigned long long sym_layer_stride
                          cudaStream_t s);
 // seek_auto: the container keeps as few of the g.nseek recorded seek points as the decoder needs and the size budget
 // allows (rangecoder.cu: kSeekLaneTarget, kSeekBudget); the count goes into st->nseek_keep and the layer headers
+// gtot != null (z-slab mode, global symbol order): [0] = coded bytes of ALL ranks, [1] = chunk streams of all ranks; the
+// seek-point decision is then the one a single GPU makes for the whole field, and the same on every rank
 void assemble_container(const uint8_t* slots, unsigned long long slot_pitch, const unsigned long long* lens,
                         const uint32_t* seek, const ChunkGeom& g, int chunked, int seek_auto, DevState* st, uint8_t* blob,
-                        unsigned long long cap, unsigned long long* dst_off, cudaStream_t s);
+                        unsigned long long cap, unsigned long long* dst_off, cudaStream_t s,
+                        const unsigned long long* gtot = nullptr);
+// my coded bytes and chunk streams (active layers) -> out[0], out[1]
+void sum_chunk_lens(const unsigned long long* lens, const ChunkGeom& g, const DevState* st, unsigned long long* out, cudaStream_t s);
 void parse_container(const uint8_t* blob, const ChunkGeom& g, int chunked, int nlay, const unsigned long long* lay_off,
                      unsigned long long* offs, int* error, cudaStream_t s);
 void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, const unsigned long long* lay_off,

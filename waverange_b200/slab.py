@@ -112,9 +112,9 @@ class DistHooks:
                 r.wait()
         self.halo_bytes += sum(op.tensor.numel() for op in ops if op.op == dist.irecv)
 
-    def reduce_min(self, t):
-        """t: int64 tensor, reduced in place with MIN over the group (a single collective)"""
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+    def reduce_min(self, t, total=False):
+        """t: int64 tensor, reduced in place with MIN (total: SUM) over the group (a single collective)"""
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM if total else self.dist.ReduceOp.MIN, group=self.group)
 
     def _halo(self, user, send_down, send_up, recv_lo, recv_hi, down_bytes, up_bytes):
         try:
@@ -127,7 +127,7 @@ class DistHooks:
 
     def _reduce(self, user, pbuf, count):
         try:
-            self.reduce_min(_tensor_from_ptr(self.torch, pbuf, 8 * count, self.cuda).view(self.torch.int64))
+            self.reduce_min(_tensor_from_ptr(self.torch, pbuf, 8 * abs(count), self.cuda).view(self.torch.int64), total=count < 0)
             return 0
         except Exception as e:
             self.error = e
@@ -162,11 +162,11 @@ class LocalGroup:
             return 0
 
         def reduce(user, pbuf, count):
-            t = _tensor_from_ptr(torch, pbuf, 8 * count, True).view(torch.int64)
+            t = _tensor_from_ptr(torch, pbuf, 8 * abs(count), True).view(torch.int64)
             torch.cuda.synchronize()
             self.slots[rank] = t
             self.barrier.wait()
-            mn = torch.stack(list(self.slots)).min(dim=0).values
+            mn = torch.stack(list(self.slots)).sum(dim=0) if count < 0 else torch.stack(list(self.slots)).min(dim=0).values
             torch.cuda.synchronize()
             self.barrier.wait()                      # everyone has read before anyone writes
             t.copy_(mn)
