@@ -1006,11 +1006,24 @@ static int decode_impl(wrb_codec* c, void* d_out, int dtype, int nx, int ny, int
     unsigned long long lstride = ((unsigned long long)g.nchunks * g.pitch + 15ull) & ~15ull;
     if (global) {
         // my run is decoded into the exchange window; then every rank gathers its local planes from the peers' runs
+        static const bool dbg = getenv("WRB_DEBUG_TIMING") != nullptr;      // development: split this stage on stderr
+        cudaEvent_t de[4] = {nullptr, nullptr, nullptr, nullptr};
+        if (dbg) { for (auto& e : de) cudaEventCreate(&e); cudaEventRecord(de[0], s); }
         range_decode_chunks(d_data_enc, (const unsigned long long*)c->offs.p, (const unsigned long long*)c->layoff.p, g, nlay,
                             (uint8_t*)c->xrun.p, c->xrun_stride, (unsigned long long)hdr->ntot_enc, d_err, s);
+        if (dbg) cudaEventRecord(de[1], s);
         if ((rc = slab_barrier(c))) return rc;
+        if (dbg) cudaEventRecord(de[2], s);
         lstride = c->xsym_stride;
         scatter_local_planes(og, c->hooks.rank, c->peer_xrun, c->xrun_stride, nlay, (uint8_t*)c->xsym.p, lstride, s);
+        if (dbg) {
+            cudaEventRecord(de[3], s);
+            cudaEventSynchronize(de[3]);
+            float t[3];
+            for (int i = 0; i < 3; i++) cudaEventElapsedTime(&t[i], de[i], de[i + 1]);
+            fprintf(stderr, "[wrb rank %d] decode: range_decode %.3f ms, barrier %.3f ms, scatter %.3f ms (nseek %u)\n", c->hooks.rank, t[0], t[1], t[2], g.nseek);
+            for (auto& e : de) cudaEventDestroy(e);
+        }
         g = gl;
     } else {
         range_decode_chunks(d_data_enc, (const unsigned long long*)c->offs.p, (const unsigned long long*)c->layoff.p, g, nlay,
