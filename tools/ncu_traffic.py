@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""profiles/traffic_<commit>.json from an `ncu --set full` (or --metrics dram__bytes_*) CSV of ONE compress of the benchmark
+r"""profiles/traffic_<commit>.json from an `ncu --set full` (or --metrics dram__bytes_*) CSV of ONE compress of the benchmark
 workload: the DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the forward-transform and quantise kernels, the
 scope bench.py's `roofline` is quoted on.  bench.py prints the figure only while the kernel sources it was captured from
 (kernels_sha) are unchanged.
