@@ -577,7 +577,7 @@ __device__ __forceinline__ uint32_t dec_short(Dec& d)
     return t;
 }
 
-constexpr int kDecVariantDefault = 1;     // bit 0: lazy stream loads (see range_decode_kernel)
+constexpr int kDecVariantDefault = 3;     // bit 0: lazy stream loads, bit 1: L1 prefetch of the stream two sectors ahead (see range_decode_kernel)
 // Table footprint per chunk decides how many chunks an SM can hold (227 KB of shared memory), and with one or two lanes
 // per chunk that is what bounds the decoder.  Two forms: compact (16-bit cumulative counts only -- a count is the
 // difference of two neighbours -- and 128-wide LUT buckets: 1 KB per chunk) and fast (cum/count entry pairs, 64-wide
@@ -617,7 +617,7 @@ static bool decode_uses_pair_tables(unsigned int nsub, unsigned long long blocks
 //   * symbols leave as 32-bit words (groups of four), bytes only for a ragged head/tail.
 // LAZY (WRB_DEC_VARIANT bit 0, for A/B timing; both bit-identical): a new stream word is fetched (predicated) only
 // by the lanes that crossed a word boundary, one word ahead of its use, instead of two 32-sector loads per symbol.
-template <int NSUB, bool LAZY, bool PAIR>
+template <int NSUB, bool LAZY, bool PAIR, bool PF>
 __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restrict__ blob,
                                                           const unsigned long long* __restrict__ offs,
                                                           const unsigned long long* __restrict__ lay_off, ChunkGeom g,
@@ -760,6 +760,10 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
                 // touched four stream bytes later, so even an L1 miss (one per 32-byte sector and lane, i.e. every few
                 // symbols somewhere in the warp) is off the dependency chain.
                 if ((an ^ a) & 4u) { w0 = w1; w1 = w2; w2 = ldw((an >> 2) + 2); }
+                // every lane reads its own stream, so the first touch of a 32-byte sector is an L2 round trip for the whole
+                // warp (r2 profile: 19 % of the loop's stall samples are long-scoreboard waits on these words): pull the
+                // sector after next into L1 when a sector boundary is crossed
+                if (PF && ((an ^ a) & 32u)) asm volatile("prefetch.global.L1 [%0];" :: "l"(wbase + min((an >> 2) + 16u, wmax)));
             } else {
                 if ((an ^ a) & 0x80u) asm volatile("prefetch.global.L1 [%0];" :: "l"(wbase + min((an >> 2) + 64, wmax)));
                 w0 = ldw(an >> 2);
@@ -789,20 +793,26 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
                 uint32_t ent = adv ? e.y : e.x;
                 s += adv ? 1u : 0u;
                 if (adv) {                        // rare: more than one step from the bucket's first symbol
-                    const uint32_t nx = tl[(s + 1) * (CPW * TW)];
-                    if (s < lastsym && help * (nx >> 16) <= V) {
-                        // Third or later symbol of its bucket: where many symbols have small counts a bucket holds a dozen of
-                        // them, and a linear scan costs every lane of the warp the longest scan among its 32 lanes at every
-                        // symbol (measured: 5.4 ms instead of 2.0 for such a run).  Binary search for the largest symbol whose
-                        // cumulative count does not exceed cf = V / help; it lies before the first symbol of the bucket after
-                        // next (the estimate q is cf or cf - 1).
-                        uint32_t lo = s + 1, hi = min(lastsym, (uint32_t)ll[((q >> kLutShift) + 2) * CPW]);
-                        while (lo < hi) {
-                            const uint32_t mid = (lo + hi + 1) >> 1;
-                            if (help * (tl[mid * (CPW * TW)] >> 16) <= V) lo = mid; else hi = mid - 1;
+                    // A few linear steps (the common case where a bucket holds three or four symbols), then a binary search:
+                    // where many symbols have small counts a bucket holds a dozen of them, and a linear scan costs every
+                    // lane of the warp the longest scan among its 32 lanes at every symbol (measured: a run of such data
+                    // decoded in 5.4 ms instead of 2.0).  The search looks for the largest symbol whose cumulative count
+                    // does not exceed cf = V / help; it lies before the first symbol of the bucket after next (q is cf or
+                    // cf - 1).
+                    uint32_t nx = tl[(s + 1) * (CPW * TW)];
+                    int steps = 0;
+                    while (s < lastsym && help * (nx >> 16) <= V) {
+                        if (++steps > 2) {
+                            uint32_t lo = s + 1, hi = min(lastsym, (uint32_t)ll[((q >> kLutShift) + 2) * CPW]);
+                            while (lo < hi) {
+                                const uint32_t mid = (lo + hi + 1) >> 1;
+                                if (help * (tl[mid * (CPW * TW)] >> 16) <= V) lo = mid; else hi = mid - 1;
+                            }
+                            s = lo;
+                            ent = tl[s * (CPW * TW)];
+                            break;
                         }
-                        s = lo;
-                        ent = tl[s * (CPW * TW)];
+                        s++; ent = nx; nx = tl[(s + 1) * (CPW * TW)];
                     }
                 }
                 // (testing help * (cum + count) of the chosen entry instead -- no load, branch rarely taken -- measured
@@ -815,15 +825,22 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
                 lt = adv ? c1 : c0;
                 uint32_t nx = adv ? c2 : c1;
                 s += adv ? 1u : 0u;
-                if (adv && s < lastsym && help * nx <= V) {       // third or later symbol of its bucket: binary search (see above)
-                    uint32_t lo = s + 1, hi = min(lastsym, (uint32_t)ll[((q >> kLutShift) + 2) * CPW]);
-                    while (lo < hi) {
-                        const uint32_t mid = (lo + hi + 1) >> 1;
-                        if (help * (uint32_t)cum16[col + mid * CPW] <= V) lo = mid; else hi = mid - 1;
+                if (adv) {                        // a few linear steps, then a binary search (see above)
+                    int steps = 0;
+                    while (s < lastsym && help * nx <= V) {
+                        if (++steps > 2) {
+                            uint32_t lo = s + 1, hi = min(lastsym, (uint32_t)ll[((q >> kLutShift) + 2) * CPW]);
+                            while (lo < hi) {
+                                const uint32_t mid = (lo + hi + 1) >> 1;
+                                if (help * (uint32_t)cum16[col + mid * CPW] <= V) lo = mid; else hi = mid - 1;
+                            }
+                            s = lo;
+                            lt = cum16[col + s * CPW];
+                            nx = cum16[col + (s + 1) * CPW];
+                            break;
+                        }
+                        s++; lt = nx; nx = cum16[col + (s + 1) * CPW];
                     }
-                    s = lo;
-                    lt = cum16[col + s * CPW];
-                    nx = cum16[col + (s + 1) * CPW];
                 }
                 sy = nx - lt;
             }
@@ -873,20 +890,21 @@ void range_decode_chunks(const uint8_t* blob, const unsigned long long* offs, co
     // lazy stream loads with one word of lookahead beat two 32-sector loads per symbol at every lane count
     // (512^3, 1 / 3 / 7 seek points: 12.4 vs 13.1, 5.01 vs 5.59, 2.67 vs 3.11 ms)
     const char* e = getenv("WRB_DEC_VARIANT");
-    const bool lazy = ((e && *e) ? atoi(e) : kDecVariantDefault) & 1;
+    const int variant = (e && *e) ? atoi(e) : kDecVariantDefault;
+    const bool lazy = variant & 1, pf = (variant & 2) != 0;
     const bool pair = decode_uses_pair_tables(nsub, (unsigned long long)grid.x * grid.y);
     const int smem = dec_table_bytes(pair) * (int)cpw;
-#define WRB_DEC_LAUNCH(NS, V, P)                                                                                       \
+#define WRB_DEC_LAUNCH(NS, V, P, F)                                                                                       \
     do {                                                                                                               \
         /* the fast form with one lane per chunk needs more than the 48 KB default; the attribute is per device */      \
         static DeviceOnce once;                                                                                        \
-        once.run([] { cudaFuncSetAttribute(range_decode_kernel<NS, V, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }); \
-        range_decode_kernel<NS, V, P><<<grid, 32, smem, s>>>(blob, offs, lay_off, g, sym, sym_layer_stride, blob_len, error); \
+        once.run([] { cudaFuncSetAttribute(range_decode_kernel<NS, V, P, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }); \
+        range_decode_kernel<NS, V, P, F><<<grid, 32, smem, s>>>(blob, offs, lay_off, g, sym, sym_layer_stride, blob_len, error); \
     } while (0)
 #define WRB_DEC_VARIANTS(NS)                                                                                 \
     do {                                                                                                     \
-        if (pair) { if (lazy) WRB_DEC_LAUNCH(NS, true, true); else WRB_DEC_LAUNCH(NS, false, true); }        \
-        else      { if (lazy) WRB_DEC_LAUNCH(NS, true, false); else WRB_DEC_LAUNCH(NS, false, false); }      \
+        if (pair) { if (!lazy) WRB_DEC_LAUNCH(NS, false, true, false); else if (pf) WRB_DEC_LAUNCH(NS, true, true, true); else WRB_DEC_LAUNCH(NS, true, true, false); }        \
+        else      { if (!lazy) WRB_DEC_LAUNCH(NS, false, false, false); else if (pf) WRB_DEC_LAUNCH(NS, true, false, true); else WRB_DEC_LAUNCH(NS, true, false, false); }      \
     } while (0)
     switch (nsub) {
     case 1: WRB_DEC_VARIANTS(1); break;

@@ -14,6 +14,7 @@
 // Segments restart the z pipeline two pairs early (the lifting stencil reaches 4 samples back), so
 // any segmentation gives bit-identical results.  Requires even box extents >= 8; other shapes take
 // the general three-pass path.
+#include <cstdlib>
 #include "wr_common.cuh"
 #include "wr_kernels.h"
 
@@ -58,7 +59,7 @@ __device__ __forceinline__ int mirror_idx(int i, int n)
 __device__ __forceinline__ void track_ext(float v, float& mn, float& mx) { mn = fminf(mn, v); mx = fmaxf(mx, v); }
 __device__ __forceinline__ void track_ext(double v, double& mn, double& mx) { mn = dmin2(mn, v); mx = dmax2(mx, v); }
 
-constexpr int FTP = FTX + 2;                                        // row pitch of the input tile (73: odd)
+// (row pitch of the input tile: template parameter PITCH of the kernel, 73 = FTX + 2: odd)
 constexpr int FSLOTS = (FTY * FTX + FTHREADS - 1) / FTHREADS;       // tile elements per thread (7)
 
 // For even line lengths the reference's line-end formulas (waveletcdf97_3d.c:113,116,121,124) are what
@@ -70,9 +71,13 @@ constexpr int FSLOTS = (FTY * FTX + FTHREADS - 1) / FTHREADS;       // tile elem
 // Everything that does not change from plane to plane is computed once per thread: the (mirrored) global
 // offset and the shared-memory offset of its FSLOTS tile elements, the in-plane offsets and masks of its
 // eight outputs.  Per plane a load is then one IMAD.WIDE + LDG and a store one IMAD.WIDE + STG.
-template <class TIN, bool TRACK_IN>
+// PITCH: row pitch of the input tile in doubles.  73 (odd) is what runs; 72 is kept as a measurement variant
+// (WRB_FWD_PITCH=72): it is the densest pitch a TMA box could deliver (box rows are multiples of 16 bytes, so the pitch of a
+// TMA-written tile of doubles is even) and shows what the x-lifting -- consecutive lanes on consecutive ROWS -- pays for it.
+template <class TIN, bool TRACK_IN, int PITCH = FTX + 2>
 __global__ void __launch_bounds__(FTHREADS, 2) fwd_level_fused_kernel(FusedFwdArgs a)
 {
+    constexpr int FTP = PITCH;
     // odd row pitches: the x-lifting tasks run with consecutive lanes on consecutive ROWS, so an odd
     // pitch (in doubles) spreads them over the banks; the y-lifting reads run along a row
     __shared__ double tin[FTY * FTP];           // input tile incl. halo
@@ -241,6 +246,18 @@ void fused_forward_level(const void* src, int src_is_f32, long long ssy, long lo
     a.zpairs = zp;
     dim3 grid(gx, gy, (m2 + zp - 1) / zp);
     const bool track = in_min != nullptr;
+    const char* pe = getenv("WRB_FWD_PITCH");
+    if (pe && atoi(pe) == 72) {                                  // measurement variant, see the kernel's comment
+        if (src_is_f32) {
+            if (track) fwd_level_fused_kernel<float, true, 72><<<grid, FTHREADS, 0, s>>>(a);
+            else fwd_level_fused_kernel<float, false, 72><<<grid, FTHREADS, 0, s>>>(a);
+        } else {
+            if (track) fwd_level_fused_kernel<double, true, 72><<<grid, FTHREADS, 0, s>>>(a);
+            else fwd_level_fused_kernel<double, false, 72><<<grid, FTHREADS, 0, s>>>(a);
+        }
+        note_launch(1);
+        return;
+    }
     if (src_is_f32) {
         if (track) fwd_level_fused_kernel<float, true><<<grid, FTHREADS, 0, s>>>(a);
         else fwd_level_fused_kernel<float, false><<<grid, FTHREADS, 0, s>>>(a);
