@@ -11,6 +11,7 @@
 // coder block the symbol belongs to.  Layer parameters live in device memory (DevState), so the
 // host never waits between layers; layers after the terminating one exit immediately.
 #include <cfloat>
+#include <type_traits>
 #include "wr_common.cuh"
 #include "wr_kernels.h"
 
@@ -182,13 +183,21 @@ __global__ void __launch_bounds__(kQThreads, (LAYER <= 2) ? 3 : 2) quantise_kern
     const unsigned int mine = (tid & 63) * 4 + (tid >> 6);      // < 256: byte 0 of a counter's offset, the bin is byte 1
     const double kInf = __longlong_as_double(0x7ff0000000000000ll);
     double rmin = kInf, rmax = -kInf;
+    // The residual extrema feed the NEXT layer's parameters: the terminating layer (st->done is set by its layer_params)
+    // has no successor, so its pass skips them -- six instructions per coefficient of a pass that issues ~40.  Two
+    // copies of the loop (a generic lambda instantiated for both cases): the choice costs nothing per element.
+    const bool track = st->done == 0;
+    auto sweep = [&](auto track_tag) {
+    constexpr bool TRACK = decltype(track_tag)::value;
     auto one = [&](double r, uint8_t* dst) {
         unsigned int q;
         const double res = quantise_one<LAYER>(r, s_a, s_b, s_d, s_m, layer, q);
         *dst = (uint8_t)q;
         cnt[__byte_perm(q, mine, 0x6504)] += 1;                  // offset = bin * 256 + mine in one PRMT
-        rmin = dmin2(rmin, res);
-        rmax = dmax2(rmax, res);
+        if (TRACK) {
+            rmin = dmin2(rmin, res);
+            rmax = dmax2(rmax, res);
+        }
     };
     // full tiles: no predicates; the loads of tile t+1 are issued before tile t is processed (two register
     // sets used alternately); running pointers keep every access at base + immediate
@@ -222,6 +231,8 @@ __global__ void __launch_bounds__(kQThreads, (LAYER <= 2) ? 3 : 2) quantise_kern
         for (int k = 0; k < kQLoads; k++)
             if (i0 + k * kQThreads + tid < n) one(r[k], out + k * kQThreads);
     }
+    };
+    if (track) sweep(std::true_type{}); else sweep(std::false_type{});
     __syncthreads();
     {   // thread = bin: add up the 256 private counters of the bin (64 words, rotated start -> no bank conflicts)
         const uint4* row = reinterpret_cast<const uint4*>(s_cnt + tid * 64);
@@ -236,9 +247,10 @@ __global__ void __launch_bounds__(kQThreads, (LAYER <= 2) ? 3 : 2) quantise_kern
         }
         if (tot) atomicAdd(&hist[(unsigned long long)b * 256 + tid], tot);      // hist is zeroed per encode
     }
-    const bool any = (unsigned int)tid < n;
-    block_minmax_commit(any ? dkey(rmin) : kKeyMinInit, any ? dkey(rmax) : kKeyMaxInit, &st->rmin_key[layer + 1],
-                        &st->rmax_key[layer + 1]);
+    const bool any = track && (unsigned int)tid < n;
+    if (track)                                            // uniform over the CTA (it contains barriers)
+        block_minmax_commit(any ? dkey(rmin) : kKeyMinInit, any ? dkey(rmax) : kKeyMaxInit, &st->rmin_key[layer + 1],
+                            &st->rmax_key[layer + 1]);
 }
 
 template <int LAYER>

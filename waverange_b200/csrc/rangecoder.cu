@@ -793,26 +793,21 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
                 uint32_t ent = adv ? e.y : e.x;
                 s += adv ? 1u : 0u;
                 if (adv) {                        // rare: more than one step from the bucket's first symbol
-                    // A few linear steps (the common case where a bucket holds three or four symbols), then a binary search:
-                    // where many symbols have small counts a bucket holds a dozen of them, and a linear scan costs every
-                    // lane of the warp the longest scan among its 32 lanes at every symbol (measured: a run of such data
-                    // decoded in 5.4 ms instead of 2.0).  The search looks for the largest symbol whose cumulative count
-                    // does not exceed cf = V / help; it lies before the first symbol of the bucket after next (q is cf or
-                    // cf - 1).
-                    uint32_t nx = tl[(s + 1) * (CPW * TW)];
-                    int steps = 0;
-                    while (s < lastsym && help * (nx >> 16) <= V) {
-                        if (++steps > 2) {
-                            uint32_t lo = s + 1, hi = min(lastsym, (uint32_t)ll[((q >> kLutShift) + 2) * CPW]);
-                            while (lo < hi) {
-                                const uint32_t mid = (lo + hi + 1) >> 1;
-                                if (help * (tl[mid * (CPW * TW)] >> 16) <= V) lo = mid; else hi = mid - 1;
-                            }
-                            s = lo;
-                            ent = tl[s * (CPW * TW)];
-                            break;
+                    const uint32_t nx = tl[(s + 1) * (CPW * TW)];
+                    if (s < lastsym && help * (nx >> 16) <= V) {
+                        // Third or later symbol of its bucket: where many symbols have small counts a bucket holds a dozen of
+                        // them, and a linear scan costs every lane of the warp the longest scan among its 32 lanes at every
+                        // symbol (measured: a run of such data decoded in 5.4 ms instead of 2.0).  Binary search for the
+                        // largest symbol whose cumulative count does not exceed cf = V / help; it lies before the first
+                        // symbol of the bucket after next (the estimate q is cf or cf - 1).  (Two linear steps before the
+                        // search were measured too: 256^3 2.02 instead of 2.11 ms, but 512^3 at 8 layers 5.07 instead of 4.27.)
+                        uint32_t lo = s + 1, hi = min(lastsym, (uint32_t)ll[((q >> kLutShift) + 2) * CPW]);
+                        while (lo < hi) {
+                            const uint32_t mid = (lo + hi + 1) >> 1;
+                            if (help * (tl[mid * (CPW * TW)] >> 16) <= V) lo = mid; else hi = mid - 1;
                         }
-                        s++; ent = nx; nx = tl[(s + 1) * (CPW * TW)];
+                        s = lo;
+                        ent = tl[s * (CPW * TW)];
                     }
                 }
                 // (testing help * (cum + count) of the chosen entry instead -- no load, branch rarely taken -- measured
@@ -825,22 +820,15 @@ __global__ void __launch_bounds__(32) range_decode_kernel(const uint8_t* __restr
                 lt = adv ? c1 : c0;
                 uint32_t nx = adv ? c2 : c1;
                 s += adv ? 1u : 0u;
-                if (adv) {                        // a few linear steps, then a binary search (see above)
-                    int steps = 0;
-                    while (s < lastsym && help * nx <= V) {
-                        if (++steps > 2) {
-                            uint32_t lo = s + 1, hi = min(lastsym, (uint32_t)ll[((q >> kLutShift) + 2) * CPW]);
-                            while (lo < hi) {
-                                const uint32_t mid = (lo + hi + 1) >> 1;
-                                if (help * (uint32_t)cum16[col + mid * CPW] <= V) lo = mid; else hi = mid - 1;
-                            }
-                            s = lo;
-                            lt = cum16[col + s * CPW];
-                            nx = cum16[col + (s + 1) * CPW];
-                            break;
-                        }
-                        s++; lt = nx; nx = cum16[col + (s + 1) * CPW];
+                if (adv && s < lastsym && help * nx <= V) {       // third or later symbol of its bucket: binary search (see above)
+                    uint32_t lo = s + 1, hi = min(lastsym, (uint32_t)ll[((q >> kLutShift) + 2) * CPW]);
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi + 1) >> 1;
+                        if (help * (uint32_t)cum16[col + mid * CPW] <= V) lo = mid; else hi = mid - 1;
                     }
+                    s = lo;
+                    lt = cum16[col + s * CPW];
+                    nx = cum16[col + (s + 1) * CPW];
                 }
                 sy = nx - lt;
             }
