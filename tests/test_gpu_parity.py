@@ -93,11 +93,14 @@ def test_range_coder_chunks_vs_oracle(codec, torch_cuda, oracle, n, chunk, kind)
     assert np.array_equal(back.cpu().numpy(), sym)
 
 
+@pytest.mark.parametrize("pack", ["0", "1"])
 @pytest.mark.parametrize("form", ["full", "compact"])
-def test_encoder_table_forms_are_bit_identical(codec, torch_cuda, oracle, monkeypatch, form):
-    """the encoder's two table forms (32 KB full entries / 16.5 KB cumulative counts only, chosen by grid size): both
-    must give the oracle's bytes; skewed, uniform and single-symbol data"""
+def test_encoder_table_forms_are_bit_identical(codec, torch_cuda, oracle, monkeypatch, form, pack):
+    """the encoder's two table forms (32 KB full entries / 16.5 KB cumulative counts only, chosen by grid size) and its
+    two ways of storing the raw entries (scattered 2-byte stores / packed groups of four): all must give the oracle's
+    bytes; skewed, uniform and single-symbol data"""
     monkeypatch.setenv("WRB_ENC_TABLES", form)
+    monkeypatch.setenv("WRB_ENC_PACK", pack)
     rng = np.random.default_rng(3)
     n = 59999 * 5 + 123
     for sym in (rng.integers(0, 256, n, dtype=np.uint8), np.clip(np.rint(128 + 0.7 * rng.standard_normal(n)), 0, 255).astype(np.uint8),

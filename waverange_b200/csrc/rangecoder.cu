@@ -69,47 +69,74 @@ __device__ __forceinline__ uint32_t div_magic(uint32_t n, const Magic& m)
 struct Enc {
     uint32_t low, range, pos;    // pos = raw entries written (entry 0 is the lead byte)
     uint16_t* raw;
+    unsigned long long acc;      // PACK: the entries of the current group of four (pos & ~3 ...), not yet stored
 };
 
+// PACK: raw entries leave in 8-byte stores of four.  Every lane writes its own chunk's scratch, so a 2-byte store per
+// lane is 32 scattered sector writes per warp instruction; a layer of nearly incompressible symbols makes one per
+// symbol and lane and the L2's write path, not the recurrence, sets the pace (512^3 f64 at 8 layers: 1.06 ms per layer
+// against 0.63 at 3).  Packing costs ~8 instructions per symbol, which the one-warp-per-scheduler case has to spare only
+// partly -- so it is a launch-time choice (range_encode_chunks).
+template <bool PACK>
+__device__ __forceinline__ void enc_emit(Enc& e, uint32_t v)
+{
+    if (!PACK) { e.raw[e.pos++] = (uint16_t)v; return; }
+    const uint32_t slot = e.pos & 3u;
+    e.acc |= (unsigned long long)v << (16u * slot);
+    e.pos++;
+    if (slot == 3u) { *reinterpret_cast<unsigned long long*>(e.raw + (e.pos - 4u)) = e.acc; e.acc = 0ull; }
+}
+template <bool PACK>
+__device__ __forceinline__ void enc_flush_pack(Enc& e)
+{
+    if (!PACK) return;
+    for (uint32_t i = e.pos & ~3u; i < e.pos; i++) e.raw[i] = (uint16_t)(e.acc >> (16u * (i & 3u)));
+}
+
 // generic renormalisation (markers, raw shorts, flush).  rangecod.c:182-207 minus the carry logic
+template <bool PACK>
 __device__ __forceinline__ void enc_renorm(Enc& e)
 {
     while (e.range <= kBottom) {
-        e.raw[e.pos++] = (uint16_t)(e.low >> kShiftBits);
+        enc_emit<PACK>(e, e.low >> kShiftBits);
         e.range <<= 8;
         e.low = (e.low << 8) & (kTop - 1);
     }
 }
 
 // rangecod.c:217-229 with tot == 2 (block / end markers, wrappers.cpp:95,131)
+template <bool PACK>
 __device__ __forceinline__ void enc_marker(Enc& e, uint32_t bit)
 {
-    enc_renorm(e);
+    enc_renorm<PACK>(e);
     const uint32_t r = e.range >> 1;
     if (bit) { e.low += r; e.range -= r; }   // sy=1, lt=1: lt+sy == tot
     else     { e.range = r; }                // sy=1, lt=0
 }
 
 // rangecod.c:231-245 as encode_short (rangecod.h:155)
+template <bool PACK>
 __device__ __forceinline__ void enc_short(Enc& e, uint32_t v)
 {
-    enc_renorm(e);
+    enc_renorm<PACK>(e);
     const uint32_t r = e.range >> 16, t = r * v;
     e.low += t;
     if ((v + 1) >> 16) e.range -= t; else e.range = r;
 }
 
 // rangecod.c:254-276.  bytecount of the reference == number of shifts == pos - 1.
+template <bool PACK>
 __device__ __forceinline__ void enc_finish(Enc& e)
 {
-    enc_renorm(e);
+    enc_renorm<PACK>(e);
     const uint32_t count = (e.pos - 1) + 5;
     uint32_t t = e.low >> kShiftBits;
     if (!((e.low & (kBottom - 1)) < ((count & 0xFFFFFFu) >> 1))) t += 1;
-    e.raw[e.pos++] = (uint16_t)(t | kTerm);                    // carries like any entry (t > 0xFF)
-    e.raw[e.pos++] = (uint16_t)(((count >> 16) & 0xFFu) | kTerm);
-    e.raw[e.pos++] = (uint16_t)(((count >> 8) & 0xFFu) | kTerm);
-    e.raw[e.pos++] = (uint16_t)((count & 0xFFu) | kTerm);
+    enc_emit<PACK>(e, t | kTerm);                              // carries like any entry (t > 0xFF)
+    enc_emit<PACK>(e, ((count >> 16) & 0xFFu) | kTerm);
+    enc_emit<PACK>(e, ((count >> 8) & 0xFFu) | kTerm);
+    enc_emit<PACK>(e, (count & 0xFFu) | kTerm);
+    enc_flush_pack<PACK>(e);
 }
 
 // Code one symbol (rangecod.c:217-229).  ent = cum << 16 | count; `last`: the symbol is the last
@@ -117,25 +144,38 @@ __device__ __forceinline__ void enc_finish(Enc& e)
 // entries go out through predicated stores and the shifted state is chosen with selects.  ONE: the block
 // holds a single symbol (tot == 1: no division); decided per block, outside the symbol loop, so that the
 // choice costs no select on the range recurrence.
-template <bool ONE>
+template <bool ONE, bool PACK>
 __device__ __forceinline__ void enc_symbol(Enc& e, uint32_t ent, bool last, const Magic& mg)
 {
     const uint32_t range = e.range, low = e.low;
-    uint16_t* w = e.raw + e.pos;
-    // (plain `if (k1) w[0] = ...` makes the compiler branch around the stores: 38 instructions per symbol and a
-    //  reconvergence point; the predicated stores are spelled out instead)
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p1, p2;\n\t"
-        "setp.le.u32 p1, %1, 0x800000;\n\t"
-        "setp.le.u32 p2, %1, 0x8000;\n\t"
-        "@p1 st.global.u16 [%0], %2;\n\t"
-        "@p2 st.global.u16 [%0+2], %3;\n\t"
-        "}"
-        :: "l"(w), "r"(range), "h"((uint16_t)(low >> kShiftBits)), "h"((uint16_t)((low >> (kShiftBits - 8)) & 0xFFu))
-        : "memory");
     const bool k1 = range <= kBottom, k2 = range <= (kBottom >> 8);
-    e.pos += (k1 ? 1u : 0u) + (k2 ? 1u : 0u);
+    if (PACK) {
+        const uint32_t e1 = low >> kShiftBits, e2 = (low >> (kShiftBits - 8)) & 0xFFu;
+        const uint32_t vm = k2 ? (e1 | (e2 << 16)) : (k1 ? e1 : 0u);          // the entries of this symbol, first one low
+        const uint32_t slot = e.pos & 3u;
+        e.acc |= (unsigned long long)vm << (16u * slot);                      // slot 3 with two entries: the second falls off the top
+        const uint32_t np = e.pos + (k1 ? 1u : 0u) + (k2 ? 1u : 0u);
+        if ((np ^ e.pos) & 4u) {                                              // the group of four is complete
+            *reinterpret_cast<unsigned long long*>(e.raw + (e.pos & ~3u)) = e.acc;
+            e.acc = (slot == 3u && k2) ? (unsigned long long)e2 : 0ull;
+        }
+        e.pos = np;
+    } else {
+        uint16_t* w = e.raw + e.pos;
+        // (plain `if (k1) w[0] = ...` makes the compiler branch around the stores: 38 instructions per symbol and a
+        //  reconvergence point; the predicated stores are spelled out instead)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p1, p2;\n\t"
+            "setp.le.u32 p1, %1, 0x800000;\n\t"
+            "setp.le.u32 p2, %1, 0x8000;\n\t"
+            "@p1 st.global.u16 [%0], %2;\n\t"
+            "@p2 st.global.u16 [%0+2], %3;\n\t"
+            "}"
+            :: "l"(w), "r"(range), "h"((uint16_t)(low >> kShiftBits)), "h"((uint16_t)((low >> (kShiftBits - 8)) & 0xFFu))
+            : "memory");
+        e.pos += (k1 ? 1u : 0u) + (k2 ? 1u : 0u);
+    }
     const uint32_t rs = k2 ? (range << 16) : (k1 ? (range << 8) : range);
     const uint32_t ls = k2 ? ((low << 16) & (kTop - 1)) : (k1 ? ((low << 8) & (kTop - 1)) : low);   // carry bit survives k == 0
     const uint32_t r = ONE ? rs : (__umulhi(rs, mg.mul) >> mg.sh);               // exact range / bs
@@ -147,10 +187,9 @@ __device__ __forceinline__ void enc_symbol(Enc& e, uint32_t ent, bool last, cons
 // grid (ceil(nchunks/32), layers), block 32: lane == chunk.
 // COMPACT: the per-lane tables hold 16-bit cumulative counts only, two per word ([symbol pair][lane]: conflict-free like
 // the full form) -- 16.5 KB per warp instead of 32 KB, so twice the warps fit an SM; an entry (cum, count) is then two
-// loads and a subtraction, ~6 instructions more per symbol, all off the recurrence.  The full form while every warp of
-// the grid is resident anyway (the 512^3 benchmark: one warp per scheduler, the recurrence is what counts), the compact
-// form for larger grids, where the resident warps per scheduler are what counts (1024^3 f64, 5 layers: 2797 warps).
-template <bool COMPACT>
+// loads and a subtraction, ~6 instructions more per symbol, all off the recurrence.  Measured slower even where the grid
+// exceeds what is resident (1024^3 f64, 5 layers, 2797 warps: 16.3 vs 14.1 ms), so it is only a switch (WRB_ENC_TABLES).
+template <bool COMPACT, bool PACK>
 __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restrict__ sym,
                                                           unsigned long long sym_layer_stride,
                                                           const uint32_t* __restrict__ hist,
@@ -176,7 +215,8 @@ __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restr
     Enc e;
     e.low = 0; e.range = kTop;                                             // rangecod.c:170-176
     e.raw = reinterpret_cast<uint16_t*>(slots + id * slot_pitch);
-    e.raw[0] = 0;                                                          // lead byte
+    e.acc = 0ull;
+    if (!PACK) e.raw[0] = 0;                                               // lead byte (PACK: entry 0 of the first group)
     e.pos = 1;
     const uint32_t* __restrict__ tl = tab + lane;
     auto table_entry = [&](uint32_t c) -> uint32_t {              // cum << 16 | count of symbol c
@@ -190,7 +230,7 @@ __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restr
     unsigned long long done = 0;
     for (;;) {                                                              // wrappers.cpp:85-128
         const uint32_t bs = (clen - done < kBlock) ? (uint32_t)(clen - done) : kBlock;
-        enc_marker(e, 1);
+        enc_marker<PACK>(e, 1);
         uint32_t cum = 0, lastsym = 0;
         for (int s = 0; s < 256; s += 4) {
             const uint4 c4 = *reinterpret_cast<const uint4*>(hrow + s);
@@ -198,7 +238,7 @@ __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restr
             uint32_t pairw = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                enc_short(e, cc[k]);
+                enc_short<PACK>(e, cc[k]);
                 if (COMPACT) {
                     if (k & 1) tab[((s + k) >> 1) * 32 + lane] = pairw | (cum << 16); else pairw = cum;
                 } else {
@@ -209,7 +249,7 @@ __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restr
             }
         }
         if (COMPACT) tab[128 * 32 + lane] = cum;                             // cum[256] = block size (< 2^16)
-        enc_renorm(e);                            // up to three shifts may be pending after a raw short
+        enc_renorm<PACK>(e);                      // up to three shifts may be pending after a raw short
         const Magic mg = make_magic(bs);
         const uint4* __restrict__ p = reinterpret_cast<const uint4*>(in + done);
         const uint32_t nfull = bs >> 4;
@@ -237,7 +277,7 @@ __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restr
                 ent[k] = table_entry(cs[k]);
             }
 #pragma unroll
-            for (int k = 0; k < 16; k++) enc_symbol<ONE>(e, ent[k], cs[k] == lastsym, mg);
+            for (int k = 0; k < 16; k++) enc_symbol<ONE, PACK>(e, ent[k], cs[k] == lastsym, mg);
             w = wn;
         }
         {
@@ -248,7 +288,7 @@ __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restr
             }
             for (uint32_t k = 0; k < rem; k++) {
                 const uint32_t c = (ww[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
-                enc_symbol<ONE>(e, table_entry(c), c == lastsym, mg);
+                enc_symbol<ONE, PACK>(e, table_entry(c), c == lastsym, mg);
             }
         }
         for (; g.nseek && nsk < g.nseek; nsk++) { sk[nsk * 3 + 0] = 0; sk[nsk * 3 + 1] = 0; sk[nsk * 3 + 2] = 0; }
@@ -258,8 +298,8 @@ __global__ void __launch_bounds__(32) range_encode_kernel(const uint8_t* __restr
         hrow += 256;
         if (bs < kBlock) break;
     }
-    enc_marker(e, 0);
-    enc_finish(e);
+    enc_marker<PACK>(e, 0);
+    enc_finish<PACK>(e);
     lens[id] = (unsigned long long)e.pos;
 }
 
@@ -270,13 +310,21 @@ void range_encode_chunks(const uint8_t* sym, unsigned long long sym_layer_stride
 {
     dim3 grid((g.nchunks + 31) / 32, nlayers, 1);
     const char* e = getenv("WRB_ENC_TABLES");                        // "full" / "compact": force a form (tests, A/B timing)
-    bool compact = (unsigned long long)grid.x * grid.y > 148ull * 6;    // the full form keeps 6-7 warps per SM resident (32 KB each)
+    // measured (1024^3 f64, 5 layers, 2797 warps): compact 16.3 ms, full 14.1 ms -- the extra instructions cost more than
+    // the doubled residency buys, so the full form is the default at every size and the compact one stays a switch
+    bool compact = false;
     if (e && *e == 'f') compact = false;
     if (e && *e == 'c') compact = true;
-    if (compact)
-        range_encode_kernel<true><<<grid, 32, 0, s>>>(sym, sym_layer_stride, hist, hist_layer_stride, g, active, slots, slot_pitch, lens, seek);
-    else
-        range_encode_kernel<false><<<grid, 32, 0, s>>>(sym, sym_layer_stride, hist, hist_layer_stride, g, active, slots, slot_pitch, lens, seek);
+    const char* pe = getenv("WRB_ENC_PACK");                         // "0" / "1": force scattered 2-byte / packed 8-byte stores of the raw entries
+    // measured at 512^3: packed stores make the loop ~135 instead of 62 cycles per symbol whatever the data (a second
+    // dependency chain through the accumulator), scattered stores cost 1.88 ms at 3 layers, 3.3 at 5, 8.5 at 8: packing
+    // pays only when most layers are nearly incompressible (4.1 ms at 8 layers)
+    bool pack = nlayers >= 7;
+    if (pe && *pe) pack = atoi(pe) != 0;
+#define WRB_ENC_LAUNCH(C, P) range_encode_kernel<C, P><<<grid, 32, 0, s>>>(sym, sym_layer_stride, hist, hist_layer_stride, g, active, slots, slot_pitch, lens, seek)
+    if (compact) { if (pack) WRB_ENC_LAUNCH(true, true); else WRB_ENC_LAUNCH(true, false); }
+    else { if (pack) WRB_ENC_LAUNCH(false, true); else WRB_ENC_LAUNCH(false, false); }
+#undef WRB_ENC_LAUNCH
     note_launch(1);
 }
 
