@@ -644,7 +644,11 @@ static int encode_slab_global(wrb_codec* c, const void* d_field, int dtype, int 
     if ((rc = run_transform_and_quantise(c, d_field, dtype, nx, ny, nzl, wtflag, tolrel, gq, sg, nlayers, (uint8_t*)c->xsym.p, c->xsym_stride))) return rc;
     // every rank's symbol planes are complete; then my run comes straight out of the peers' windows (NVLink), lands in
     // the coder's chunk-major layout and is histogrammed per coder block on the way
+    static const bool dbg = getenv("WRB_DEBUG_TIMING") != nullptr;         // development: split the exchange on stderr
+    cudaEvent_t de[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (dbg) { for (auto& e : de) cudaEventCreate(&e); cudaEventRecord(de[0], s); }
     if ((rc = slab_barrier(c))) return rc;
+    if (dbg) cudaEventRecord(de[1], s);
     // (the two windows serve both directions: `xsym` holds the rank's local symbol planes -- written by the quantiser
     //  here, by the exchange when decoding -- and `xrun` its run of the global sequence -- gathered here in the coder's
     //  chunk-major layout, written by the range decoder when decoding; no further symbol buffer exists in this mode)
@@ -652,7 +656,16 @@ static int encode_slab_global(wrb_codec* c, const void* d_field, int dtype, int 
     const unsigned long long hstride = (unsigned long long)gr.nblocks * 256;
     uint8_t* const runp = (uint8_t*)c->xrun.p;
     gather_global_run(og, rank, c->peer_xsym, c->xsym_stride, nlayers, st->active, gr, runp, lstride,
-                      (uint32_t*)c->hist.p, hstride, s);
+                      (uint32_t*)c->hist.p, hstride, s, de[2]);
+    if (dbg) {
+        cudaEventRecord(de[3], s);
+        cudaEventSynchronize(de[3]);
+        float t[4];
+        for (int i = 0; i < 3; i++) cudaEventElapsedTime(&t[i], de[i], de[i + 1]);
+        cudaEventElapsedTime(&t[3], c->ev[1], de[0]);
+        fprintf(stderr, "[wrb rank %d] encode: quantise %.3f ms, barrier %.3f ms, gather %.3f ms, block histograms %.3f ms\n", rank, t[3], t[0], t[1], t[2]);
+        for (auto& e : de) cudaEventDestroy(e);
+    }
     if (c->timing) cudaEventRecord(c->ev[2], s);                        // "quantise" includes the exchange in this mode
     const unsigned long long sp = chunk_slot_pitch(gr);
     range_encode_chunks(runp, lstride, (const uint32_t*)c->hist.p, hstride, gr, nlayers, st->active,

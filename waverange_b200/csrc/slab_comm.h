@@ -37,7 +37,7 @@ struct PeerPtrs { const uint8_t* p[kMaxRanks]; };
 // local array order) into the coder's chunk-major padded layout, with the coder blocks' histograms
 void gather_global_run(const OrderGeom& og, int rank, const PeerPtrs& peer, unsigned long long peer_stride, int nlayers,
                        const int* active, const ChunkGeom& g, uint8_t* sym, unsigned long long sym_layer_stride,
-                       uint32_t* hist, unsigned long long hist_layer_stride, cudaStream_t s);
+                       uint32_t* hist, unsigned long long hist_layer_stride, cudaStream_t s, cudaEvent_t after_gather = nullptr);
 // decode side: my local symbol planes (array order, layer l at out + l*out_stride) gathered from the ranks' decoded
 // runs (peer[r] + layer*peer_stride + (j - j0[r]))
 void scatter_local_planes(const OrderGeom& og, int rank, const PeerPtrs& peer, unsigned long long peer_stride, int nlay,

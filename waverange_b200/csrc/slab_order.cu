@@ -363,9 +363,9 @@ __global__ void __launch_bounds__(kHThreads) hist_blocks_kernel(const uint8_t* _
 
 void gather_global_run(const OrderGeom& og, int rank, const PeerPtrs& peer, unsigned long long peer_stride, int nlayers,
                        const int* active, const ChunkGeom& g, uint8_t* sym, unsigned long long sym_layer_stride,
-                       uint32_t* hist, unsigned long long hist_layer_stride, cudaStream_t s)
+                       uint32_t* hist, unsigned long long hist_layer_stride, cudaStream_t s, cudaEvent_t after_gather)
 {
-    if (g.nblocks == 0 || nlayers <= 0) return;
+    if (g.nblocks == 0 || nlayers <= 0) { if (after_gather) cudaEventRecord(after_gather, s); return; }
     const OrderDev o = make_dev(og);
     static DeviceOnce once;
     once.run([] { cudaFuncSetAttribute(hist_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHHistBytes); });
@@ -378,6 +378,7 @@ void gather_global_run(const OrderGeom& og, int rank, const PeerPtrs& peer, unsi
     } else {
         gather_run_small_kernel<<<grid, 256, 0, s>>>(o, rank, peer, peer_stride, active, g, sym, sym_layer_stride);
     }
+    if (after_gather) cudaEventRecord(after_gather, s);
     hist_blocks_kernel<<<grid, kHThreads, kHHistBytes, s>>>(sym, sym_layer_stride, active, g, hist, hist_layer_stride);
     note_launch(2);
 }
