@@ -15,6 +15,7 @@
 // any segmentation gives bit-identical results.  Requires even box extents >= 8; other shapes take
 // the general three-pass path.
 #include <cstdlib>
+#include <type_traits>
 #include "wr_common.cuh"
 #include "wr_kernels.h"
 
@@ -28,6 +29,7 @@ constexpr int FTX = 2 * FPX + 7;        // 71
 constexpr int FTY = 2 * FPY + 7;        // 23
 constexpr int FXR = 4;                  // pairs per x-lifting task
 constexpr int FTHREADS = 256;
+constexpr int kFwdImplDefault = 2;          // see the kernel: 0 two barriers per plane, 1 software pipeline, 2 pipeline + native-type tile
 
 struct FusedFwdArgs {
     const void* src; long long ssy, ssz;       // level input (x stride 1)
@@ -74,14 +76,39 @@ constexpr int FSLOTS = (FTY * FTX + FTHREADS - 1) / FTHREADS;       // tile elem
 // PITCH: row pitch of the input tile in doubles.  73 (odd) is what runs; 72 is kept as a measurement variant
 // (WRB_FWD_PITCH=72): it is the densest pitch a TMA box could deliver (box rows are multiples of 16 bytes, so the pitch of a
 // TMA-written tile of doubles is even) and shows what the x-lifting -- consecutive lanes on consecutive ROWS -- pays for it.
-template <class TIN, bool TRACK_IN, int PITCH = FTX + 2>
+//
+// PIPE: the three stages of a plane -- tile store, x-lifting, y-lifting + z pipeline -- run as a software pipeline over
+// double-buffered tiles: round q stores plane q, x-lifts plane q-1 and y-lifts plane q-2, so ONE barrier per plane
+// separates the rounds instead of two, and a warp without an x-lifting task (184 tasks on 256 threads) goes straight
+// on to its y-lifting.  Same arithmetic on the same values: bit-identical.
+constexpr int FTXP = 2 * FPX + 1;               // row pitch of the x-lifted tile (65)
+//
+// NATIVE: the input tile stays in the input's own type (a float field: half the shared-memory traffic of the tile store and
+// of the x-lifting loads; the widening moves into the x-lifting), and the x-lifting tasks are numbered 24 per group of
+// pairs instead of 23 (one idle lane per group): with row pitches 75 (float) / 73 (double) no two lanes of a warp / half
+// warp then meet in a bank, where the dense numbering costs every straddling half warp a replay.  The r3 profile of the
+// level-1 kernel showed why this matters: the shared-memory data pipe was the busiest unit (70 % of its wavefront peak, a
+// quarter of the wavefronts bank-conflict replays) ahead of the FP64 pipe (42 %) and DRAM (30 %).
+template <class TIN, bool NATIVE> struct FwdTile { typedef double type; };
+template <class TIN> struct FwdTile<TIN, true> { typedef TIN type; };
+template <class TIN, int PITCH, bool NATIVE> __host__ __device__ constexpr int fused_fwd_pitch() { return NATIVE ? (sizeof(TIN) == 4 ? 75 : 73) : PITCH; }
+template <class TIN, bool PIPE, int PITCH, bool NATIVE> constexpr int fused_fwd_smem()
+{
+    return (PIPE ? 2 : 1) * FTY * (fused_fwd_pitch<TIN, PITCH, NATIVE>() * (int)sizeof(typename FwdTile<TIN, NATIVE>::type) + FTXP * (int)sizeof(double)) + 16;
+}
+
+template <class TIN, bool TRACK_IN, int PITCH = FTX + 2, bool PIPE = false, bool NATIVE = false>
 __global__ void __launch_bounds__(FTHREADS, 2) fwd_level_fused_kernel(FusedFwdArgs a)
 {
-    constexpr int FTP = PITCH;
+    typedef typename FwdTile<TIN, NATIVE>::type TT;
+    constexpr int FTP = fused_fwd_pitch<TIN, PITCH, NATIVE>();
+    constexpr int XTG = NATIVE ? FTY + 1 : FTY;  // x-lifting task numbers per group of FXR pairs
+    constexpr int NB = PIPE ? 2 : 1;
     // odd row pitches: the x-lifting tasks run with consecutive lanes on consecutive ROWS, so an odd
-    // pitch (in doubles) spreads them over the banks; the y-lifting reads run along a row
-    __shared__ double tin[FTY * FTP];           // input tile incl. halo
-    __shared__ double tx[FTY][2 * FPX + 1];     // after x-lifting: [row][low 32 | high 32] (pitch 65)
+    // pitch spreads them over the banks; the y-lifting reads run along a row
+    extern __shared__ __align__(16) double fsm[];
+    double* const tx = fsm;                     // [NB] after x-lifting: [row][low 32 | high 32], FTY x FTXP
+    TT* const tin = reinterpret_cast<TT*>(fsm + NB * FTY * FTXP);   // [NB] input tile incl. halo, FTY x FTP
     const TIN* __restrict__ src = (const TIN*)a.src;
     const int tid = threadIdx.x;
     const int m0 = a.n0 >> 1, m1 = a.n1 >> 1;
@@ -140,43 +167,40 @@ __global__ void __launch_bounds__(FTHREADS, 2) fwd_level_fused_kernel(FusedFwdAr
 #pragma unroll
         for (int k = 0; k < FSLOTS; k++) nxt[k] = plane[goff[k]];
     };
-    // x- and y-lifting of the plane held in nxt[]; prefetches plane znext meanwhile; returns the four
-    // (x, y, sub-band) values this thread feeds into its z pipelines
-    auto lift_plane = [&](int znext, bool more, double (&yv)[4]) {
+    // the three stages of a plane (b: tile buffer)
+    auto stage_store = [&](int b) {                // nxt[] -> input tile
+        TT* const t = tin + b * (FTY * FTP);
 #pragma unroll
         for (int k = 0; k < FSLOTS; k++) {
             const TIN v = nxt[k];
             if (TRACK_IN) track_ext(v, fmn, fmx);
-            tin[soff[k]] = (double)v;
+            t[soff[k]] = (TT)v;
         }
-        __syncthreads();
-        if (more) load_plane(znext);               // next plane in flight while this one is lifted
-        // x-lifting: FXR pairs per task, consecutive lanes on consecutive rows
-        for (int t = tid; t < FTY * (FPX / FXR); t += FTHREADS) {
-            const int g = t / FTY, ry = t - g * FTY;
+    };
+    auto stage_x = [&](int b) {                    // x-lifting: FXR pairs per task, consecutive lanes on consecutive rows
+        const TT* const t = tin + b * (FTY * FTP);
+        double* const o = tx + b * (FTY * FTXP);
+        for (int tk = tid; tk < XTG * (FPX / FXR); tk += FTHREADS) {
+            const int g = tk / XTG, ry = tk - g * XTG;
+            if (NATIVE && ry >= FTY) continue;                       // the idle number of the group
             double so[FXR], dd[FXR];
-            const double* row = &tin[ry * FTP + 4 + 2 * g * FXR];   // sample 2*i0 of the line
-            auto ld = [&](int j) -> double { return row[j]; };
+            const TT* row = &t[ry * FTP + 4 + 2 * g * FXR];         // sample 2*i0 of the line
+            auto ld = [&](int j) -> double { return (double)row[j]; };
             fwd_pairs_interior<FXR>(ld, 0, so, dd);
 #pragma unroll
-            for (int k = 0; k < FXR; k++) { tx[ry][g * FXR + k] = so[k]; tx[ry][FPX + g * FXR + k] = dd[k]; }
+            for (int k = 0; k < FXR; k++) { o[ry * FTXP + g * FXR + k] = so[k]; o[ry * FTXP + FPX + g * FXR + k] = dd[k]; }
         }
-        __syncthreads();
-        // y-lifting of column c for pairs j0, j0+1
+    };
+    auto stage_y = [&](int b, double (&yv)[4]) {   // y-lifting of column c for pairs j0, j0+1: the four values fed to the z pipelines
+        const double* const o = tx + b * (FTY * FTXP);
         double sy[2], dy[2];
         const int rb = 4 + 4 * (tid >> 6);                           // tile row of sample 2*j0
-        auto ldy = [&](int j) -> double { return tx[rb + j][c]; };
+        auto ldy = [&](int j) -> double { return o[(rb + j) * FTXP + c]; };
         fwd_pairs_interior<2>(ldy, 0, sy, dy);
         yv[0] = sy[0]; yv[1] = sy[1]; yv[2] = dy[0]; yv[3] = dy[1];
-        // no trailing barrier: tin is next written only by threads that have passed the second barrier
-        // (x-lifting done), and tx is next written after the first barrier of the next plane
     };
-    // Pairs e0-2 .. e1+1 are fed: the pipeline restarts two pairs before the segment, and the last output
-    // pair e1-1 completes when the even plane of pair e1+1 has been lifted (its odd plane is not needed).
-    load_plane(2 * (e0 - 2));
-    for (int m = e0 - 2; m <= e1 + 1; m++) {
-        double yv[4];
-        lift_plane(2 * m + 1, m <= e1, yv);                      // even plane: s0[m]; pair m-2 completes
+    // z pipeline: the even plane of pair m has arrived (s0[m]); pair m-2 completes
+    auto z_even = [&](int m, const double (&yv)[4]) {
         const bool out = (m - 2 >= e0);
 #pragma unroll
         for (int v = 0; v < 4; v++) {
@@ -200,10 +224,58 @@ __global__ void __launch_bounds__(FTHREADS, 2) fwd_level_fused_kernel(FusedFwdAr
             }
         }
         plo += a.az; phi += a.az; p01 += s01;
-        if (m <= e1) {                                               // odd plane: d0[m]
-            lift_plane(2 * m + 2, true, yv);
+    };
+    // Pairs e0-2 .. e1+1 are fed: the pipeline restarts two pairs before the segment, and the last output
+    // pair e1-1 completes when the even plane of pair e1+1 has been lifted (its odd plane is not needed).
+    if constexpr (!PIPE) {
+        // one plane at a time: store, barrier, (next plane's loads issued,) x-lifting, barrier, y-lifting.  No trailing
+        // barrier: tin is next written only by threads that have passed the second barrier (x-lifting done), and tx is
+        // next written after the first barrier of the next plane
+        auto lift_plane = [&](int znext, bool more, double (&yv)[4]) {
+            stage_store(0);
+            __syncthreads();
+            if (more) load_plane(znext);               // next plane in flight while this one is lifted
+            stage_x(0);
+            __syncthreads();
+            stage_y(0, yv);
+        };
+        load_plane(2 * (e0 - 2));
+        for (int m = e0 - 2; m <= e1 + 1; m++) {
+            double yv[4];
+            lift_plane(2 * m + 1, m <= e1, yv);                      // even plane: s0[m]
+            z_even(m, yv);
+            if (m <= e1) {                                               // odd plane: d0[m]
+                lift_plane(2 * m + 2, true, yv);
 #pragma unroll
-            for (int v = 0; v < 4; v++) d0p[v] = yv[v];
+                for (int v = 0; v < 4; v++) d0p[v] = yv[v];
+            }
+        }
+    } else {
+        // planes i = 0 .. P-1 are z = 2*(e0-2) + i (P odd: the last one is the even plane of pair e1+1); round q stores
+        // plane q (and issues the loads of plane q+1), x-lifts plane q-1 into tx[(q-1)&1] and y-lifts plane q-2 from
+        // tx[q&1].  Every buffer a round writes was last read in the round before: one barrier per round.
+        const int P = 2 * (e1 - e0) + 7, zb = 2 * (e0 - 2);
+        load_plane(zb);
+        for (int k = 0;; k++) {
+            const int q0 = 2 * k;                                        // even round: planes q0 (even), q0-1 (odd), q0-2 (even)
+            if (q0 < P) { stage_store(0); if (q0 + 1 < P) load_plane(zb + q0 + 1); }
+            if (q0 >= 1 && q0 < P) stage_x(1);                           // plane q0-1 (odd); the last round q0 = P+1 has none
+            if (q0 >= 2) {
+                double yv[4];
+                stage_y(0, yv);
+                z_even(e0 - 3 + k, yv);                                  // plane q0-2 is the even plane of pair e0-2 + (q0-2)/2
+            }
+            if (q0 == P + 1) break;
+            __syncthreads();
+            if (q0 + 1 < P) { stage_store(1); load_plane(zb + q0 + 2); }   // odd round q0+1 <= P: plane q0+2 <= P-1 exists whenever q0+1 < P (P odd)
+            stage_x(0);                                                  // plane q0 (even)
+            if (q0 >= 1) {
+                double yv[4];
+                stage_y(1, yv);                                          // plane q0-1: the odd plane of pair e0-2 + (q0-2)/2
+#pragma unroll
+                for (int v = 0; v < 4; v++) d0p[v] = yv[v];
+            }
+            __syncthreads();
         }
     }
     if (TRACK_IN) {
@@ -246,25 +318,39 @@ void fused_forward_level(const void* src, int src_is_f32, long long ssy, long lo
     a.zpairs = zp;
     dim3 grid(gx, gy, (m2 + zp - 1) / zp);
     const bool track = in_min != nullptr;
-    const char* pe = getenv("WRB_FWD_PITCH");
-    if (pe && atoi(pe) == 72) {                                  // measurement variant, see the kernel's comment
-        if (src_is_f32) {
-            if (track) fwd_level_fused_kernel<float, true, 72><<<grid, FTHREADS, 0, s>>>(a);
-            else fwd_level_fused_kernel<float, false, 72><<<grid, FTHREADS, 0, s>>>(a);
-        } else {
-            if (track) fwd_level_fused_kernel<double, true, 72><<<grid, FTHREADS, 0, s>>>(a);
-            else fwd_level_fused_kernel<double, false, 72><<<grid, FTHREADS, 0, s>>>(a);
+    // measurement variants: WRB_FWD_PITCH=72 (see the kernel's comment), WRB_FWD_IMPL=plain|pipe (two barriers per plane / the
+    // software pipeline with one)
+    const int pitch = [] { const char* e = getenv("WRB_FWD_PITCH"); return (e && atoi(e) == 72) ? 72 : FTX + 2; }();
+    // 0: two barriers per plane, 1: the software pipeline, 2: the pipeline over the native-type tile
+    const int impl = [] { const char* e = getenv("WRB_FWD_IMPL"); return (e && *e) ? (e[0] == 'n' ? 2 : (e[1] == 'i' ? 1 : 0)) : kFwdImplDefault; }();
+    auto launch = [&](auto pitch_tag, auto pipe_tag, auto native_tag) {
+        constexpr int PT = decltype(pitch_tag)::value;
+        constexpr bool PP = decltype(pipe_tag)::value, NT = decltype(native_tag)::value;
+        constexpr int smem_f = fused_fwd_smem<float, PP, PT, NT>(), smem_d = fused_fwd_smem<double, PP, PT, NT>();
+        if (smem_d > 48 * 1024) {                                    // opt-in size: the attribute is per device and per kernel
+            static DeviceOnce once;
+            once.run([] {
+                cudaFuncSetAttribute(fwd_level_fused_kernel<float, true, PT, PP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f);
+                cudaFuncSetAttribute(fwd_level_fused_kernel<float, false, PT, PP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f);
+                cudaFuncSetAttribute(fwd_level_fused_kernel<double, true, PT, PP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_d);
+                cudaFuncSetAttribute(fwd_level_fused_kernel<double, false, PT, PP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_d);
+            });
         }
-        note_launch(1);
-        return;
-    }
-    if (src_is_f32) {
-        if (track) fwd_level_fused_kernel<float, true><<<grid, FTHREADS, 0, s>>>(a);
-        else fwd_level_fused_kernel<float, false><<<grid, FTHREADS, 0, s>>>(a);
-    } else {
-        if (track) fwd_level_fused_kernel<double, true><<<grid, FTHREADS, 0, s>>>(a);
-        else fwd_level_fused_kernel<double, false><<<grid, FTHREADS, 0, s>>>(a);
-    }
+        if (src_is_f32) {
+            if (track) fwd_level_fused_kernel<float, true, PT, PP, NT><<<grid, FTHREADS, smem_f, s>>>(a);
+            else fwd_level_fused_kernel<float, false, PT, PP, NT><<<grid, FTHREADS, smem_f, s>>>(a);
+        } else {
+            if (track) fwd_level_fused_kernel<double, true, PT, PP, NT><<<grid, FTHREADS, smem_d, s>>>(a);
+            else fwd_level_fused_kernel<double, false, PT, PP, NT><<<grid, FTHREADS, smem_d, s>>>(a);
+        }
+    };
+    using std::integral_constant;
+    typedef integral_constant<bool, true> Yes;
+    typedef integral_constant<bool, false> No;
+    if (pitch == 72) launch(integral_constant<int, 72>{}, No{}, No{});
+    else if (impl == 2) launch(integral_constant<int, FTX + 2>{}, Yes{}, Yes{});
+    else if (impl == 1) launch(integral_constant<int, FTX + 2>{}, Yes{}, No{});
+    else launch(integral_constant<int, FTX + 2>{}, No{}, No{});
     note_launch(1);
 }
 

@@ -575,6 +575,20 @@ void inverse_level_two_pass(const double* coef, long long ay, long long az, cons
         // that the TMA prefetch of the next round has something to hide behind
         int ppc = 2 * np;
         while (ppc > 4 && (long long)gx * gy * ((2 * np + ppc - 1) / ppc) < 148ll * 4) ppc = ((ppc / 2 + 1) / 2) * 2;
+        // ... and whole waves: three CTAs are resident per SM (shared memory), all take about the same time, so a grid of
+        // 2.3 waves (512^3, level 1: 1024 CTAs on 444 slots) runs for three.  Among the z-splits with at least as many CTAs,
+        // take the one with the smallest waves x (planes per CTA + start-up) product.
+        if (getenv("WRB_INV_WAVES") == nullptr || atoi(getenv("WRB_INV_WAVES")) != 0) {
+            const long long tiles = (long long)gx * gy, slots = 148ll * 3;
+            auto cost = [&](int pp) { const long long ctas = tiles * ((2 * np + pp - 1) / pp); return ((ctas + slots - 1) / slots) * (pp + 3); };
+            int best = ppc;
+            long long best_cost = cost(ppc);
+            for (int pp = ppc - 2; pp >= 4 && pp >= ppc / 4; pp -= 2) {
+                const long long c = cost(pp);
+                if (c < best_cost) { best_cost = c; best = pp; }
+            }
+            ppc = best;
+        }
         ya.planes_per_cta = ppc;
         dim3 ygrid(gx, gy, (2 * np + ppc - 1) / ppc);
         CUtensorMap tm;
