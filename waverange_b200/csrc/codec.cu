@@ -11,6 +11,7 @@
 #include <cstring>
 #include <string>
 #include <algorithm>
+#include <functional>
 #include <atomic>
 #include <new>
 #include <thread>
@@ -65,6 +66,9 @@ struct wrb_codec {
     // second stream + events: wrb_decode_host copies finished z-pieces of the field out while the rest is computed
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t piece_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // z-slab partition, global order: the exchange of layer l runs on this stream while layer l+1 is quantised
+    cudaStream_t xchg_stream = nullptr;
+    cudaEvent_t xchg_ev[2] = {nullptr, nullptr};
     HostSource* src_pipe = nullptr;   // set by wrb_encode_host for the duration of one call: the field arrives in z-pieces
     unsigned long long guess_misses = 0;      // encodes that had to be repeated with all 8 layers (layer_guess)
     // ---- z-slab partition: transport and the global symbol order (slab_comm.cu, slab_order.cu) ----
@@ -255,6 +259,8 @@ void wrb_destroy(wrb_codec* c)
     }
     for (int i = 0; i < 4; i++) if (c->piece_ev[i]) cudaEventDestroy(c->piece_ev[i]);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (auto& e : c->xchg_ev) if (e) cudaEventDestroy(e);
+    if (c->xchg_stream) cudaStreamDestroy(c->xchg_stream);
     delete c;
 }
 
@@ -495,7 +501,8 @@ static int layer_guess(double tolrel)
 // sym_out / sym_stride: where the layers' symbols go (default: the codec's chunk-major buffer c->sym)
 static int run_transform_and_quantise(wrb_codec* c, const void* d_field, int dtype, int nx, int ny, int nz, int wtflag,
                                       double tolrel, const ChunkGeom& g, const SlabGeom* sg = nullptr, int nlayers = kNLayMax,
-                                      uint8_t* sym_out = nullptr, unsigned long long sym_stride = 0)
+                                      uint8_t* sym_out = nullptr, unsigned long long sym_stride = 0,
+                                      uint32_t* hist_out = nullptr, const std::function<int(int)>* layer_complete = nullptr)
 {
     DevState* st = (DevState*)c->state.p;
     cudaStream_t s = c->stream;
@@ -522,17 +529,19 @@ static int run_transform_and_quantise(wrb_codec* c, const void* d_field, int dty
     const unsigned long long lstride = sym_out ? sym_stride : (unsigned long long)g.nchunks * g.pitch;
     uint8_t* const symp = sym_out ? sym_out : (uint8_t*)c->sym.p;
     const unsigned long long hstride = (unsigned long long)g.nblocks * 256;
-    CK(cudaMemsetAsync(c->hist.p, 0, (size_t)nlayers * hstride * 4, s));      // the quantiser adds partial histograms
+    uint32_t* const histp = hist_out ? hist_out : (uint32_t*)c->hist.p;
+    CK(cudaMemsetAsync(histp, 0, (size_t)nlayers * hstride * 4, s));          // the quantiser adds partial histograms
     for (int l = 0; l < nlayers; l++) {
         // global extrema of the coefficients (l == 0) / of the residual left by layer l-1 (wrappers.cpp:308-314)
         if (dist && reduce_extrema(c, &st->rmin_key[l], &st->rmax_key[l])) return fail(c, WRB_E_CUDA, "reduce callback failed");
+        // the all-reduce needs every rank's residual extrema of layer l-1: once it has completed on this stream, layer
+        // l-1 is quantised on ALL ranks
+        if (dist && l > 0 && layer_complete != nullptr) { const int rc = (*layer_complete)(l - 1); if (rc) return rc; }
         layer_params(st, l, s);
         if (local)
-            quantise_layer_masked((const double*)c->coef.p, g, l, st, symp + l * lstride,
-                                  (uint32_t*)c->hist.p + l * hstride, lc, s);
+            quantise_layer_masked((const double*)c->coef.p, g, l, st, symp + l * lstride, histp + l * hstride, lc, s);
         else
-            quantise_layer((const double*)c->coef.p, g, l, st, symp + l * lstride,
-                           (uint32_t*)c->hist.p + l * hstride, s);
+            quantise_layer((const double*)c->coef.p, g, l, st, symp + l * lstride, histp + l * hstride, s);
     }
     if (c->timing) cudaEventRecord(c->ev[2], s);
     CK(cudaGetLastError());
@@ -636,35 +645,68 @@ static int encode_slab_global(wrb_codec* c, const void* d_field, int dtype, int 
     const bool fused_fwd = !wtflag || slab_forward_all_fused(nx, ny, sg->nz_global, nzl, kWavLvl);
     if ((rc = ensure_transform_buffers(c, nx, ny, nzl, true, true, !fused_fwd, false, false))) return rc;
     if ((rc = ensure_coder_buffers(c, gr, nlayers, true, true, false))) return rc;         // the run lives in the exchange window
-    CK(c->hist.ensure((size_t)nlayers * std::max(gq.nblocks, gr.nblocks) * 256 * 4));      // the quantiser's (unused) local histograms too
+    // the coder blocks' histograms, then the quantiser's (unused) histograms of its local blocks
+    const unsigned long long hstride = (unsigned long long)gr.nblocks * 256;
+    CK(c->hist.ensure(((size_t)nlayers * hstride + (size_t)nlayers * gq.nblocks * 256) * 4));
+    uint32_t* const qhist = (uint32_t*)c->hist.p + (size_t)nlayers * hstride;
     const OrderGeom ogw = og;
     if ((rc = slab_windows(c, ogw, nlayers))) return rc;
     DevState* st = (DevState*)c->state.p;
     cudaStream_t s = c->stream;
-    if ((rc = run_transform_and_quantise(c, d_field, dtype, nx, ny, nzl, wtflag, tolrel, gq, sg, nlayers, (uint8_t*)c->xsym.p, c->xsym_stride))) return rc;
-    // every rank's symbol planes are complete; then my run comes straight out of the peers' windows (NVLink), lands in
-    // the coder's chunk-major layout and is histogrammed per coder block on the way
-    static const bool dbg = getenv("WRB_DEBUG_TIMING") != nullptr;         // development: split the exchange on stderr
-    cudaEvent_t de[4] = {nullptr, nullptr, nullptr, nullptr};
-    if (dbg) { for (auto& e : de) cudaEventCreate(&e); cudaEventRecord(de[0], s); }
-    if ((rc = slab_barrier(c))) return rc;
-    if (dbg) cudaEventRecord(de[1], s);
     // (the two windows serve both directions: `xsym` holds the rank's local symbol planes -- written by the quantiser
     //  here, by the exchange when decoding -- and `xrun` its run of the global sequence -- gathered here in the coder's
     //  chunk-major layout, written by the range decoder when decoding; no further symbol buffer exists in this mode)
     const unsigned long long lstride = c->xrun_stride;
-    const unsigned long long hstride = (unsigned long long)gr.nblocks * 256;
     uint8_t* const runp = (uint8_t*)c->xrun.p;
-    gather_global_run(og, rank, c->peer_xsym, c->xsym_stride, nlayers, st->active, gr, runp, lstride,
-                      (uint32_t*)c->hist.p, hstride, s, de[2]);
-    if (dbg) {
-        cudaEventRecord(de[3], s);
-        cudaEventSynchronize(de[3]);
-        float t[4];
-        for (int i = 0; i < 3; i++) cudaEventElapsedTime(&t[i], de[i], de[i + 1]);
-        cudaEventElapsedTime(&t[3], c->ev[1], de[0]);
-        fprintf(stderr, "[wrb rank %d] encode: quantise %.3f ms, barrier %.3f ms, gather %.3f ms, block histograms %.3f ms\n", rank, t[3], t[0], t[1], t[2]);
-        for (auto& e : de) cudaEventDestroy(e);
+    // My run of layer l comes straight out of the peers' windows (NVLink), lands in the coder's chunk-major layout and is
+    // histogrammed per coder block: one gather + one histogram launch per layer.
+    auto exchange_layer = [&](int l, cudaStream_t xs, cudaEvent_t mid) {
+        PeerPtrs pl = c->peer_xsym;
+        for (int r = 0; r < R; r++) pl.p[r] += (unsigned long long)l * c->xsym_stride;
+        gather_global_run(og, rank, pl, c->xsym_stride, 1, st->active + l, gr, runp + (unsigned long long)l * lstride, lstride,
+                          (uint32_t*)c->hist.p + (unsigned long long)l * hstride, hstride, xs, mid);
+    };
+    static const bool dbg = getenv("WRB_DEBUG_TIMING") != nullptr;         // development: split the exchange on stderr
+    const char* eo = getenv("WRB_SLAB_OVERLAP");                           // "0": exchange after the last layer (A/B timing)
+    const bool overlap = !dbg && !(eo && *eo == '0') && nlayers > 1;
+    if (overlap) {
+        // Layers 0 .. nlayers-2 are exchanged on a second stream while the next layer is quantised: the all-reduce of the
+        // residual extrema that opens layer l+1 is also the proof that layer l is complete on every rank.
+        if (!c->xchg_stream) CK(cudaStreamCreateWithFlags(&c->xchg_stream, cudaStreamNonBlocking));
+        for (auto& e : c->xchg_ev) if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        const std::function<int(int)> layer_complete = [&](int l) -> int {
+            CK(cudaEventRecord(c->xchg_ev[0], s));
+            CK(cudaStreamWaitEvent(c->xchg_stream, c->xchg_ev[0], 0));
+            exchange_layer(l, c->xchg_stream, nullptr);
+            return 0;
+        };
+        if ((rc = run_transform_and_quantise(c, d_field, dtype, nx, ny, nzl, wtflag, tolrel, gq, sg, nlayers, (uint8_t*)c->xsym.p,
+                                             c->xsym_stride, qhist, &layer_complete))) {
+            cudaStreamSynchronize(c->xchg_stream);
+            return rc;
+        }
+        if ((rc = slab_barrier(c))) { cudaStreamSynchronize(c->xchg_stream); return rc; }     // the last layer is complete everywhere
+        exchange_layer(nlayers - 1, s, nullptr);
+        CK(cudaEventRecord(c->xchg_ev[1], c->xchg_stream));
+        CK(cudaStreamWaitEvent(s, c->xchg_ev[1], 0));
+    } else {
+        if ((rc = run_transform_and_quantise(c, d_field, dtype, nx, ny, nzl, wtflag, tolrel, gq, sg, nlayers, (uint8_t*)c->xsym.p,
+                                             c->xsym_stride, qhist))) return rc;
+        cudaEvent_t de[4] = {nullptr, nullptr, nullptr, nullptr};
+        if (dbg) { for (auto& e : de) cudaEventCreate(&e); cudaEventRecord(de[0], s); }
+        if ((rc = slab_barrier(c))) return rc;                              // every rank's symbol planes are complete
+        if (dbg) cudaEventRecord(de[1], s);
+        gather_global_run(og, rank, c->peer_xsym, c->xsym_stride, nlayers, st->active, gr, runp, lstride,
+                          (uint32_t*)c->hist.p, hstride, s, de[2]);
+        if (dbg) {
+            cudaEventRecord(de[3], s);
+            cudaEventSynchronize(de[3]);
+            float t[4];
+            for (int i = 0; i < 3; i++) cudaEventElapsedTime(&t[i], de[i], de[i + 1]);
+            cudaEventElapsedTime(&t[3], c->ev[1], de[0]);
+            fprintf(stderr, "[wrb rank %d] encode: quantise %.3f ms, barrier %.3f ms, gather %.3f ms, block histograms %.3f ms\n", rank, t[3], t[0], t[1], t[2]);
+            for (auto& e : de) cudaEventDestroy(e);
+        }
     }
     if (c->timing) cudaEventRecord(c->ev[2], s);                        // "quantise" includes the exchange in this mode
     const unsigned long long sp = chunk_slot_pitch(gr);
