@@ -107,7 +107,7 @@ def test_slab_rejects_bad_partition(codec, torch_cuda):
 @pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("shape,tol,dtype", [((128, 64, 96), 1e-5, F64), ((128, 48, 40), 1e-9, F64), ((256, 40, 72), 1e-4, F32),
                                              ((128, 33, 50), 1e-6, F64), ((128, 24, 320), 1e-5, F64), ((128, 20, 264), 1e-3, F32)])
-def test_slab_global_symbol_order(torch_cuda, oracle, world, shape, tol, dtype):
+def test_slab_global_symbol_order(torch_cuda, oracle, world, shape, tol, dtype, monkeypatch):
     """SURVEY.md section 8e(3), inside the library (csrc/slab_order.cu): the ranks exchange the symbols and code whole
     chunks of the GLOBAL sequence.  Every chunk stream equals the oracle's range_encode of that chunk (= the single-GPU
     run's), the joined pieces are an ordinary container that the single-GPU decoder reads, and the slab decoder (run
@@ -116,6 +116,8 @@ def test_slab_global_symbol_order(torch_cuda, oracle, world, shape, tol, dtype):
     torch = torch_cuda
     from waverange_b200 import api, slab
     nz, ny, nx = shape
+    if ny == 40:                       # one shape per world also runs the overlapped exchange (off by default: no gain measured)
+        monkeypatch.setenv("WRB_SLAB_OVERLAP", "1")
     f = oracle.probe_field(shape, seed=77 + world, nm=16)
     if dtype == F32:
         f = f.astype(np.float32).astype(np.float64)

@@ -667,11 +667,13 @@ static int encode_slab_global(wrb_codec* c, const void* d_field, int dtype, int 
                           (uint32_t*)c->hist.p + (unsigned long long)l * hstride, hstride, xs, mid);
     };
     static const bool dbg = getenv("WRB_DEBUG_TIMING") != nullptr;         // development: split the exchange on stderr
-    const char* eo = getenv("WRB_SLAB_OVERLAP");                           // "0": exchange after the last layer (A/B timing)
-    const bool overlap = !dbg && !(eo && *eo == '0') && nlayers > 1;
+    // WRB_SLAB_OVERLAP=1: layers 0 .. nlayers-2 are exchanged on a second stream while the next layer is quantised (the
+    // all-reduce of the residual extrema that opens layer l+1 is also the proof that layer l is complete on every rank).
+    // Measured on 4 B200 (512 x 512 x 2048, profiles/r2_bench_512_n4_overlap_ab.txt): no gain -- the stage takes 1.91 ms
+    // instead of 1.76, the quantiser and the gather slow each other down by what the overlap saves -- so it is off.
+    const char* eo = getenv("WRB_SLAB_OVERLAP");
+    const bool overlap = !dbg && (eo && *eo == '1') && nlayers > 1;
     if (overlap) {
-        // Layers 0 .. nlayers-2 are exchanged on a second stream while the next layer is quantised: the all-reduce of the
-        // residual extrema that opens layer l+1 is also the proof that layer l is complete on every rank.
         if (!c->xchg_stream) CK(cudaStreamCreateWithFlags(&c->xchg_stream, cudaStreamNonBlocking));
         for (auto& e : c->xchg_ev) if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         const std::function<int(int)> layer_complete = [&](int l) -> int {

@@ -115,19 +115,29 @@ __device__ __forceinline__ uint32_t load4_unaligned(const uint8_t* src)
 // lane (the obvious way) move every sector five times; here a lane loads ONE aligned 16-byte vector, takes the next one
 // from its neighbour by shuffle (or loads it itself where the run ends) and shifts the pair in registers.
 // All 32 lanes must call it; `on` = this lane wants data.
-__device__ __forceinline__ uint4 warp_load16_unaligned(const uint8_t* src, bool on)
+// Two phases, so that a thread can have the vectors of several items in flight before it touches the first.
+struct Load16 { unsigned long long a; uint4 v; bool on; };
+__device__ __forceinline__ Load16 load16_issue(const uint8_t* src, bool on)
 {
-    const unsigned long long a = on ? (unsigned long long)src : 0ull;
+    Load16 l;
+    l.a = on ? (unsigned long long)src : 0ull;
+    l.on = on;
+    l.v = make_uint4(0, 0, 0, 0);
+    if (on) l.v = *reinterpret_cast<const uint4*>(l.a & ~15ull);
+    return l;
+}
+__device__ __forceinline__ uint4 load16_finish(const Load16& l)
+{
+    const unsigned long long a = l.a;
+    const uint4 v = l.v;
     const uint4* vp = reinterpret_cast<const uint4*>(a & ~15ull);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (on) v = *vp;
     // the neighbour's vector is my next one iff its aligned address is mine + 16
     const unsigned long long an = __shfl_down_sync(0xffffffffu, a & ~15ull, 1);
     uint4 n;
     n.x = __shfl_down_sync(0xffffffffu, v.x, 1); n.y = __shfl_down_sync(0xffffffffu, v.y, 1);
     n.z = __shfl_down_sync(0xffffffffu, v.z, 1); n.w = __shfl_down_sync(0xffffffffu, v.w, 1);
     const unsigned int s = (unsigned int)(a & 15ull);
-    const bool own = on && s != 0 && ((threadIdx.x & 31) == 31 || an != (a & ~15ull) + 16ull);
+    const bool own = l.on && s != 0 && ((threadIdx.x & 31) == 31 || an != (a & ~15ull) + 16ull);
     if (own) n = vp[1];
     // bytes [s, s + 16) of (v, n)
     const unsigned int ws = s >> 2, bs = (s & 3u) * 8u;
@@ -144,6 +154,7 @@ __device__ __forceinline__ uint4 warp_load16_unaligned(const uint8_t* src, bool 
     return make_uint4(__funnelshift_r(o[0], o[1], bs), __funnelshift_r(o[1], o[2], bs), __funnelshift_r(o[2], o[3], bs),
                       __funnelshift_r(o[3], o[4], bs));
 }
+__device__ __forceinline__ uint4 warp_load16_unaligned(const uint8_t* src, bool on) { return load16_finish(load16_issue(src, on)); }
 
 // ---- encode side -----------------------------------------------------------------------------------------------
 // Generic version (any shape; used for rows shorter than 256 symbols).  Pure copy kernel, grid (coder blocks of my run,
@@ -278,6 +289,7 @@ __global__ void __launch_bounds__(256) gather_run_kernel(OrderDev o, FastDiv dnx
         if (ky > 1) { if (x >= m1) s++; else { xe = m1; return s; } }
         return s;
     };
+    // (two items per thread and iteration, both loads in flight before the first is used, were measured on 4 B200: 10 % slower)
     for (unsigned int q0 = 0; q0 < bs; q0 += 16u * 256u) {            // warp-uniform trip count: the lanes shuffle
         const unsigned int q = q0 + 16u * tid;
         bool fast = false;
@@ -334,8 +346,13 @@ __global__ void __launch_bounds__(kHThreads) hist_blocks_kernel(const uint8_t* _
     const unsigned long long boff = (unsigned long long)kb * kBlock;
     const unsigned int bs = (clen - boff < kBlock) ? (unsigned int)(clen - boff) : kBlock;
     const uint8_t* __restrict__ in = sym + (unsigned long long)layer * lstride + (unsigned long long)c * g.pitch + boff;
+    // (the next vector is in flight while the sixteen counter updates of this one run: with 64 KiB of counters only three
+    //  CTAs share an SM, too few to hide the load otherwise -- r3 profile: 7.6 stall cycles per issue on it)
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    if (16u * tid < bs) nxt = *reinterpret_cast<const uint4*>(in + 16u * tid);      // chunks start 16-byte aligned, pitch slack covers the tail
     for (unsigned int q = 16u * tid; q < bs; q += 16u * kHThreads) {                  // <= 15 vectors = 240 symbols per thread
-        const uint4 v4 = *reinterpret_cast<const uint4*>(in + q);                    // chunks start 16-byte aligned, pitch slack covers the tail
+        const uint4 v4 = nxt;
+        if (q + 16u * kHThreads < bs) nxt = *reinterpret_cast<const uint4*>(in + q + 16u * kHThreads);
         const uint32_t vv[4] = {v4.x, v4.y, v4.z, v4.w};
         const unsigned int n = bs - q;
 #pragma unroll
@@ -381,6 +398,18 @@ void gather_global_run(const OrderGeom& og, int rank, const PeerPtrs& peer, unsi
     if (after_gather) cudaEventRecord(after_gather, s);
     hist_blocks_kernel<<<grid, kHThreads, kHHistBytes, s>>>(sym, sym_layer_stride, active, g, hist, hist_layer_stride);
     note_launch(2);
+}
+
+// segment of x in a row with ky segments (see gather_run_kernel), and the end of that segment
+__device__ __forceinline__ int row_segment(int x, int ky, int m1, int m2, int m3, int m4, int nx, int& xe)
+{
+    int s = 0;
+    xe = nx;
+    if (ky > 4) { if (x >= m4) s++; else { xe = m4; return s; } }
+    if (ky > 3) { if (x >= m3) s++; else { xe = m3; return s; } }
+    if (ky > 2) { if (x >= m2) s++; else { xe = m2; return s; } }
+    if (ky > 1) { if (x >= m1) s++; else { xe = m1; return s; } }
+    return s;
 }
 
 // ---- decode side -----------------------------------------------------------------------------------------------
@@ -443,13 +472,98 @@ __global__ void __launch_bounds__(256) scatter_local_kernel(OrderDev o, int rank
     }
 }
 
+// Fast version for rows of >= 256 symbols, as on the encode side: the generic kernel above runs ~350 instructions per
+// 16-byte item (region and owner searches, 64-bit index arithmetic; r3 profile: 281 M warp instructions, issue-bound at
+// 84 %).  Here the CTA first writes the source pointer of every (row, segment) it covers into shared memory -- a segment
+// is a run of one region, i.e. of one global plane, and almost always lies inside one rank's run -- and an item then costs
+// one multiply-shift, a few comparisons and one shared load.  Segments that straddle the end of a run keep the generic path.
+constexpr int kSSeg = 5;
+__global__ void __launch_bounds__(256) scatter_local_fast_kernel(OrderDev o, FastDiv dipr, int ipr, int rank, PeerPtrs peer,
+                                                                 unsigned long long peer_stride, uint8_t* __restrict__ out,
+                                                                 unsigned long long out_stride)
+{
+    __shared__ const uint8_t* s_src[kSRows * kSSeg];   // source of x = 0 of the row's segment (add x); null: generic path
+    __shared__ uint8_t s_ky[kSRows];
+    const int p = blockIdx.y, layer = blockIdx.z, tid = threadIdx.x;
+    const unsigned long long loff = (unsigned long long)layer * peer_stride;
+    const int y0 = blockIdx.x * kSRows;
+    const int nrows = min(kSRows, o.ny - y0);
+    const int L = o.levels;
+    if (tid < nrows * kSSeg) {
+        const int r = tid / kSSeg, sgm = tid - r * kSSeg;
+        const int y = y0 + r;
+        int ky = L + 1;
+        for (int k = L; k >= 1; k--) if (y >= o.my[k]) ky = k;
+        if (sgm == 0) s_ky[r] = (uint8_t)ky;
+        const uint8_t* src = nullptr;
+        if (sgm < ky) {
+            const int reg = (sgm == 0) ? ky : ky - sgm;
+            const int xb = (sgm == 0) ? 0 : o.mx[ky - sgm];
+            const int xe = (sgm + 1 < ky) ? o.mx[ky - sgm - 1] : o.nx;
+            const int w = order_plane(o, rank, p, reg);
+            const unsigned long long j = ((unsigned long long)w * o.ny + y) * o.nx + xb;
+            int d = 0;
+            while (d + 1 < o.nranks && j >= o.j0[d + 1]) d++;
+            if (o.j0[d + 1] - j >= (unsigned long long)(xe - xb)) src = peer.p[d] + loff + (j - o.j0[d]) - xb;
+        }
+        s_src[tid] = src;
+    }
+    __syncthreads();
+    const int m1 = o.mx[1], m2 = o.mx[2], m3 = o.mx[3], m4 = o.mx[4];
+    uint8_t* const obase = out + (unsigned long long)layer * out_stride + ((unsigned long long)p * o.ny + y0) * o.nx;
+    const int nitems = nrows * ipr;
+    struct Item { int ry, x; bool live, fast; const uint8_t* src; };
+    auto locate_item = [&](int it) -> Item {
+        Item m{0, 0, it < nitems, false, nullptr};
+        if (m.live) {
+            m.ry = (int)fdiv((uint32_t)it, dipr);
+            m.x = 16 * (it - m.ry * ipr);
+            int xe;
+            const int sgm = row_segment(m.x, s_ky[m.ry], m1, m2, m3, m4, o.nx, xe);
+            const uint8_t* s0 = s_src[m.ry * kSSeg + sgm];
+            m.fast = s0 != nullptr && m.x + 16 <= xe;
+            m.src = s0 + m.x;
+        }
+        return m;
+    };
+    auto finish_item = [&](const Item& m, const Load16& ld) {
+        const uint4 v = load16_finish(ld);
+        uint8_t* __restrict__ row = obase + (unsigned long long)m.ry * o.nx;
+        if (m.fast) { *reinterpret_cast<uint4*>(row + m.x) = v; return; }
+        if (!m.live) return;
+        const int y = y0 + m.ry;                                      // generic path, symbol by symbol
+        for (int e = m.x; e < m.x + 16 && e < o.nx; e++) {
+            const int reg = order_region(o, e, y);
+            const unsigned long long j = ((unsigned long long)order_plane(o, rank, p, reg) * o.ny + y) * o.nx + e;
+            int d = 0;
+            while (d + 1 < o.nranks && j >= o.j0[d + 1]) d++;
+            row[e] = *(peer.p[d] + loff + (j - o.j0[d]));
+        }
+    };
+    for (int it0 = 0; it0 < nitems; it0 += 512) {                     // warp-uniform trip count: the lanes shuffle; two items in flight
+        const Item a = locate_item(it0 + tid), b = locate_item(it0 + 256 + tid);
+        const Load16 la = load16_issue(a.src, a.fast), lb = load16_issue(b.src, b.fast);
+        finish_item(a, la);
+        finish_item(b, lb);
+    }
+}
+
 void scatter_local_planes(const OrderGeom& og, int rank, const PeerPtrs& peer, unsigned long long peer_stride, int nlay,
                           uint8_t* out, unsigned long long out_stride, cudaStream_t s)
 {
     if (nlay <= 0) return;
     const OrderDev o = make_dev(og);
     dim3 grid((og.ny + kSRows - 1) / kSRows, og.nzl, nlay);
-    scatter_local_kernel<<<grid, 256, 0, s>>>(o, rank, peer, peer_stride, out, out_stride);
+    const bool aligned = og.nx % 16 == 0 && (reinterpret_cast<size_t>(out) % 16) == 0 && out_stride % 16 == 0;
+    if (og.nx >= 256 && og.levels <= 4 && aligned) {
+        const uint32_t ipr = (uint32_t)og.nx / 16u;
+        uint32_t l2 = 0;
+        while ((1u << l2) < ipr) l2++;                                   // ceil(log2 ipr)
+        const FastDiv d{(uint32_t)(((1ull << (31 + l2)) + ipr - 1) / ipr), l2 - 1};
+        scatter_local_fast_kernel<<<grid, 256, 0, s>>>(o, d, (int)ipr, rank, peer, peer_stride, out, out_stride);
+    } else {
+        scatter_local_kernel<<<grid, 256, 0, s>>>(o, rank, peer, peer_stride, out, out_stride);
+    }
     note_launch(1);
 }
 
