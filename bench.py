@@ -345,6 +345,28 @@ def run_ours(args, rank, world, local_rank):
     wall_ms = (time.perf_counter() - t_wall0) * 1e3 / args.steps
     clocks = sampler.stop(t_region0, time.time()) if rank == 0 else None
 
+    # N > 1, for context only: the same steps in the rank-local symbol order (no symbol exchange; the pieces are then NOT
+    # the reference encoder's chunk streams of the whole field) -- what the global order costs
+    local_ms = float('nan')
+    if slab_mode and not args.no_check:
+        codec.set_slab_order(False)
+        for it in range(2):
+            hl = encode_dev(field.data_ptr(), blob.data_ptr())
+            decode_dev(recon.data_ptr(), hl, blob.data_ptr())
+        barrier()
+        le0, le1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        le0.record(stream)
+        for it in range(args.steps):
+            hl = encode_dev(field.data_ptr(), blob.data_ptr())
+            decode_dev(recon.data_ptr(), hl, blob.data_ptr())
+        le1.record(stream)
+        barrier()
+        local_ms = le0.elapsed_time(le1) / args.steps
+        codec.set_slab_order(True)
+        h = encode_dev(field.data_ptr(), blob.data_ptr())            # blob / recon back to the global-order result
+        decode_dev(recon.data_ptr(), h, blob.data_ptr())
+        barrier()
+
     # correctness guard inside the bench: the reconstruction meets the requested tolerance
     errt = torch.stack([(recon.view(n, n, n).double() - field.double()).abs().max(), field.double().abs().max()])
     if world > 1:
@@ -425,10 +447,10 @@ def run_ours(args, rank, world, local_rank):
         dist.barrier()
 
     # ---- max over ranks ------------------------------------------------------------------------
-    vals = torch.tensor([step_ms, statistics.mean(enc_ms), statistics.mean(dec_ms), e2e_step], device=dev, dtype=torch.float64)
+    vals = torch.tensor([step_ms, statistics.mean(enc_ms), statistics.mean(dec_ms), e2e_step, local_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    step_ms, enc_mean, dec_mean, e2e_step = [float(v) for v in vals.tolist()]
+    step_ms, enc_mean, dec_mean, e2e_step, local_ms = [float(v) for v in vals.tolist()]
     if rank != 0:
         return
 
@@ -502,6 +524,10 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "host_wall_ms_per_step": wall_ms,
     }
+    if local_ms == local_ms:
+        line["rank_local_order"] = {"value": world * 2 * nbytes / (local_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": local_ms,
+                                    "note": "same steps without the symbol exchange (round 1's mode): pieces are not the "
+                                            "reference's chunk streams of the whole field; not the headline"}
     if streams_equal is not None:
         line["global_order_check"] = streams_equal
         line["nccl_rank0"] = codec.comm_counters()
