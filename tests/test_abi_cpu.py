@@ -107,3 +107,21 @@ def test_reference_front_ends_link_against_the_library_and_refuse_to_run_without
     r = subprocess.run([exe, "data.bin", "data.wrb", "data.wrh", "2", "0", "1", "2", "16", "16", "16", "1e-6"], cwd=tmp_path,
                        capture_output=True, text=True, timeout=120)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_every_environment_switch_is_documented():
+    """Every WRB_* variable the library or its Python mirror reads is listed in INTEGRATION.md's table."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set()
+    for path in glob.glob(os.path.join(root, "waverange_b200", "csrc", "**", "*.*"), recursive=True) + \
+            glob.glob(os.path.join(root, "waverange_b200", "*.py")):
+        if path.endswith((".cu", ".cpp", ".cuh", ".h", ".py")):
+            text = open(path, errors="replace").read()
+            names.update(re.findall(r'getenv\("(WRB_[A-Z_0-9]+)"\)', text))
+            names.update(re.findall(r'environ(?:\.get)?[\(\[]\s*["\'](WRB_[A-Z_0-9]+)', text))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    assert names, "no switches found: the scan is broken"
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, "undocumented environment switches: %s" % missing
