@@ -115,30 +115,38 @@ __device__ __forceinline__ uint32_t load4_unaligned(const uint8_t* src)
 // lane (the obvious way) move every sector five times; here a lane loads ONE aligned 16-byte vector, takes the next one
 // from its neighbour by shuffle (or loads it itself where the run ends) and shifts the pair in registers.
 // All 32 lanes must call it; `on` = this lane wants data.
-// Two phases, so that a thread can have the vectors of several items in flight before it touches the first.
-struct Load16 { unsigned long long a; uint4 v; bool on; };
+// Two phases, so that a thread can have the vectors of several items in flight before it touches the first.  A lane at the
+// end of a contiguous run (no neighbour to take the next vector from) loads that vector itself, and it does so in the
+// SAME phase as its first one: whether it is a run end follows from the addresses alone.  (Issued after the shuffle of
+// the data, as a first version did, the second load cost every warp a second trip over NVLink -- with sub-band rows of
+// 256 symbols two lanes of every warp are run ends; tools/p2p_probe.cu: a plain copy kernel pulls 650-750 GB/s where the
+// exchange kernels reached 450.)  All 32 lanes must call both phases.
+struct Load16 { unsigned long long a; uint4 v, n2; bool on, own; };
 __device__ __forceinline__ Load16 load16_issue(const uint8_t* src, bool on)
 {
     Load16 l;
     l.a = on ? (unsigned long long)src : 0ull;
     l.on = on;
+    const unsigned long long base = l.a & ~15ull;
+    // the neighbour's vector is my next one iff its aligned address is mine + 16
+    const unsigned long long an = __shfl_down_sync(0xffffffffu, base, 1);
+    l.own = on && (l.a & 15ull) != 0 && ((threadIdx.x & 31) == 31 || an != base + 16ull);
+    const uint4* vp = reinterpret_cast<const uint4*>(base);
     l.v = make_uint4(0, 0, 0, 0);
-    if (on) l.v = *reinterpret_cast<const uint4*>(l.a & ~15ull);
+    l.n2 = make_uint4(0, 0, 0, 0);
+    if (on) l.v = vp[0];
+    if (l.own) l.n2 = vp[1];
     return l;
 }
 __device__ __forceinline__ uint4 load16_finish(const Load16& l)
 {
     const unsigned long long a = l.a;
     const uint4 v = l.v;
-    const uint4* vp = reinterpret_cast<const uint4*>(a & ~15ull);
-    // the neighbour's vector is my next one iff its aligned address is mine + 16
-    const unsigned long long an = __shfl_down_sync(0xffffffffu, a & ~15ull, 1);
     uint4 n;
     n.x = __shfl_down_sync(0xffffffffu, v.x, 1); n.y = __shfl_down_sync(0xffffffffu, v.y, 1);
     n.z = __shfl_down_sync(0xffffffffu, v.z, 1); n.w = __shfl_down_sync(0xffffffffu, v.w, 1);
+    if (l.own) n = l.n2;
     const unsigned int s = (unsigned int)(a & 15ull);
-    const bool own = l.on && s != 0 && ((threadIdx.x & 31) == 31 || an != (a & ~15ull) + 16ull);
-    if (own) n = vp[1];
     // bytes [s, s + 16) of (v, n)
     const unsigned int ws = s >> 2, bs = (s & 3u) * 8u;
     const uint32_t W[8] = {v.x, v.y, v.z, v.w, n.x, n.y, n.z, n.w};
